@@ -1,0 +1,81 @@
+"""Import shim for the UNMODIFIED reference (test infrastructure, container-only).
+
+TEST INFRASTRUCTURE — only `tests/`, `oracle/gen_golden.py`, `__graft_entry__.smoke()`
+and `bench.py`'s cpu_baseline / `--impl reference` leg may import anything under
+`oracle/`.  This particular module additionally needs `/root/reference`, which exists
+only in the build container (never on the GPU box), so nothing marked `gpu` uses it.
+
+The reference imports `gym` and `pygame` at module top
+(`/root/reference/envs/my_pong_env_2p.py:1-4`); neither is installed here.  `gym.Env`
+contributes nothing to the arithmetic (only `super().__init__()` / `super().reset(seed=)`
+at `:40,84`), and pygame is used by `render()` only, so two stub modules are enough to
+import `envs/` and `models/` unmodified.
+"""
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("PP_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "envs", "my_pong_env_2p.py"))
+
+
+def _install_stubs() -> None:
+    if "gym" not in sys.modules:
+        gym = types.ModuleType("gym")
+
+        class Env:  # what PongEnv2P needs from gym.Env
+            def reset(self, seed=None, options=None):
+                return None
+
+        class MultiDiscrete:
+            def __init__(self, nvec):
+                self.nvec = list(nvec)
+
+        class Box:
+            def __init__(self, low, high, dtype=None):
+                self.low, self.high, self.dtype = low, high, dtype
+                self.shape = low.shape
+
+        spaces = types.ModuleType("gym.spaces")
+        spaces.MultiDiscrete = MultiDiscrete
+        spaces.Box = Box
+        gym.Env = Env
+        gym.spaces = spaces
+        sys.modules["gym"] = gym
+        sys.modules["gym.spaces"] = spaces
+    if "pygame" not in sys.modules:
+        sys.modules["pygame"] = types.ModuleType("pygame")
+
+
+def load_reference():
+    """Returns (PongEnv2P, collide_sphere_with_moving_plane, QNet, QNetRNN) from the reference."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    _install_stubs()
+    # the reference's top-level packages are `envs` and `models`; this repo must not
+    # shadow them, so put the reference root FIRST for the duration of the import.
+    for name in ("envs", "envs.physics", "envs.my_pong_env_2p", "models", "models.qnet", "models.qnet_rnn"):
+        mod = sys.modules.get(name)
+        if mod is None:
+            continue
+        where = getattr(mod, "__file__", None) or next(iter(getattr(mod, "__path__", [])), "")
+        if not str(where).startswith(REFERENCE_ROOT):
+            del sys.modules[name]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        from envs.my_pong_env_2p import PongEnv2P
+        from envs.physics import collide_sphere_with_moving_plane
+        from models.qnet import QNet
+        from models.qnet_rnn import QNetRNN
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    return PongEnv2P, collide_sphere_with_moving_plane, QNet, QNetRNN
+
+
+def load_reference_config(name: str = "config.yaml") -> dict:
+    import yaml
+    with open(os.path.join(REFERENCE_ROOT, name), "r") as f:
+        return yaml.safe_load(f)

@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests must fail loudly, not skip, when the CUDA library cannot run; CPU runs never see them."""
+    from oracle import ref_shim
+    have_ref = ref_shim.reference_available()
+    for item in items:
+        if "reference" in item.keywords and not have_ref:
+            item.add_marker(pytest.mark.skip(reason="/root/reference not present on this machine"))
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
