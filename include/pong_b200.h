@@ -1,0 +1,220 @@
+/*
+ * pong_b200.h — C ABI of libpong_b200.so, the B200 (sm_100a) engine for the self-play hot path of
+ * MaxChen228/pingpong-selfplay-ai: N lock-step PongEnv2P environments stepped on the device with both
+ * paddles' actions chosen by QNet / QNetRNN on the device.
+ *
+ * The reference has no FFI (it is pure Python); each entry point below names the reference
+ * interface it replaces (file:line under /root/reference).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference adds to call them.
+ *
+ * Conventions
+ *   - plain C: raw pointers + sizes + a cudaStream_t passed as void*; no torch types.
+ *   - every function returns int: 0 ok, <0 bad argument (PP_E_*), >0 a cudaError_t value.
+ *     pp_last_error() gives a text for the calling thread's last non-zero return.
+ *   - pointers are DEVICE pointers unless the parameter is named host_* or the function is pp_host_*.
+ *   - functions never allocate and never synchronise (pp_host_* excepted: they own their staging
+ *     buffers and return after the result is in the host buffers).
+ *   - `mode` selects the arithmetic of the env state: PP_MODE_F64 reproduces the reference's
+ *     IEEE double arithmetic bit for bit (one rounding per Python operation, no FMA contraction);
+ *     PP_MODE_F32 is the same operation order in binary32.
+ *   - env state is SoA: one array of n reals per field, owned by the caller (torch tensors).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns a cudaError_t.
+ */
+#ifndef PONG_B200_H_
+#define PONG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+
+enum { PP_MODE_F64 = 0, PP_MODE_F32 = 1 };
+
+enum {
+    PP_OK = 0,
+    PP_E_NULL = -1,       /* required pointer is NULL         */
+    PP_E_SIZE = -2,       /* n / k / capacity out of range    */
+    PP_E_MODE = -3,       /* unknown mode / policy / precision */
+    PP_E_ALIGN = -4,      /* pointer not aligned as required  */
+    PP_E_PARAM = -5       /* inconsistent PPParams            */
+};
+
+/* Environment constants, precomputed on the host "the Python way" so that YAML ints
+ * (restitution: 1) and libm pow (R**2) behave as in the reference.
+ * Replaces the attributes stored by PongEnv2P.__init__  envs/my_pong_env_2p.py:19-62
+ * and the per-call constants of collide_sphere_with_moving_plane  envs/physics.py:7-11. */
+typedef struct PPParams {
+    double paddle_speed;        /* my_pong_env_2p.py:43                                   */
+    double half_width;          /* paddle_width / 2              :152-153,190-191        */
+    double magnus_factor;       /*                               :136                     */
+    double neg_e;               /* -restitution                  physics.py:7             */
+    double m_1pe;               /* m * (1 + e)                   physics.py:8             */
+    double inertia;             /* (2/5) * m * R**2              physics.py:9             */
+    double two_m_over_7;        /* 2*m/7.0                       physics.py:10            */
+    double mu;                  /* friction                      physics.py:11            */
+    double mass;                /* ball_mass                     physics.py:20            */
+    double radius;              /* world_ball_radius             physics.py:10,16,21      */
+    double speed_scale;         /* 1.0 + speed_increment         my_pong_env_2p.py:230    */
+    /* serve distribution (device-generated serves only)        my_pong_env_2p.py:98-111 */
+    double speed_lo, speed_hi;
+    double angle_lo[2], angle_hi[2];    /* degrees; interval 0 is taken when u < 0.5      */
+    double spin_lo, spin_hi;
+    int32_t enable_spin;
+    int32_t max_score;
+    int32_t speed_scale_every;
+    int32_t reserved;
+} PPParams;
+
+/* SoA state of n environments.  `real` = double (PP_MODE_F64) or float (PP_MODE_F32).
+ * Fields mirror the public attributes of PongEnv2P  envs/my_pong_env_2p.py:85-111. */
+typedef struct PPEnvState {
+    void *ball_x, *ball_y, *ball_vx, *ball_vy, *spin, *top_paddle_x, *bottom_paddle_x;   /* real[n]  */
+    int32_t *score_a, *score_b, *bounce_count;                                          /* int32[n] */
+    int32_t *ep_idx;    /* episodes this env has finished = index of its current serve; may be NULL for pp_env_step */
+    int32_t *ep_len;    /* steps taken in the current episode;                          may be NULL for pp_env_step */
+} PPEnvState;
+
+/* Where reset() takes (vx, vy, spin) from.  The reference draws them from CPython's global
+ * MT19937 (envs/my_pong_env_2p.py:98-111), which cannot be reproduced on the device:
+ *   PP_SERVE_POOL    host-generated queue, real[depth][n]; env i's j-th episode uses row j % depth
+ *   PP_SERVE_PHILOX  Philox4x32-10 keyed by (seed; global env id, episode index): same formula,
+ *                    distribution-equal, and independent of how envs are sharded over GPUs. */
+enum { PP_SERVE_POOL = 0, PP_SERVE_PHILOX = 1 };
+typedef struct PPServeSource {
+    int32_t kind;
+    int32_t depth;
+    const void *pool_vx, *pool_vy, *pool_spin;
+    uint64_t seed;
+} PPServeSource;
+
+/* A player.  Replaces the per-step `model(torch.tensor(obs).unsqueeze(0)).argmax(1).item()` of
+ * scripts/train_iterative.py:124-130,176-177,240 and select_action_universal tests/arena.py:199-219. */
+enum { PP_POLICY_QNET = 0, PP_POLICY_QNETRNN = 1, PP_POLICY_FOLLOWER = 2, PP_POLICY_RANDOM = 3 };
+enum { PP_PREC_F32 = 0,     /* CUDA-core fp32, fmaf chain in ascending k: bit-identical to the oracle  */
+       PP_PREC_BF16 = 1 };  /* tcgen05 bf16 tiles with fp32 accumulation in TMEM (QNet hidden layers)   */
+typedef struct PPPolicy {
+    int32_t kind;
+    int32_t precision;
+    uint64_t eps_threshold;     /* explore iff (uint64)philox.x < eps_threshold; floor(eps * 2^32), 0 = greedy */
+    float follower_tol;         /* tests/arena.py:213                                                       */
+    int32_t reserved;
+    const float *weights;       /* packed blob, see PP_QNET_* / PP_RNN_* offsets                            */
+    float *h, *c;               /* QNetRNN only: [n][128] each, zeroed by the engine at episode start       */
+} PPPolicy;
+
+/* QNet blob (floats): effective weights (eval: mu, train: mu + sigma*eps — models/qnet.py:43-50),
+ * transposed to k-major so a warp reads one weight row with broadcast 128-bit loads.
+ *   W1t[7][64]  b1[64]  W2t[64][64]  b2[64]  Wht[64][4] (col 0 = V, 1..3 = A)  bh[4] */
+enum {
+    PP_QNET_W1T = 0, PP_QNET_B1 = 448, PP_QNET_W2T = 512, PP_QNET_B2 = 4608,
+    PP_QNET_WHT = 4672, PP_QNET_BH = 4928, PP_QNET_BLOB_FLOATS = 4932
+};
+
+/* QNetRNN blob (floats), default dims 7-64-128 / LSTM 128 / head 128 (config_rnn.yaml:39-42):
+ *   Wf1t[7][64] bf1[64] Wf2t[64][128] bf2[128] Wgt[256][512] (rows 0..127 = W_ih^T, 128..255 = W_hh^T;
+ *   column = gate*128 + unit, gates i,f,g,o) bg[512] (= b_ih + b_hh) Wst[128][128] bs[128] Wht[128][4] bh[4] */
+enum {
+    PP_RNN_WF1T = 0, PP_RNN_BF1 = 448, PP_RNN_WF2T = 512, PP_RNN_BF2 = 8704, PP_RNN_WGT = 8832,
+    PP_RNN_BG = 139904, PP_RNN_WST = 140416, PP_RNN_BS = 156800, PP_RNN_WHT = 156928, PP_RNN_BH = 157440,
+    PP_RNN_BLOB_FLOATS = 157444
+};
+
+/* Per-call outputs of the multi-step kernels.  counters[8] (accumulated with atomics, never reset
+ * by the engine): 0 env-steps, 1 episodes, 2 wins A, 3 wins B, 4 points A, 5 points B,
+ * 6 paddle hits, 7 sum of finished-episode lengths.  ep_log[cap][4] = {global env id, ep_idx,
+ * scoreA<<16|scoreB, ep_len}; *ep_log_count counts every finished episode, also those beyond cap. */
+typedef struct PPRolloutOut {
+    unsigned long long *counters;
+    int32_t *ep_log;
+    int64_t ep_log_cap;
+    unsigned long long *ep_log_count;
+    uint8_t *actions_out;       /* [k][n][2] or NULL                                           */
+    void *trace_real;           /* real[k][7][n] post-step pre-reset state, or NULL            */
+    int32_t *trace_int;         /* int32[k][4][n] = scoreA, scoreB, bounce, flags, or NULL     */
+} PPRolloutOut;
+
+/* Replay ring of player B's transitions (oB, aB, rB, nB, done)  scripts/train_iterative.py:243;
+ * 62 bytes per row over five arrays; *head is a monotonically increasing write cursor. */
+typedef struct PPReplayRing {
+    float *obs;                 /* [capacity][7] */
+    uint8_t *act;               /* [capacity]    */
+    float *rew;                 /* [capacity]    */
+    float *next_obs;            /* [capacity][7] terminal obs on done, not the post-reset one */
+    uint8_t *done;              /* [capacity]    */
+    int64_t capacity;
+    unsigned long long *head;
+} PPReplayRing;
+
+int pp_version(void);
+const char *pp_last_error(void);
+
+/* PongEnv2P.step for n envs, all outputs materialised          envs/my_pong_env_2p.py:116-225,235-263
+ * obs [n][7] fp32, rewards fp32, done u8.  No reset. */
+int pp_env_step(int mode, int64_t n, const PPParams *params, const PPEnvState *state,
+                const uint8_t *action_a, const uint8_t *action_b,
+                float *obs_a, float *obs_b, float *reward_a, float *reward_b, uint8_t *done, void *stream);
+
+/* PongEnv2P._get_obs                                           envs/my_pong_env_2p.py:235-263 */
+int pp_env_observe(int mode, int64_t n, const PPEnvState *state, float *obs_a, float *obs_b, void *stream);
+
+/* PongEnv2P.reset with injected serves (vx, vy, spin real[n]) for envs whose mask byte is non-zero
+ * (mask NULL = all)                                            envs/my_pong_env_2p.py:83-114 */
+int pp_env_serve(int mode, int64_t n, const PPEnvState *state, const uint8_t *mask,
+                 const void *vx, const void *vy, const void *spin, void *stream);
+
+/* PongEnv2P.reset drawing from a PPServeSource; `advance` != 0 first increments ep_idx of the
+ * reset envs (the reference consumes one serve per reset() call). */
+int pp_env_reset(int mode, int64_t n, const PPParams *params, const PPEnvState *state, const uint8_t *mask,
+                 const PPServeSource *serve, int64_t env_id_base, int advance, void *stream);
+
+/* k lock-step steps with an injected action stream actions[k][n][2] and auto-reset; state stays in
+ * registers between steps.  An env whose ep_idx reached `quota` (> 0) is frozen.
+ * Replaces the `step(); if done: reset()` loop of scripts/train_iterative.py:174-179. */
+int pp_env_rollout(int mode, int64_t n, int64_t k, const PPParams *params, const PPEnvState *state,
+                   const uint8_t *actions, const PPServeSource *serve, int32_t quota, int64_t env_id_base,
+                   const PPRolloutOut *out, void *stream);
+
+/* obs[n][7] -> Q -> (epsilon-)greedy action for one player       models/qnet.py:71-75 +
+ * scripts/train_iterative.py:124-130.  q_out [n][3] may be NULL.  `stream_id` = 1 for player A, 2 for B. */
+int pp_qnet_act(int64_t n, const float *obs, const PPPolicy *policy, uint64_t seed, int64_t step_index,
+                int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out, void *stream);
+
+/* one QNetRNN step (seq_len 1) with carried per-env (h, c)        models/qnet_rnn.py:107-144.
+ * reset_mask (may be NULL): envs whose byte is non-zero get (h, c) = 0 BEFORE the step
+ * (init_hidden at episode start, tests/arena.py:298-299). */
+int pp_qnetrnn_act(int64_t n, const float *obs, const PPPolicy *policy, const uint8_t *reset_mask,
+                   uint64_t seed, int64_t step_index, int64_t env_id_base, int32_t stream_id,
+                   uint8_t *actions, float *q_out, void *stream);
+
+/* k fused lock-step iterations of {act A, act B, step, replay row, auto-reset}: the inner loops of
+ * scripts/train_iterative.py:171-196,238-245 and tests/arena.py:294-304.  Policies of kind QNET,
+ * FOLLOWER and RANDOM; observations never leave registers.  ring may be NULL. */
+int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, const PPEnvState *state,
+                        const PPPolicy *policy_a, const PPPolicy *policy_b, uint64_t seed, int64_t step_base,
+                        const PPServeSource *serve, int32_t quota, int64_t env_id_base,
+                        const PPRolloutOut *out, const PPReplayRing *ring, void *stream);
+
+/* memory.push for a batch: append rows whose valid byte is non-zero (NULL = all) to the ring,
+ * compacted with warp ballot + scan, one cursor atomic per warp   scripts/train_iterative.py:56-63,243 */
+int pp_replay_scatter(int64_t n, const PPReplayRing *ring, const float *obs, const uint8_t *act,
+                      const float *rew, const float *next_obs, const uint8_t *done, const uint8_t *valid,
+                      void *stream);
+
+/* Whole evaluation from HOST buffers (what a reference caller holds): eval_vs_model of
+ * scripts/train_iterative.py:171-181 for n envs x quota episodes each, QNet A vs QNet B.
+ * Copies serves and weights to the device, runs pp_selfplay_rollout in chunks of `chunk` steps until
+ * every env has finished its quota (or max_steps), copies counters[8] and per-episode records back.
+ * host_ep_log may be NULL.  Returns after the results are in the host buffers. */
+int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *params,
+                          const void *host_pool_vx, const void *host_pool_vy, const void *host_pool_spin,
+                          const float *host_weights_a, const float *host_weights_b, int32_t precision,
+                          int64_t chunk, int64_t max_steps,
+                          unsigned long long *host_counters, int32_t *host_ep_log, int64_t ep_log_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PONG_B200_H_ */

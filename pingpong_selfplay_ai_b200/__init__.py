@@ -1,0 +1,19 @@
+"""pingpong_selfplay_ai_b200 — B200-native batched self-play engine for the PongEnv2P hot path of
+MaxChen228/pingpong-selfplay-ai (envs/my_pong_env_2p.py + envs/physics.py stepped in lock step with both
+paddles' actions chosen by QNet / QNetRNN on the device).
+
+Host side: Python/PyTorch (buffers, streams, torch.distributed).  Compute: hand-written sm_100a CUDA in
+`csrc/`, reached through the C ABI of `include/pong_b200.h` (libpong_b200.so).  There is no CPU fallback.
+"""
+from . import _lib
+from ._lib import PongB200Error
+from .env import COUNTER_NAMES, PongEnv2P, ServePool, VecPongEnv2P
+from .params import ENV_DEFAULTS, make_params, resolve_env_config
+from .policy import NoisyLinear, Policy, QNet, QNetRNN, pack_qnet, pack_qnetrnn
+from .selfplay import ReplayRing, SelfPlayEngine, host_selfplay_eval, qnet_act, qnetrnn_act
+
+__all__ = [
+    "PongB200Error", "PongEnv2P", "VecPongEnv2P", "ServePool", "COUNTER_NAMES", "ENV_DEFAULTS", "make_params",
+    "resolve_env_config", "NoisyLinear", "QNet", "QNetRNN", "Policy", "pack_qnet", "pack_qnetrnn", "ReplayRing",
+    "SelfPlayEngine", "host_selfplay_eval", "qnet_act", "qnetrnn_act",
+]

@@ -1,0 +1,260 @@
+// capi.cu — the extern "C" surface declared in include/pong_b200.h: argument validation, error text,
+// and the HOST-buffer evaluation entry (pp_host_selfplay_eval).  No kernel code lives here.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "pp_host.h"
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char *what) {
+    if (code > 0) snprintf(g_err, sizeof g_err, "%s: CUDA error %d (%s)", what, code, cudaGetErrorString((cudaError_t)code));
+    else snprintf(g_err, sizeof g_err, "%s: bad argument (%d)", what, code);
+    return code;
+}
+int ok_or(int cuda_code, const char *what) { return cuda_code == 0 ? 0 : fail(cuda_code, what); }
+
+bool mode_ok(int mode) { return mode == PP_MODE_F64 || mode == PP_MODE_F32; }
+bool state_ok(const PPEnvState *s, bool need_ep) {
+    if (!s) return false;
+    const void *p[] = {s->ball_x, s->ball_y, s->ball_vx, s->ball_vy, s->spin, s->top_paddle_x, s->bottom_paddle_x,
+                       s->score_a, s->score_b, s->bounce_count};
+    for (const void *q : p) if (!q) return false;
+    return !need_ep || (s->ep_idx && s->ep_len);
+}
+bool params_ok(const PPParams *p) { return p && p->speed_scale_every > 0 && p->max_score > 0; }
+bool serve_ok(const PPServeSource *s) {
+    if (!s) return false;
+    if (s->kind == PP_SERVE_POOL) return s->depth > 0 && s->pool_vx && s->pool_vy && s->pool_spin;
+    return s->kind == PP_SERVE_PHILOX;
+}
+bool policy_ok(const PPPolicy *p, bool allow_rnn) {
+    if (!p) return false;
+    switch (p->kind) {
+        case PP_POLICY_QNET: return p->weights && (reinterpret_cast<uintptr_t>(p->weights) & 15u) == 0;
+        case PP_POLICY_QNETRNN: return allow_rnn && p->weights && p->h && p->c && (reinterpret_cast<uintptr_t>(p->weights) & 15u) == 0;
+        case PP_POLICY_FOLLOWER:
+        case PP_POLICY_RANDOM: return true;
+        default: return false;
+    }
+}
+bool out_ok(const PPRolloutOut *o) {
+    if (!o) return false;
+    if (o->ep_log && (!o->ep_log_count || o->ep_log_cap < 0 || (reinterpret_cast<uintptr_t>(o->ep_log) & 15u))) return false;
+    if (o->actions_out && (reinterpret_cast<uintptr_t>(o->actions_out) & 1u)) return false;
+    return true;
+}
+bool ring_ok(const PPReplayRing *r) {
+    return r && r->obs && r->act && r->rew && r->next_obs && r->done && r->head && r->capacity > 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pp_version(void) { return PP_ABI_VERSION; }
+const char *pp_last_error(void) { return g_err; }
+
+int pp_env_step(int mode, int64_t n, const PPParams *params, const PPEnvState *state, const uint8_t *action_a,
+                const uint8_t *action_b, float *obs_a, float *obs_b, float *reward_a, float *reward_b, uint8_t *done,
+                void *stream) {
+    if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_env_step");
+    if (n < 0 || n > (int64_t)1 << 40) return fail(PP_E_SIZE, "pp_env_step");
+    if (!params_ok(params)) return fail(PP_E_PARAM, "pp_env_step");
+    if (!state_ok(state, false) || !action_a || !action_b || !obs_a || !obs_b || !reward_a || !reward_b || !done)
+        return fail(PP_E_NULL, "pp_env_step");
+    if (n == 0) return 0;
+    return ok_or(pp::env_step_launch(mode, n, *params, *state, action_a, action_b, obs_a, obs_b, reward_a, reward_b, done,
+                                     (cudaStream_t)stream), "pp_env_step");
+}
+
+int pp_env_observe(int mode, int64_t n, const PPEnvState *state, float *obs_a, float *obs_b, void *stream) {
+    if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_env_observe");
+    if (n < 0) return fail(PP_E_SIZE, "pp_env_observe");
+    if (!state_ok(state, false) || !obs_a || !obs_b) return fail(PP_E_NULL, "pp_env_observe");
+    if (n == 0) return 0;
+    return ok_or(pp::env_observe_launch(mode, n, *state, obs_a, obs_b, (cudaStream_t)stream), "pp_env_observe");
+}
+
+int pp_env_serve(int mode, int64_t n, const PPEnvState *state, const uint8_t *mask, const void *vx, const void *vy,
+                 const void *spin, void *stream) {
+    if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_env_serve");
+    if (n < 0) return fail(PP_E_SIZE, "pp_env_serve");
+    if (!state_ok(state, false) || !vx || !vy || !spin) return fail(PP_E_NULL, "pp_env_serve");
+    if (n == 0) return 0;
+    return ok_or(pp::env_serve_launch(mode, n, *state, mask, vx, vy, spin, (cudaStream_t)stream), "pp_env_serve");
+}
+
+int pp_env_reset(int mode, int64_t n, const PPParams *params, const PPEnvState *state, const uint8_t *mask,
+                 const PPServeSource *serve, int64_t env_id_base, int advance, void *stream) {
+    if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_env_reset");
+    if (n < 0) return fail(PP_E_SIZE, "pp_env_reset");
+    if (!params_ok(params)) return fail(PP_E_PARAM, "pp_env_reset");
+    if (!state_ok(state, true) || !serve_ok(serve)) return fail(PP_E_NULL, "pp_env_reset");
+    if (n == 0) return 0;
+    return ok_or(pp::env_reset_launch(mode, n, *params, *state, mask, *serve, env_id_base, advance, (cudaStream_t)stream),
+                 "pp_env_reset");
+}
+
+int pp_env_rollout(int mode, int64_t n, int64_t k, const PPParams *params, const PPEnvState *state, const uint8_t *actions,
+                   const PPServeSource *serve, int32_t quota, int64_t env_id_base, const PPRolloutOut *out, void *stream) {
+    if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_env_rollout");
+    if (n < 0 || k < 0) return fail(PP_E_SIZE, "pp_env_rollout");
+    if (!params_ok(params)) return fail(PP_E_PARAM, "pp_env_rollout");
+    if (!state_ok(state, true) || !actions || !serve_ok(serve) || !out_ok(out)) return fail(PP_E_NULL, "pp_env_rollout");
+    if (reinterpret_cast<uintptr_t>(actions) & 1u) return fail(PP_E_ALIGN, "pp_env_rollout");
+    if (n == 0 || k == 0) return 0;
+    return ok_or(pp::env_rollout_launch(mode, n, k, *params, *state, actions, *serve, quota, env_id_base, *out,
+                                        (cudaStream_t)stream), "pp_env_rollout");
+}
+
+int pp_qnet_act(int64_t n, const float *obs, const PPPolicy *policy, uint64_t seed, int64_t step_index,
+                int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out, void *stream) {
+    if (n < 0) return fail(PP_E_SIZE, "pp_qnet_act");
+    if (!obs || !actions) return fail(PP_E_NULL, "pp_qnet_act");
+    if (!policy_ok(policy, false)) return fail(PP_E_MODE, "pp_qnet_act");
+    if (policy->precision != PP_PREC_F32) return fail(PP_E_MODE, "pp_qnet_act");
+    if (n == 0) return 0;
+    return ok_or(pp::qnet_act_launch(n, obs, *policy, seed, step_index, env_id_base, stream_id, actions, q_out,
+                                     (cudaStream_t)stream), "pp_qnet_act");
+}
+
+int pp_qnetrnn_act(int64_t n, const float *obs, const PPPolicy *policy, const uint8_t *reset_mask, uint64_t seed,
+                   int64_t step_index, int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out, void *stream) {
+    if (n < 0) return fail(PP_E_SIZE, "pp_qnetrnn_act");
+    if (!obs || !actions) return fail(PP_E_NULL, "pp_qnetrnn_act");
+    if (!policy_ok(policy, true) || policy->kind != PP_POLICY_QNETRNN || policy->precision != PP_PREC_F32)
+        return fail(PP_E_MODE, "pp_qnetrnn_act");
+    if (n == 0) return 0;
+    return ok_or(pp::qnetrnn_act_launch(n, obs, *policy, reset_mask, seed, step_index, env_id_base, stream_id, actions,
+                                        q_out, (cudaStream_t)stream), "pp_qnetrnn_act");
+}
+
+int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, const PPEnvState *state,
+                        const PPPolicy *policy_a, const PPPolicy *policy_b, uint64_t seed, int64_t step_base,
+                        const PPServeSource *serve, int32_t quota, int64_t env_id_base, const PPRolloutOut *out,
+                        const PPReplayRing *ring, void *stream) {
+    if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_selfplay_rollout");
+    if (n < 0 || k < 0) return fail(PP_E_SIZE, "pp_selfplay_rollout");
+    if (!params_ok(params)) return fail(PP_E_PARAM, "pp_selfplay_rollout");
+    if (!state_ok(state, true) || !serve_ok(serve) || !out_ok(out)) return fail(PP_E_NULL, "pp_selfplay_rollout");
+    if (!policy_ok(policy_a, false) || !policy_ok(policy_b, false)) return fail(PP_E_MODE, "pp_selfplay_rollout");
+    if (policy_a->precision != PP_PREC_F32 || policy_b->precision != PP_PREC_F32) return fail(PP_E_MODE, "pp_selfplay_rollout");
+    if (ring && !ring_ok(ring)) return fail(PP_E_NULL, "pp_selfplay_rollout");
+    if (n == 0 || k == 0) return 0;
+    return ok_or(pp::selfplay_launch(mode, n, k, *params, *state, *policy_a, *policy_b, seed, step_base, *serve, quota,
+                                     env_id_base, *out, ring, (cudaStream_t)stream), "pp_selfplay_rollout");
+}
+
+int pp_replay_scatter(int64_t n, const PPReplayRing *ring, const float *obs, const uint8_t *act, const float *rew,
+                      const float *next_obs, const uint8_t *done, const uint8_t *valid, void *stream) {
+    if (n < 0) return fail(PP_E_SIZE, "pp_replay_scatter");
+    if (!ring_ok(ring) || !obs || !act || !rew || !next_obs || !done) return fail(PP_E_NULL, "pp_replay_scatter");
+    if (n == 0) return 0;
+    return ok_or(pp::replay_scatter_launch(n, *ring, obs, act, rew, next_obs, done, valid, (cudaStream_t)stream),
+                 "pp_replay_scatter");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer evaluation.  Owns a small cache of device staging buffers (grown on demand, freed at
+// process exit) so repeated calls do not pay cudaMalloc; everything runs on one private stream.
+namespace {
+struct HostEvalCache {
+    cudaStream_t stream = nullptr;
+    void *dev = nullptr;
+    size_t dev_bytes = 0;
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+HostEvalCache g_cache;
+
+int ensure(HostEvalCache &c, size_t dev_bytes, size_t pinned_bytes) {
+    cudaError_t e;
+    if (!c.stream && (e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+    if (dev_bytes > c.dev_bytes) {
+        if (c.dev) cudaFree(c.dev);
+        c.dev = nullptr; c.dev_bytes = 0;
+        if ((e = cudaMalloc(&c.dev, dev_bytes)) != cudaSuccess) return (int)e;
+        c.dev_bytes = dev_bytes;
+    }
+    if (pinned_bytes > c.pinned_bytes) {
+        if (c.pinned) cudaFreeHost(c.pinned);
+        c.pinned = nullptr; c.pinned_bytes = 0;
+        if ((e = cudaMallocHost(&c.pinned, pinned_bytes)) != cudaSuccess) return (int)e;
+        c.pinned_bytes = pinned_bytes;
+    }
+    return 0;
+}
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+}  // namespace
+
+int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *params, const void *host_pool_vx,
+                          const void *host_pool_vy, const void *host_pool_spin, const float *host_weights_a,
+                          const float *host_weights_b, int32_t precision, int64_t chunk, int64_t max_steps,
+                          unsigned long long *host_counters, int32_t *host_ep_log, int64_t ep_log_cap) {
+    const char *fn = "pp_host_selfplay_eval";
+    if (!mode_ok(mode) || precision != PP_PREC_F32) return fail(PP_E_MODE, fn);
+    if (n <= 0 || quota <= 0 || chunk <= 0 || max_steps <= 0 || ep_log_cap < 0) return fail(PP_E_SIZE, fn);
+    if (!params_ok(params)) return fail(PP_E_PARAM, fn);
+    if (!host_pool_vx || !host_pool_vy || !host_pool_spin || !host_weights_a || !host_weights_b || !host_counters)
+        return fail(PP_E_NULL, fn);
+    const size_t rs = mode == PP_MODE_F64 ? 8 : 4;
+    const size_t pool_bytes = align_up((size_t)quota * n * rs, 256);
+    const size_t real_bytes = align_up((size_t)n * rs, 256), int_bytes = align_up((size_t)n * 4, 256);
+    const size_t blob_bytes = align_up(PP_QNET_BLOB_FLOATS * sizeof(float), 256);
+    const size_t log_bytes = align_up((size_t)(host_ep_log ? ep_log_cap : 0) * 16, 256);
+    const size_t dev_bytes = 3 * pool_bytes + 7 * real_bytes + 5 * int_bytes + 2 * blob_bytes + 256 + log_bytes;
+    int rc = ensure(g_cache, dev_bytes, 256);
+    if (rc) return fail(rc, fn);
+    cudaStream_t st = g_cache.stream;
+    char *d = (char *)g_cache.dev;
+    auto take = [&](size_t b) { char *p = d; d += b; return (void *)p; };
+    void *pvx = take(pool_bytes), *pvy = take(pool_bytes), *psp = take(pool_bytes);
+    PPEnvState es{};
+    es.ball_x = take(real_bytes); es.ball_y = take(real_bytes); es.ball_vx = take(real_bytes); es.ball_vy = take(real_bytes);
+    es.spin = take(real_bytes); es.top_paddle_x = take(real_bytes); es.bottom_paddle_x = take(real_bytes);
+    es.score_a = (int32_t *)take(int_bytes); es.score_b = (int32_t *)take(int_bytes); es.bounce_count = (int32_t *)take(int_bytes);
+    es.ep_idx = (int32_t *)take(int_bytes); es.ep_len = (int32_t *)take(int_bytes);
+    float *wa = (float *)take(blob_bytes), *wb = (float *)take(blob_bytes);
+    unsigned long long *ctr = (unsigned long long *)take(256);          // counters[8] + ep_log_count
+    int32_t *dlog = host_ep_log ? (int32_t *)take(log_bytes) : nullptr;
+
+    cudaError_t e;
+#define CK(x) do { if ((e = (x)) != cudaSuccess) return fail((int)e, fn); } while (0)
+    CK(cudaMemcpyAsync(pvx, host_pool_vx, (size_t)quota * n * rs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pvy, host_pool_vy, (size_t)quota * n * rs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(psp, host_pool_spin, (size_t)quota * n * rs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(wa, host_weights_a, PP_QNET_BLOB_FLOATS * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(wb, host_weights_b, PP_QNET_BLOB_FLOATS * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctr, 0, 256, st));
+    CK(cudaMemsetAsync(es.ep_idx, 0, (size_t)n * 4, st));
+    PPServeSource src{PP_SERVE_POOL, quota, pvx, pvy, psp, 0};
+    rc = pp::env_reset_launch(mode, n, *params, es, nullptr, src, 0, /*advance=*/0, st);     // serve 0 of every env
+    if (rc) return fail(rc, fn);
+    PPPolicy pa{PP_POLICY_QNET, PP_PREC_F32, 0, 0.f, 0, wa, nullptr, nullptr};
+    PPPolicy pb{PP_POLICY_QNET, PP_PREC_F32, 0, 0.f, 0, wb, nullptr, nullptr};
+    PPRolloutOut out{ctr, dlog, host_ep_log ? ep_log_cap : 0, ctr + 8, nullptr, nullptr, nullptr};
+    unsigned long long *h = (unsigned long long *)g_cache.pinned;
+    const unsigned long long want = (unsigned long long)n * (unsigned long long)quota;
+    for (int64_t done_steps = 0; done_steps < max_steps; done_steps += chunk) {
+        const int64_t k = (max_steps - done_steps) < chunk ? (max_steps - done_steps) : chunk;
+        rc = pp::selfplay_launch(mode, n, k, *params, es, pa, pb, 0, done_steps, src, quota, 0, out, nullptr, st);
+        if (rc) return fail(rc, fn);
+        CK(cudaMemcpyAsync(h, ctr, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h[1] >= want) break;                     // every env has played its quota
+    }
+    memcpy(host_counters, h, 8 * sizeof(unsigned long long));
+    if (host_ep_log) {
+        const unsigned long long rows = h[8] < (unsigned long long)ep_log_cap ? h[8] : (unsigned long long)ep_log_cap;
+        CK(cudaMemcpyAsync(host_ep_log, dlog, rows * 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+#undef CK
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// pp_host.h — launchers behind the C ABI (one per kernel family); all return a cudaError_t as int.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pong_b200.h"
+
+namespace pp {
+
+int env_step_launch(int mode, int64_t n, const PPParams &p, const PPEnvState &st, const uint8_t *aa, const uint8_t *ab,
+                    float *oa, float *ob, float *ra, float *rb, uint8_t *dn, cudaStream_t stream);
+int env_observe_launch(int mode, int64_t n, const PPEnvState &st, float *oa, float *ob, cudaStream_t stream);
+int env_serve_launch(int mode, int64_t n, const PPEnvState &st, const uint8_t *mask, const void *vx, const void *vy,
+                     const void *spin, cudaStream_t stream);
+int env_reset_launch(int mode, int64_t n, const PPParams &p, const PPEnvState &st, const uint8_t *mask,
+                     const PPServeSource &src, int64_t env_id_base, int advance, cudaStream_t stream);
+int env_rollout_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const uint8_t *actions,
+                       const PPServeSource &src, int32_t quota, int64_t env_id_base, const PPRolloutOut &out,
+                       cudaStream_t stream);
+
+int qnet_act_launch(int64_t n, const float *obs, const PPPolicy &pol, uint64_t seed, int64_t step_index,
+                    int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out, cudaStream_t stream);
+int qnetrnn_act_launch(int64_t n, const float *obs, const PPPolicy &pol, const uint8_t *reset_mask, uint64_t seed,
+                       int64_t step_index, int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out,
+                       cudaStream_t stream);
+int selfplay_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
+                    const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
+                    int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream);
+int replay_scatter_launch(int64_t n, const PPReplayRing &ring, const float *obs, const uint8_t *act, const float *rew,
+                          const float *next_obs, const uint8_t *done, const uint8_t *valid, cudaStream_t stream);
+
+}  // namespace pp

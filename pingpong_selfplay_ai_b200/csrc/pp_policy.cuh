@@ -1,0 +1,102 @@
+// pp_policy.cuh — per-env action selection on CUDA cores (PP_PREC_F32).
+//
+// QNet (models/qnet.py:52-75): 7 -> 64 -> 64 -> dueling (V 1, A 3).  One env per thread; the packed
+// k-major weight blob (PP_QNET_* offsets, 19.7 KB) lives in shared memory and every lane of a warp
+// reads the same weight row, so each LDS.128 is a 4-weight broadcast feeding 4 FFMAs.
+// Accumulation order is DEFINED: acc = bias; acc = fmaf(W[j][k], x[k], acc) for k ascending — the C
+// oracle (oracle/pong_oracle.c: dense()) executes the same chain, so Q-values and therefore greedy
+// actions are bit-identical to the oracle, which in turn is within 1e-5 of torch.
+#pragma once
+#include "pp_device.cuh"
+
+namespace pp {
+
+__device__ __forceinline__ float relu(float v) { return v > 0.0f ? v : 0.0f; }
+
+// sw: blob in shared memory (16-byte aligned).  q[3] out.
+__device__ __forceinline__ void qnet_forward(const float *__restrict__ sw, const float (&obs)[7], float (&q)[3]) {
+    float h1[64];
+    {
+        const float4 *w1 = reinterpret_cast<const float4 *>(sw + PP_QNET_W1T);
+        const float4 *b1 = reinterpret_cast<const float4 *>(sw + PP_QNET_B1);
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4) {
+            float4 acc = b1[j4];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const float4 w = w1[k * 16 + j4];
+                acc.x = fmaf(w.x, obs[k], acc.x); acc.y = fmaf(w.y, obs[k], acc.y);
+                acc.z = fmaf(w.z, obs[k], acc.z); acc.w = fmaf(w.w, obs[k], acc.w);
+            }
+            h1[j4 * 4 + 0] = relu(acc.x); h1[j4 * 4 + 1] = relu(acc.y);
+            h1[j4 * 4 + 2] = relu(acc.z); h1[j4 * 4 + 3] = relu(acc.w);
+        }
+    }
+    float4 head = *reinterpret_cast<const float4 *>(sw + PP_QNET_BH);      // (V, A0, A1, A2) accumulators
+    const float4 *w2 = reinterpret_cast<const float4 *>(sw + PP_QNET_W2T);
+    const float4 *b2 = reinterpret_cast<const float4 *>(sw + PP_QNET_B2);
+    const float4 *wh = reinterpret_cast<const float4 *>(sw + PP_QNET_WHT);
+#pragma unroll 1
+    for (int jb = 0; jb < 4; ++jb) {              // 16 hidden units per pass keeps the live set ~100 registers
+        float4 a0 = b2[jb * 4 + 0], a1 = b2[jb * 4 + 1], a2 = b2[jb * 4 + 2], a3 = b2[jb * 4 + 3];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const float x = h1[k];
+            const float4 u0 = w2[k * 16 + jb * 4 + 0], u1 = w2[k * 16 + jb * 4 + 1];
+            const float4 u2 = w2[k * 16 + jb * 4 + 2], u3 = w2[k * 16 + jb * 4 + 3];
+            a0.x = fmaf(u0.x, x, a0.x); a0.y = fmaf(u0.y, x, a0.y); a0.z = fmaf(u0.z, x, a0.z); a0.w = fmaf(u0.w, x, a0.w);
+            a1.x = fmaf(u1.x, x, a1.x); a1.y = fmaf(u1.y, x, a1.y); a1.z = fmaf(u1.z, x, a1.z); a1.w = fmaf(u1.w, x, a1.w);
+            a2.x = fmaf(u2.x, x, a2.x); a2.y = fmaf(u2.y, x, a2.y); a2.z = fmaf(u2.z, x, a2.z); a2.w = fmaf(u2.w, x, a2.w);
+            a3.x = fmaf(u3.x, x, a3.x); a3.y = fmaf(u3.y, x, a3.y); a3.z = fmaf(u3.z, x, a3.z); a3.w = fmaf(u3.w, x, a3.w);
+        }
+        const float h2[16] = {relu(a0.x), relu(a0.y), relu(a0.z), relu(a0.w), relu(a1.x), relu(a1.y), relu(a1.z), relu(a1.w),
+                              relu(a2.x), relu(a2.y), relu(a2.z), relu(a2.w), relu(a3.x), relu(a3.y), relu(a3.z), relu(a3.w)};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {            // heads accumulate in ascending hidden index, like the oracle
+            const float4 w = wh[jb * 16 + i];
+            head.x = fmaf(w.x, h2[i], head.x); head.y = fmaf(w.y, h2[i], head.y);
+            head.z = fmaf(w.z, h2[i], head.z); head.w = fmaf(w.w, h2[i], head.w);
+        }
+    }
+    // V + (A - mean(A))                                                       models/qnet.py:75
+    const float mean = __fdiv_rn(__fadd_rn(__fadd_rn(head.y, head.z), head.w), 3.0f);
+    q[0] = __fadd_rn(head.x, __fsub_rn(head.y, mean));
+    q[1] = __fadd_rn(head.x, __fsub_rn(head.z, mean));
+    q[2] = __fadd_rn(head.x, __fsub_rn(head.w, mean));
+}
+
+__device__ __forceinline__ int argmax3(const float (&q)[3]) {     // first maximum wins (torch.argmax)
+    int best = 0;
+    float m = q[0];
+    if (q[1] > m) { best = 1; m = q[1]; }
+    if (q[2] > m) { best = 2; }
+    return best;
+}
+
+// HardcodedBallFollower                                                      tests/arena.py:211-217
+__device__ __forceinline__ int follower_action(const float (&obs)[7], float tol) {
+    const float lo = __fsub_rn(obs[4], tol), hi = __fadd_rn(obs[4], tol);
+    return obs[0] < lo ? 0 : (obs[0] > hi ? 2 : 1);
+}
+
+// epsilon-greedy overlay                                        scripts/train_iterative.py:124-130
+__device__ __forceinline__ int explore(int greedy, uint64_t eps_threshold, uint64_t seed, uint32_t env_id, uint32_t step,
+                                       uint32_t stream_id) {
+    if (eps_threshold == 0) return greedy;
+    const uint4 r = philox4x32_10(env_id, step, stream_id, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return ((uint64_t)r.x < eps_threshold) ? (int)(((uint64_t)r.y * 3u) >> 32) : greedy;
+}
+
+__device__ __forceinline__ int random_action(uint64_t seed, uint32_t env_id, uint32_t step, uint32_t stream_id) {
+    const uint4 r = philox4x32_10(env_id, step, stream_id, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return (int)(((uint64_t)r.y * 3u) >> 32);
+}
+
+// cooperative copy of a blob into shared memory (n_floats % 4 == 0, both 16-byte aligned)
+__device__ __forceinline__ void stage_blob(float *dst, const float *__restrict__ src, int n_floats) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    for (int i = threadIdx.x; i < n_floats / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+}  // namespace pp

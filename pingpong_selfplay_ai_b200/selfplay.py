@@ -1,0 +1,151 @@
+"""Self-play drivers: the lock-step form of the reference's per-step loops.
+
+    reference loop                                              here
+    scripts/train_iterative.py:171-181  eval_vs_model           SelfPlayEngine.evaluate / host_selfplay_eval
+    scripts/train_iterative.py:238-245  epsilon-greedy rollout  SelfPlayEngine.run(..., ring=ReplayRing)
+    tests/arena.py:294-304              match loop              SelfPlayEngine.evaluate (QNet / follower / random)
+    per-step model(obs).argmax(1)       :124-130,176-177        qnet_act / qnetrnn_act
+
+Everything numeric happens in libpong_b200.so; this file sequences launches and owns buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .env import COUNTER_NAMES, VecPongEnv2P, _ptr, _stream_ptr
+from .params import make_params, resolve_env_config
+from .policy import Policy
+
+
+class ReplayRing:
+    """Device replay ring of player B's transitions (oB, aB, rB, nB, done): 62 bytes per row over five arrays
+    (scripts/train_iterative.py:49-63,243).  `head` counts every row ever written; slot = head % capacity."""
+
+    def __init__(self, capacity: int, device="cuda"):
+        dev = torch.device(device)
+        self.capacity = int(capacity)
+        self.obs = torch.zeros(capacity, 7, dtype=torch.float32, device=dev)
+        self.act = torch.zeros(capacity, dtype=torch.uint8, device=dev)
+        self.rew = torch.zeros(capacity, dtype=torch.float32, device=dev)
+        self.next_obs = torch.zeros(capacity, 7, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(capacity, dtype=torch.uint8, device=dev)
+        self.head = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def struct(self) -> _lib.PPReplayRing:
+        return _lib.PPReplayRing(_ptr(self.obs), _ptr(self.act), _ptr(self.rew), _ptr(self.next_obs), _ptr(self.done),
+                                 self.capacity, _ptr(self.head))
+
+    def __len__(self):
+        return min(int(self.head.item()), self.capacity)
+
+    def scatter(self, obs, act, rew, next_obs, done, valid=None):
+        """memory.push for a batch of rows (rows with valid == 0 are skipped)."""
+        n = int(obs.shape[0])
+        lib = _lib.load()
+        f = lambda t, dt: None if t is None else torch.as_tensor(t, device=self.obs.device).to(dt).contiguous()
+        obs, next_obs, rew = f(obs, torch.float32), f(next_obs, torch.float32), f(rew, torch.float32)
+        act, done, valid = f(act, torch.uint8), f(done, torch.uint8), f(valid, torch.uint8)
+        ring = self.struct()
+        with torch.cuda.device(self.obs.device):
+            _lib.check(lib.pp_replay_scatter(n, C.byref(ring), _ptr(obs), _ptr(act), _ptr(rew), _ptr(next_obs),
+                                             _ptr(done), _ptr(valid), _stream_ptr(self.obs.device)), "pp_replay_scatter")
+
+
+def qnet_act(obs, policy: Policy, seed=0, step_index=0, env_id_base=0, stream_id=_lib.STREAM_ACT_A, want_q=False):
+    """obs[n, 7] -> (actions u8[n], q[n, 3] or None): the reference's `model(obs).argmax(1)` for one player."""
+    lib = _lib.load()
+    obs = obs.to(torch.float32).contiguous()
+    n = int(obs.shape[0])
+    actions = torch.empty(n, dtype=torch.uint8, device=obs.device)
+    q = torch.empty(n, 3, dtype=torch.float32, device=obs.device) if want_q else None
+    ps = policy.struct()
+    with torch.cuda.device(obs.device):
+        _lib.check(lib.pp_qnet_act(n, _ptr(obs), C.byref(ps), int(seed), int(step_index), int(env_id_base),
+                                   int(stream_id), _ptr(actions), _ptr(q), _stream_ptr(obs.device)), "pp_qnet_act")
+    return actions, q
+
+
+def qnetrnn_act(obs, policy: Policy, reset_mask=None, seed=0, step_index=0, env_id_base=0,
+                stream_id=_lib.STREAM_ACT_A, want_q=False):
+    """One QNetRNN step (seq_len 1) with the policy's carried per-env (h, c), updated in place."""
+    lib = _lib.load()
+    obs = obs.to(torch.float32).contiguous()
+    n = int(obs.shape[0])
+    actions = torch.empty(n, dtype=torch.uint8, device=obs.device)
+    q = torch.empty(n, 3, dtype=torch.float32, device=obs.device) if want_q else None
+    m = None if reset_mask is None else torch.as_tensor(reset_mask, device=obs.device).to(torch.uint8).contiguous()
+    ps = policy.struct()
+    with torch.cuda.device(obs.device):
+        _lib.check(lib.pp_qnetrnn_act(n, _ptr(obs), C.byref(ps), _ptr(m), int(seed), int(step_index), int(env_id_base),
+                                      int(stream_id), _ptr(actions), _ptr(q), _stream_ptr(obs.device)), "pp_qnetrnn_act")
+    return actions, q
+
+
+class SelfPlayEngine:
+    """n lock-step envs + player A + player B on one GPU; `run(k)` is one launch of the fused kernel."""
+
+    def __init__(self, env: VecPongEnv2P, policy_a: Policy, policy_b: Policy, seed: int = 0):
+        self.env, self.pa, self.pb = env, policy_a, policy_b
+        self.seed = int(seed)
+        self.step_base = 0
+        self.lib = _lib.load()
+
+    def run(self, k: int, quota: int = 0, ring: ReplayRing | None = None, log_cap: int = 0, want_actions: bool = False):
+        env = self.env
+        out, bufs = env.make_rollout_out(k, log_cap, want_actions, False)
+        pa, pb = self.pa.struct(), self.pb.struct()
+        rs = ring.struct() if ring is not None else None
+        with torch.cuda.device(env.device):
+            _lib.check(self.lib.pp_selfplay_rollout(
+                env.mode_id, env.n, int(k), C.byref(env.params), C.byref(env.state), C.byref(pa), C.byref(pb),
+                self.seed, self.step_base, C.byref(env.serve), int(quota), env.env_id_base, C.byref(out),
+                C.byref(rs) if rs is not None else None, _stream_ptr(env.device)), "pp_selfplay_rollout")
+        self.step_base += int(k)
+        env._served_once = True
+        return bufs
+
+    def evaluate(self, episodes_per_env: int, chunk: int = 64, max_steps: int = 1 << 20) -> dict:
+        """eval_vs_model (scripts/train_iterative.py:171-181) in lock step: every env plays exactly
+        `episodes_per_env` episodes (a fixed quota per env, so short games are not over-sampled) and is frozen
+        afterwards.  Returns the counters and win rates."""
+        env = self.env
+        env.counters.zero_()
+        env.ep_idx.zero_()
+        env._served_once = False
+        env.reset()
+        want = env.n * int(episodes_per_env)
+        steps = 0
+        while steps < max_steps:
+            self.run(chunk, quota=episodes_per_env)
+            steps += chunk
+            if int(env.counters[1].item()) >= want:
+                break
+        c = env.read_counters()
+        c["win_rate_b"] = c["wins_b"] / max(c["episodes"], 1)
+        c["win_rate_a"] = c["wins_a"] / max(c["episodes"], 1)
+        c["lockstep_steps"] = steps
+        return c
+
+
+def host_selfplay_eval(env_kwargs: dict, n: int, quota: int, pool, weights_a, weights_b, mode="f64", chunk=64,
+                       max_steps=1 << 20, ep_log_cap=0):
+    """eval_vs_model for n envs x quota episodes from HOST buffers through the C ABI (pp_host_selfplay_eval):
+    serves [quota, n] x3 and the two packed QNet blobs are numpy arrays; returns (counters dict, ep_log)."""
+    lib = _lib.load()
+    rt = np.float64 if mode == "f64" else np.float32
+    params = make_params(resolve_env_config(env_kwargs))
+    pvx, pvy, psp = (np.ascontiguousarray(a, dtype=rt) for a in pool)
+    assert pvx.shape == (quota, n)
+    wa = np.ascontiguousarray(weights_a, dtype=np.float32)
+    wb = np.ascontiguousarray(weights_b, dtype=np.float32)
+    counters = np.zeros(8, np.uint64)
+    log = np.zeros((max(ep_log_cap, 1), 4), np.int32) if ep_log_cap else None
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    _lib.check(lib.pp_host_selfplay_eval(_lib.MODE_F64 if mode == "f64" else _lib.MODE_F32, n, quota, C.byref(params),
+                                         vp(pvx), vp(pvy), vp(psp), vp(wa), vp(wb), _lib.PREC_F32, chunk, max_steps,
+                                         vp(counters), vp(log), ep_log_cap), "pp_host_selfplay_eval")
+    return dict(zip(COUNTER_NAMES, (int(v) for v in counters))), log

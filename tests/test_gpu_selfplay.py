@@ -1,0 +1,166 @@
+"""Fused self-play kernel, replay scatter and the host-buffer entry (`-m gpu`) against the oracle's closed loop.
+
+The fp32 QNet path computes the oracle's exact fmaf chain, so greedy actions — and with them every trajectory,
+score, done step and winner — are bit-identical to the oracle even in closed loop."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pingpong_selfplay_ai_b200 as pp
+from oracle import pong_oracle as po
+import pp_testutil as gu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def H():
+    return gu.hashes()
+
+
+@pytest.fixture(scope="module")
+def nets():
+    qg = dict(np.load(os.path.join(gu.GOLDEN, "qnet_golden.npz")))
+    return {k: gu.golden_sd(qg, k) for k in ("seed0", "seed1", "ckpt_model5_1_fault_B")}
+
+
+def _oracle_policy(kind, sd=None, eps=0.0, tol=0.02, noisy=False):
+    w = po.qnet_weights_from_state_dict(sd, noisy=noisy) if sd is not None else None
+    return po.make_policy(kind, w, eps=eps, tol=tol)
+
+
+def _sorted_rows(*cols):
+    m = np.concatenate([np.ascontiguousarray(c).reshape(len(c), -1).view(np.uint8).reshape(len(c), -1) for c in cols], 1)
+    return m[np.lexsort(m.T[::-1])]
+
+
+CASES = {
+    "qnet_vs_qnet_greedy": dict(a=("qnet", "seed0", 0.0), b=("qnet", "seed1", 0.0)),
+    "ckpt_vs_follower": dict(a=("follower", None, 0.0), b=("qnet", "ckpt_model5_1_fault_B", 0.0)),
+    "eps_greedy_vs_random": dict(a=("random", None, 0.0), b=("qnet", "seed1", 0.25)),
+}
+
+
+def _mk(spec, nets, which):
+    kind, name, eps = spec
+    if kind == "qnet":
+        return (pp.Policy.qnet(nets[name], eps=eps), _oracle_policy(po.POLICY_QNET, nets[name], eps=eps))
+    if kind == "follower":
+        return pp.Policy.follower(tol=0.02), _oracle_policy(po.POLICY_FOLLOWER, tol=0.02)
+    return pp.Policy.random(), _oracle_policy(po.POLICY_RANDOM)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("mode", ["f64", "f32"])
+def test_selfplay_rollout_bit_exact_vs_oracle(H, nets, case, mode):
+    cfg = H["env_config_yaml"]
+    n, K, depth, seed = 1000, 300, 6, 424242
+    pool = gu.make_pool(11, n, depth, cfg, mode)
+    env = pp.VecPongEnv2P(n, mode=mode, serve=pool, env_id_base=5000, **cfg)
+    env.reset()
+    b = gu.oracle_batch_like(env, mode)
+    (ga, oa), (gb, ob) = _mk(CASES[case]["a"], nets, 0), _mk(CASES[case]["b"], nets, 1)
+    eng = pp.SelfPlayEngine(env, ga, gb, seed=seed)
+    ring = pp.ReplayRing(n * K)
+    acts = []
+    wacts = []
+    want_c = np.zeros(8, np.int64)
+    wlog, wrep = [], []
+    for chunk in (100, 200):                                   # two launches: state and step index carry over
+        got = eng.run(chunk, ring=ring, log_cap=1 << 15, want_actions=True)
+        acts.append(gu.np_of(got["actions"]))
+        w = po.selfplay(po.make_params(cfg), b, oa, ob, chunk, pool, seed=seed, step_base=eng.step_base - chunk,
+                        env_id_base=5000, log_cap=1 << 15, want_actions=True, replay_cap=n * chunk)
+        wacts.append(w["actions"]); want_c += w["counters"]; wlog.append(w["ep_log"]); wrep.append(w["replay"])
+    assert np.array_equal(np.concatenate(acts), np.concatenate(wacts))
+    gu.assert_state_equal(env, b)
+    assert np.array_equal(gu.np_of(env.counters), want_c) and want_c[1] > 100
+    rows = int(ring.head.item())
+    assert rows == sum(len(r["act"]) for r in wrep) == n * K
+    g_rows = _sorted_rows(gu.np_of(ring.obs[:rows]), gu.np_of(ring.act[:rows]), gu.np_of(ring.rew[:rows]),
+                          gu.np_of(ring.next_obs[:rows]), gu.np_of(ring.done[:rows]))
+    w_rows = _sorted_rows(*[np.concatenate([r[k] for r in wrep]) for k in ("obs", "act", "rew", "next", "done")])
+    assert np.array_equal(g_rows, w_rows)                       # same transitions; order inside a step is free
+
+
+def test_selfplay_quota_freezes_envs_and_matches_oracle(H, nets):
+    """Config 3 shape (fixed episode quota per env): outcomes (scores, episode lengths, winners) bit-exact."""
+    cfg = H["env_config_yaml"]
+    n, quota = 2048, 3
+    pool = gu.make_pool(5, n, quota, cfg, "f64")
+    env = pp.VecPongEnv2P(n, mode="f64", serve=pool, **cfg)
+    ga, oa = _mk(("qnet", "seed0", 0.0), nets, 0)
+    gb, ob = _mk(("qnet", "seed1", 0.0), nets, 1)
+    eng = pp.SelfPlayEngine(env, ga, gb, seed=1)
+    res = eng.evaluate(quota, chunk=128)
+    assert res["episodes"] == n * quota and int(env.ep_idx.min().item()) == quota
+    b = po.EnvBatch(n, "f64")
+    b.serve(pool[0][0], pool[1][0], pool[2][0])
+    w = po.selfplay(po.make_params(cfg), b, oa, ob, res["lockstep_steps"], pool, seed=1, quota=quota, log_cap=n * quota)
+    assert np.array_equal(gu.np_of(env.counters), w["counters"])
+    gu.assert_state_equal(env, b)
+    assert res["win_rate_b"] == w["counters"][3] / (n * quota)
+
+
+def test_host_selfplay_eval_from_host_buffers(H, nets):
+    """The HOST-buffer C-ABI entry (what a reference caller holds: numpy serves + weights) == oracle outcomes."""
+    cfg = H["env_config_yaml"]
+    n, quota = 1500, 2
+    pool = gu.make_pool(8, n, quota, cfg, "f64")
+    wa, wb = pp.pack_qnet(nets["seed1"]).numpy(), pp.pack_qnet(nets["ckpt_model5_1_fault_B"]).numpy()
+    c, log = pp.host_selfplay_eval(cfg, n, quota, pool, wa, wb, chunk=64, ep_log_cap=n * quota)
+    b = po.EnvBatch(n, "f64")
+    b.serve(pool[0][0], pool[1][0], pool[2][0])
+    oa = _oracle_policy(po.POLICY_QNET, nets["seed1"]); ob = _oracle_policy(po.POLICY_QNET, nets["ckpt_model5_1_fault_B"])
+    w = po.selfplay(po.make_params(cfg), b, oa, ob, 4096, pool, quota=quota, log_cap=n * quota)
+    assert c["episodes"] == n * quota
+    for i, k in enumerate(pp.COUNTER_NAMES):
+        if k != "env_steps":
+            assert c[k] == w["counters"][i], k
+    assert c["env_steps"] == w["counters"][0]
+    key = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]
+    assert np.array_equal(key(log[:n * quota]), key(w["ep_log"]))
+
+
+def test_shard_invariance_philox(H, nets):
+    """n envs on one slab == the same envs as two slabs with env_id_base offsets (serves, exploration and random
+    players are keyed by the GLOBAL env id), so multi-GPU sharding cannot change any outcome."""
+    cfg = H["env_config_rnn_yaml"]
+    n, K = 4096, 256
+    def run(lo, hi):
+        env = pp.VecPongEnv2P(hi - lo, mode="f64", serve="philox", seed=77, env_id_base=lo, **cfg)
+        env.reset()
+        eng = pp.SelfPlayEngine(env, pp.Policy.random(), pp.Policy.qnet(nets["seed0"], eps=0.1), seed=9)
+        eng.run(K)
+        return gu.np_of(env._real[:, :hi - lo]), gu.np_of(env._int[:, :hi - lo]), gu.np_of(env.counters)
+    r, i, c = run(0, n)
+    r0, i0, c0 = run(0, n // 2)
+    r1, i1, c1 = run(n // 2, n)
+    assert np.array_equal(gu.bits(r), gu.bits(np.concatenate([r0, r1], 1)))
+    assert np.array_equal(i, np.concatenate([i0, i1], 1)) and np.array_equal(c, c0 + c1)
+
+
+@pytest.mark.parametrize("n,cap", [(1000, 4096), (777, 500), (64, 64)])
+def test_replay_scatter_compacts_valid_rows_and_wraps(n, cap):
+    rs = np.random.RandomState(n)
+    obs = rs.rand(n, 7).astype(np.float32); nxt = rs.rand(n, 7).astype(np.float32)
+    act = rs.randint(0, 3, n).astype(np.uint8); rew = rs.choice([-1.0, 0.0, 1.0], n).astype(np.float32)
+    done = (rs.rand(n) < 0.1).astype(np.uint8); valid = (rs.rand(n) < 0.7).astype(np.uint8)
+    ring = pp.ReplayRing(cap)
+    ring.scatter(obs, act, rew, nxt, done, valid)
+    k = int(valid.sum())
+    assert int(ring.head.item()) == k
+    if k <= cap:
+        got = _sorted_rows(gu.np_of(ring.obs[:k]), gu.np_of(ring.act[:k]), gu.np_of(ring.rew[:k]),
+                           gu.np_of(ring.next_obs[:k]), gu.np_of(ring.done[:k]))
+        v = valid.astype(bool)
+        assert np.array_equal(got, _sorted_rows(obs[v], act[v], rew[v], nxt[v], done[v]))
+    ring.scatter(obs, act, rew, nxt, done)                     # all rows valid, wraps when n + k > cap
+    assert int(ring.head.item()) == k + n and len(ring) == min(k + n, cap)
+    rows = _sorted_rows(obs, act, rew, nxt, done)
+    live = _sorted_rows(gu.np_of(ring.obs[:len(ring)]), gu.np_of(ring.act[:len(ring)]), gu.np_of(ring.rew[:len(ring)]),
+                        gu.np_of(ring.next_obs[:len(ring)]), gu.np_of(ring.done[:len(ring)]))
+    present = {r.tobytes() for r in rows}
+    assert all(r.tobytes() in present for r in live)           # every slot holds one complete pushed row

@@ -1,0 +1,150 @@
+"""Host-side logic on the CPU: parameter precomputation, weight packing, network mirrors, slab partitioning and the
+world_size-2 gloo path of the collectives."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import pingpong_selfplay_ai_b200 as pp
+from pingpong_selfplay_ai_b200 import _lib, dist as ppdist
+from oracle import pong_oracle as po
+import pp_testutil as gu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("key", ["env_config_yaml", "env_config_rnn_yaml"])
+def test_params_equal_oracle_params_bitwise(key):
+    cfg = gu.hashes()[key]
+    p, o = pp.make_params(pp.resolve_env_config(cfg)), po.make_params(cfg)
+    for name, _ in po.OracleParams._fields_:
+        if name != "pad_":
+            assert getattr(p, name) == getattr(o, name), name
+    assert float(p.inertia).hex() == "0x1.797cc39ffd60fp-12" and float(p.two_m_over_7).hex() == "0x1.2492492492492p-2"
+    assert (p.speed_lo, p.speed_hi, p.spin_lo, p.spin_hi) == (0.03, 0.05, -5.0, 5.0)
+    assert list(p.angle_lo) == [-60.0, 30.0] and list(p.angle_hi) == [-30.0, 60.0]
+
+
+def test_env_kwargs_follow_reference_constructor():
+    cfg = pp.resolve_env_config({})
+    assert cfg["paddle_speed"] == 0.02 and cfg["speed_scale_every"] == 3 and cfg["ball_angle_intervals"] == [[-60, -30], [30, 60]]
+    with pytest.raises(TypeError):
+        pp.resolve_env_config({"paddle_height": 1})
+
+
+def _blob_forward(blob, obs):
+    """Numpy forward straight from the packed k-major blob (checks the packing, not the kernel)."""
+    o = _lib.QNET_OFF
+    w1t, b1 = blob[o["W1T"]:o["B1"]].reshape(7, 64), blob[o["B1"]:o["W2T"]]
+    w2t, b2 = blob[o["W2T"]:o["B2"]].reshape(64, 64), blob[o["B2"]:o["WHT"]]
+    wht, bh = blob[o["WHT"]:o["BH"]].reshape(64, 4), blob[o["BH"]:]
+    h = np.maximum(obs @ w1t + b1, 0)
+    h = np.maximum(h @ w2t + b2, 0)
+    y = h @ wht + bh
+    return y[:, :1] + (y[:, 1:] - y[:, 1:].mean(1, keepdims=True))
+
+
+@pytest.mark.parametrize("noisy", [False, True])
+def test_pack_qnet_layout_and_mirror_outputs(noisy):
+    g = dict(np.load(os.path.join(gu.GOLDEN, "qnet_golden.npz")))
+    for name in ("seed0", "ckpt_model5_1_fault_B"):
+        sd = gu.golden_sd(g, name)
+        blob = pp.pack_qnet(sd, noisy=noisy).numpy()
+        ref = g[f"{name}/q_{'train' if noisy else 'eval'}"]
+        assert np.abs(_blob_forward(blob, g["obs"]) - ref).max() < 1e-5
+        net = pp.QNet()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)     # reference keys, unchanged
+        net.train(noisy)
+        with torch.no_grad():
+            assert np.abs(net(torch.from_numpy(g["obs"])).numpy() - ref).max() < 1e-6
+        assert torch.equal(pp.pack_qnet(net, noisy=noisy), torch.from_numpy(blob))
+
+
+def test_pack_qnetrnn_layout_and_mirror_outputs():
+    g = dict(np.load(os.path.join(gu.GOLDEN, "qnetrnn_golden.npz")))
+    sd = gu.golden_sd(g, "seed0")
+    blob = pp.pack_qnetrnn(sd).numpy()
+    o = _lib.RNN_OFF
+    wg = blob[o["WGT"]:o["BG"]].reshape(256, 128, 4)                         # [k][unit][gate]
+    assert np.array_equal(wg[:128, 5, 2], sd["lstm.weight_ih_l0"][2 * 128 + 5])      # gate g, unit 5, over features
+    assert np.array_equal(wg[128:, 9, 3], sd["lstm.weight_hh_l0"][3 * 128 + 9])
+    bg = blob[o["BG"]:o["WST"]].reshape(128, 4)
+    assert np.array_equal(bg[7, 1], (sd["lstm.bias_ih_l0"] + sd["lstm.bias_hh_l0"])[128 + 7])
+    assert np.array_equal(blob[o["WST"]:o["BS"]].reshape(128, 128), sd["fc_shared_head.0.weight_mu"].T)
+    net = pp.QNetRNN()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    net.eval()
+    seq = torch.from_numpy(g["seq"])
+    hc = net.init_hidden(seq.shape[0], "cpu")
+    with torch.no_grad():
+        for t in range(seq.shape[1]):
+            q, hc = net(seq[:, t:t + 1], hc)
+            assert np.abs(q.numpy() - g["seed0/q_eval"][t]).max() < 1e-6
+    with pytest.raises(ValueError):
+        pp.pack_qnetrnn(pp.QNetRNN(feature_dim=64))
+
+
+def test_noisy_linear_statistics_and_reset():
+    torch.manual_seed(0)
+    lin = pp.NoisyLinear(64, 3)
+    assert float(lin.weight_sigma[0, 0]) == pytest.approx(0.017) and lin.weight_mu.abs().max() <= 1 / 8
+    e0 = lin.weight_epsilon.clone()
+    lin.reset_noise()
+    assert not torch.equal(e0, lin.weight_epsilon)
+    assert torch.allclose(lin.weight_epsilon, torch.outer(lin.bias_epsilon, lin.weight_epsilon[0] / lin.bias_epsilon[0]), atol=1e-5)
+
+
+def test_eps_threshold_and_slab_bounds():
+    from pingpong_selfplay_ai_b200.policy import eps_threshold
+    assert eps_threshold(0.0) == 0 and eps_threshold(1.0) == 1 << 32 and eps_threshold(0.5) == 1 << 31
+    assert eps_threshold(0.3) == po.eps_threshold(0.3)
+    for n, w in [(10, 3), (262144, 8), (7, 8), (1 << 20, 8)]:
+        b = [ppdist.slab_bounds(n, w, r) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        ppdist.slab_bounds(8, 2, 2)
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PP_ROOT"])
+from pingpong_selfplay_ai_b200 import dist as ppd, QNet
+rank, world, local = ppd.init_from_env("gloo")
+assert world == 2 and ppd.is_parallel()
+lo, hi = ppd.slab_bounds(1001, world, rank)
+counters = torch.tensor([hi - lo, rank + 1, 0, 0, 0, 0, 0, 7], dtype=torch.int64)
+tot = ppd.allreduce_counters(counters)
+assert tot.tolist() == [1001, 3, 0, 0, 0, 0, 0, 14] and counters[0] == hi - lo
+torch.manual_seed(0)
+net = QNet()
+heads = list(net.fc_V.parameters()) + list(net.fc_A.parameters())
+assert sum(p.numel() for p in heads) == 520
+x = torch.full((4, 7), float(rank + 1))
+net(x).sum().backward()
+local_g = [p.grad.clone() for p in heads]
+ppd.allreduce_mean_grads(heads)
+gathered = [torch.zeros(520) for _ in range(2)]
+dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local_g]))
+want = (gathered[0] + gathered[1]) / 2
+assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in heads]), want, atol=1e-7)
+assert ppd.max_over_ranks(float(rank)) == 1.0
+t = torch.full((3,), float(rank)); ppd.broadcast_(t, 0); assert t.tolist() == [0.0, 0.0, 0.0]
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gloo_world_size_2_counters_and_grad_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, PP_ROOT=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok 0" in r.stdout and "ok 1" in r.stdout
