@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Headline benchmark: self-play env-steps/sec (PongEnv2P step + both players' QNet action) — BASELINE.json `metric`.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on that fits one GPU): 65 536 lock-step
+envs per GPU, random-init QNet A (torch.manual_seed(0)) vs QNet B (seed 1), eval-mode weights, greedy, auto-reset
+with device (Philox) serves, fp64 bit-exact env arithmetic.  One "step" = one launch of the fused self-play kernel
+= `--lockstep` (64) lock-step env steps of every env.  Weak scaling: every rank owns its own 65 536-env slab; the
+only collective is the all-reduce of the 8 counters at the end of the timed region.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the
+host-buffer C-ABI entry (numpy serves + weights in, counters out, copies inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+ENV_CFG = dict(  # the env: block of the reference's config.yaml (values restated; the file is not on the GPU box)
+    render_size=400, paddle_width=0.2, paddle_speed=0.03, max_score=3, enable_render=False, enable_spin=True,
+    magnus_factor=0.025, restitution=1, friction=0.6, ball_mass=1.0, world_ball_radius=0.03,
+    ball_speed_range=[0.03, 0.05], spin_range=[-5, 5], ball_angle_intervals=[[-60, -30], [30, 60]],
+    speed_scale_every=1, speed_increment=0.1)
+METRIC = "self-play env-steps/sec (env + both players' QNet action)"
+UNIT = "env-steps/s"
+FLOP_PER_ENV_STEP = 19200            # 2 players x 2 x 4800 MAC
+BYTES_PER_STEP_F64 = 203             # K1 single step, all outputs materialised, fp64 mode
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), bf16_burst=float(p["bf16_tflops"]),
+                    bf16_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi as a fallback)."""
+
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        if not self.samples:
+            try:
+                import subprocess
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = (float(v) for v in out.strip().split(","))
+                return dict(sm_mhz=a, sm_max_mhz=b, reasons=["unsampled: NVML unavailable, one nvidia-smi reading after the run"])
+            except Exception:
+                return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------ CPU baselines
+def _port_selfplay_loop(n_steps: int, seed: int) -> int:
+    """The reference's own per-step eval loop (scripts/train_iterative.py:171-181) restated on the CPU port:
+    pure-Python env + torch batch-1 QNet forward + argmax().item() for A and B, reset on done."""
+    import random
+
+    from oracle import pong_port
+    from oracle.policy_torch import QNetPort
+    torch.set_num_threads(1)
+    random.seed(seed)
+    torch.manual_seed(0); net_a = QNetPort().eval()
+    torch.manual_seed(1); net_b = QNetPort().eval()
+    env = pong_port.PongPort(**ENV_CFG)
+    oa, ob = env.reset()
+    with torch.no_grad():
+        for _ in range(n_steps):
+            a = net_a(torch.tensor(oa, dtype=torch.float32).unsqueeze(0)).argmax(1).item()
+            b = net_b(torch.tensor(ob, dtype=torch.float32).unsqueeze(0)).argmax(1).item()
+            (oa, ob), _, done, _ = env.step(a, b)
+            if done:
+                oa, ob = env.reset()
+    return n_steps
+
+
+def _worker(args):
+    n_steps, seed = args
+    t0 = time.perf_counter()
+    _port_selfplay_loop(n_steps, seed)
+    return time.perf_counter() - t0
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class PortPool:
+    """`procs` forked workers, each running the reference-shaped loop independently (no CUDA in the children; the
+    parent forks BEFORE it touches the GPU)."""
+
+    def __init__(self, procs: int):
+        import multiprocessing as mp
+        self.procs = procs
+        self.pool = mp.get_context("fork").Pool(procs) if procs > 1 else None
+
+    def run(self, steps_per_proc: int) -> tuple[float, float]:
+        """env-steps/s over all workers and the wall time of this sample."""
+        t0 = time.perf_counter()
+        if self.pool is None:
+            _worker((steps_per_proc, 0))
+        else:
+            self.pool.map(_worker, [(steps_per_proc, s) for s in range(self.procs)], chunksize=1)
+        wall = time.perf_counter() - t0
+        return self.procs * steps_per_proc / wall, wall
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+def c_oracle_throughput(n: int, k: int) -> float:
+    """Single-thread C oracle (fmaf-chain QNet + fp64 env) on the same workload shape — an optimised CPU point."""
+    from oracle import pong_oracle as po
+    from oracle.policy_torch import QNetPort
+    pool = tuple(np.ascontiguousarray(a) for a in po.serve_pool_from_reference_rng(1, n, 4, ENV_CFG))
+    torch.manual_seed(0); wa = po.qnet_weights_from_state_dict(QNetPort().state_dict())
+    torch.manual_seed(1); wb = po.qnet_weights_from_state_dict(QNetPort().state_dict())
+    b = po.EnvBatch(n, "f64")
+    b.serve(pool[0][0], pool[1][0], pool[2][0])
+    pa, pb = po.make_policy(po.POLICY_QNET, wa), po.make_policy(po.POLICY_QNET, wb)
+    p = po.make_params(ENV_CFG)
+    po.selfplay(p, b, pa, pb, 2, pool)
+    t0 = time.perf_counter()
+    out = po.selfplay(p, b, pa, pb, k, pool)
+    return float(out["counters"][0]) / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank: int):
+    """`--impl reference`: the reference's CPU implementation of the path (its per-step Python loop, restated by the
+    oracle port because /root/reference cannot travel to the GPU box), one process per host core."""
+    if rank != 0:
+        return
+    cores = host_cores()
+    procs = max(1, min(cores, int(os.environ.get("PP_REF_PROCS", cores))))
+    per_proc = args.ref_steps
+    pool = PortPool(procs)
+    for _ in range(args.warmup):
+        pool.run(max(per_proc // 8, 50))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pool.run(per_proc)
+    wall = time.perf_counter() - t0
+    pool.close()
+    value = procs * per_proc * args.steps / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 env state + f32 QNet", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{procs} processes x {per_proc} env-steps per step of the reference-shaped loop "
+                                   "(pure-Python PongEnv2P port + torch batch-1 QNet A and B, argmax().item()), "
+                                   "torch.set_num_threads(1) per process"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "configs[2]: self-play eval, random-init QNet A vs QNet B, 65536 lock-step PongEnv2P envs per GPU, "
+                        "fused obs->QNet->argmax + env step, greedy, auto-reset (Philox serves), config.yaml env params",
+            "envs_per_gpu": args.envs, "lockstep_steps_per_launch": args.lockstep, "env_mode": args.mode,
+            "qnet_precision": args.precision, "parallelism": f"env-slab dp{world}",
+            "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event brackets); "
+                  "state is register-resident inside a launch"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--lockstep", type=int, default=64, help="lock-step env steps per launch")
+    ap.add_argument("--mode", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--precision", default="f32", choices=["f32", "f16"])
+    ap.add_argument("--ref-steps", type=int, default=1500, help="reference arm: env-steps per process per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-k1", action="store_true", help="skip the single-step env kernel HBM roofline measurement")
+    ap.add_argument("--k1-envs", type=int, default=16 << 20, help="envs of the single-step HBM roofline measurement")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # before CUDA is touched: the workers are forked
+        cpu_baseline = measure_cpu_baseline()
+
+    import pingpong_selfplay_ai_b200 as pp
+    from pingpong_selfplay_ai_b200 import dist as ppd
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
+    rank, world, local = ppd.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+
+    n, k = args.envs, args.lockstep
+    lo = rank * n
+    torch.manual_seed(0); net_a = pp.QNet()
+    torch.manual_seed(1); net_b = pp.QNet()
+    env = pp.VecPongEnv2P(n, device=dev, mode=args.mode, serve="philox", seed=2026, env_id_base=lo, **ENV_CFG)
+    env.reset()
+    pa = pp.Policy.qnet(net_a, device=dev, precision=args.precision)
+    pb = pp.Policy.qnet(net_b, device=dev, precision=args.precision)
+    eng = pp.SelfPlayEngine(env, pa, pb, seed=7)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    for _ in range(args.warmup):
+        eng.run(k)
+    torch.cuda.synchronize()
+    env.counters.zero_()
+    sampler = ClockSampler(local).start()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.zero_()                                   # L2 flush, outside the event bracket
+        s.record()
+        eng.run(k)                                      # ONE launch of the fused self-play kernel
+        e.record()
+    total = ppd.allreduce_counters(env.counters)        # the path's only collective (8 x int64)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    dev_ms = ppd.max_over_ranks(dev_ms, dev)
+    env_steps = int(total[0].item())
+    assert env_steps == world * n * k * args.steps, (env_steps, world, n, k, args.steps)
+    value = env_steps / (dev_ms * 1e-3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"{args.mode} env state + {args.precision} QNet", "data": "synthetic",
+        "config": workload_config(args, world), "clocks": clocks, "gpu_launches": args.steps,
+        "wall_s_timed_region_incl_flush": wall,
+        "outcomes": {"episodes": int(total[1].item()), "wins_a": int(total[2].item()), "wins_b": int(total[3].item()),
+                     "paddle_hits": int(total[6].item())},
+    }
+    tf = value / world * FLOP_PER_ENV_STEP / 1e12
+    line["roofline"] = {"bound": "tensor", "kernel": "selfplay_kernel", "achieved": tf, "peak": peaks["bf16_sustained"],
+                        "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"], "traffic": None,
+                        "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
+                        "note": "algorithmic 19200 FLOP per env-step (both players' QNet) x env-steps per launch / "
+                                "CUDA-event launch time, per GPU"}
+
+    if rank == 0 and not args.no_k1:
+        line["roofline_env_step"] = measure_k1(pp, dev, peaks, args.mode, args.k1_envs)
+    if rank == 0 and not args.no_e2e:
+        line["e2e"] = measure_e2e(pp, net_a, net_b, args)
+        if world > 1:
+            line["e2e"]["note"] = "measured on rank 0's GPU only (host-buffer entry is single-GPU)"
+    if cpu_baseline is not None:
+        line.update(cpu_baseline)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def measure_cpu_baseline() -> dict:
+    procs = max(1, min(host_cores(), 64))
+    per_proc = 120000
+    pool = PortPool(procs)
+    pool.run(200)
+    v, w = pool.run(per_proc)
+    pool.close()
+    out = {"cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                            "sample": f"{procs} processes x {per_proc} env-steps of the reference-shaped loop (pure-Python "
+                                      f"PongEnv2P port + torch batch-1 QNet A and B, argmax().item()), {w:.1f} s wall, "
+                                      f"{host_cores()} host cores available"}}
+    try:
+        out["cpu_baseline_c_oracle"] = {"value": c_oracle_throughput(4096, 64), "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": "C oracle closed loop (fp64 env + fmaf-chain QNet), 4096 envs x 64 steps, 1 thread"}
+    except Exception as e:  # an extra data point, not part of the contract
+        out["cpu_baseline_c_oracle"] = {"error": str(e)}
+    return out
+
+
+def measure_k1(pp, dev, peaks, mode, n):
+    """K1 single-step kernel (all outputs materialised) on a working set far beyond L2: HBM roofline."""
+    env = pp.VecPongEnv2P(n, device=dev, mode=mode, serve="philox", seed=1, **ENV_CFG)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(0)
+    aa = torch.randint(0, 3, (n,), dtype=torch.uint8, device=dev, generator=g)
+    ab = torch.randint(0, 3, (n,), dtype=torch.uint8, device=dev, generator=g)
+    for _ in range(3):
+        env.step(aa, ab)
+    torch.cuda.synchronize()
+    reps = 20
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        env.step(aa, ab)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    per = BYTES_PER_STEP_F64 if mode == "f64" else 147
+    gbs = n * per / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "step_kernel", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": gbs / peaks["hbm"], "traffic": None, "envs": n, "ms_per_launch": ms,
+            "env_steps_per_s": n / (ms * 1e-3), "peak_source": f"{peaks['src']} copy bandwidth",
+            "note": f"{per} algorithmic B per env-step (SURVEY.md 8d), working set {n * per / 2**20:.0f} MiB >> L2"}
+
+
+def measure_e2e(pp, net_a, net_b, args):
+    """The same metric through the reference-facing host-buffer call: numpy serves + packed weights in, counters out;
+    H2D / D2H copies and every sync inside the timed region (wall clock around the synchronous C-ABI call)."""
+    from pingpong_selfplay_ai_b200.params import make_params, resolve_env_config  # noqa: F401
+    n, quota = args.envs, 8
+    rs = np.random.RandomState(0)
+    speed = rs.uniform(0.03, 0.05, size=(quota, n))
+    ang = np.radians(np.where(rs.rand(quota, n) < 0.5, rs.uniform(-60, -30, size=(quota, n)), rs.uniform(30, 60, size=(quota, n))))
+    rt = np.float64 if args.mode == "f64" else np.float32
+    pool = ((speed * np.cos(ang)).astype(rt), (speed * np.sin(ang)).astype(rt), rs.uniform(-5, 5, size=(quota, n)).astype(rt))
+    wa, wb = pp.pack_qnet(net_a).numpy(), pp.pack_qnet(net_b).numpy()
+    pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep)      # warm-up (allocations)
+    reps, steps_total, t0 = 3, 0, time.perf_counter()
+    for _ in range(reps):
+        c, _ = pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep)
+        steps_total += c["env_steps"]
+    wall = time.perf_counter() - t0
+    h2d = 3 * quota * n * np.dtype(rt).itemsize + 2 * wa.nbytes
+    return {"value": steps_total / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 72,
+            "call": "pp_host_selfplay_eval (eval_vs_model for 65536 envs x 8 episodes each, host numpy buffers)",
+            "episodes_per_call": int(c["episodes"]), "env_steps_per_call": int(c["env_steps"]), "ms_per_call": 1e3 * wall / reps}
+
+
+if __name__ == "__main__":
+    main()

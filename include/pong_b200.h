@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 1
+#define PP_ABI_VERSION 2
 
 enum { PP_MODE_F64 = 0, PP_MODE_F32 = 1 };
 
@@ -93,8 +93,10 @@ typedef struct PPServeSource {
 /* A player.  Replaces the per-step `model(torch.tensor(obs).unsqueeze(0)).argmax(1).item()` of
  * scripts/train_iterative.py:124-130,176-177,240 and select_action_universal tests/arena.py:199-219. */
 enum { PP_POLICY_QNET = 0, PP_POLICY_QNETRNN = 1, PP_POLICY_FOLLOWER = 2, PP_POLICY_RANDOM = 3 };
-enum { PP_PREC_F32 = 0,     /* CUDA-core fp32, fmaf chain in ascending k: bit-identical to the oracle  */
-       PP_PREC_BF16 = 1 };  /* tcgen05 bf16 tiles with fp32 accumulation in TMEM (QNet hidden layers)   */
+enum { PP_PREC_F32 = 0,     /* CUDA-core fp32, fmaf chain in ascending k: bit-identical to the oracle          */
+       PP_PREC_F16 = 1 };   /* tcgen05 tensor cores: fp16 operands (obs and biases split hi/lo), fp32 accumulation
+                             * in TMEM; Q within 1e-3 of the fp32 reference.  fp16 rather than bf16: same tensor
+                             * rate, 8x smaller rounding error, range handled by saturating conversions.        */
 typedef struct PPPolicy {
     int32_t kind;
     int32_t precision;
@@ -115,7 +117,7 @@ enum {
 
 /* QNetRNN blob (floats), default dims 7-64-128 / LSTM 128 / head 128 (config_rnn.yaml:39-42):
  *   Wf1t[7][64] bf1[64] Wf2t[64][128] bf2[128] Wgt[256][512] (rows 0..127 = W_ih^T, 128..255 = W_hh^T;
- *   column = gate*128 + unit, gates i,f,g,o) bg[512] (= b_ih + b_hh) Wst[128][128] bs[128] Wht[128][4] bh[4] */
+ *   column = unit*4 + gate, gates i,f,g,o) bg[512] (= b_ih + b_hh) Wst[128][128] bs[128] Wht[128][4] bh[4] */
 enum {
     PP_RNN_WF1T = 0, PP_RNN_BF1 = 448, PP_RNN_WF2T = 512, PP_RNN_BF2 = 8704, PP_RNN_WGT = 8832,
     PP_RNN_BG = 139904, PP_RNN_WST = 140416, PP_RNN_BS = 156800, PP_RNN_WHT = 156928, PP_RNN_BH = 157440,
@@ -137,7 +139,10 @@ typedef struct PPRolloutOut {
 } PPRolloutOut;
 
 /* Replay ring of player B's transitions (oB, aB, rB, nB, done)  scripts/train_iterative.py:243;
- * 62 bytes per row over five arrays; *head is a monotonically increasing write cursor. */
+ * 62 bytes per row over five arrays; *head is a monotonically increasing write cursor (slot = cursor %
+ * capacity).  A call that pushes more rows than `capacity` writes only the rows that sequential pushes
+ * would leave in the ring (the last `capacity` rows of pp_replay_scatter, the last capacity / n lock-step
+ * steps of pp_selfplay_rollout, which needs capacity >= n); *head counts written rows. */
 typedef struct PPReplayRing {
     float *obs;                 /* [capacity][7] */
     uint8_t *act;               /* [capacity]    */

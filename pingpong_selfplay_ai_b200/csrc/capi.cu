@@ -41,6 +41,8 @@ bool policy_ok(const PPPolicy *p, bool allow_rnn) {
         default: return false;
     }
 }
+bool prec_ok(const PPPolicy *p) { return p->precision == PP_PREC_F32 || p->precision == PP_PREC_F16; }
+bool uses_tc(const PPPolicy *p) { return p->kind == PP_POLICY_QNET && p->precision == PP_PREC_F16; }
 bool out_ok(const PPRolloutOut *o) {
     if (!o) return false;
     if (o->ep_log && (!o->ep_log_count || o->ep_log_cap < 0 || (reinterpret_cast<uintptr_t>(o->ep_log) & 15u))) return false;
@@ -116,8 +118,11 @@ int pp_qnet_act(int64_t n, const float *obs, const PPPolicy *policy, uint64_t se
     if (n < 0) return fail(PP_E_SIZE, "pp_qnet_act");
     if (!obs || !actions) return fail(PP_E_NULL, "pp_qnet_act");
     if (!policy_ok(policy, false)) return fail(PP_E_MODE, "pp_qnet_act");
-    if (policy->precision != PP_PREC_F32) return fail(PP_E_MODE, "pp_qnet_act");
+    if (!prec_ok(policy)) return fail(PP_E_MODE, "pp_qnet_act");
     if (n == 0) return 0;
+    if (uses_tc(policy))
+        return ok_or(pp::qnet_act_tc_launch(n, obs, *policy, seed, step_index, env_id_base, stream_id, actions, q_out,
+                                            (cudaStream_t)stream), "pp_qnet_act");
     return ok_or(pp::qnet_act_launch(n, obs, *policy, seed, step_index, env_id_base, stream_id, actions, q_out,
                                      (cudaStream_t)stream), "pp_qnet_act");
 }
@@ -142,9 +147,16 @@ int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, 
     if (!params_ok(params)) return fail(PP_E_PARAM, "pp_selfplay_rollout");
     if (!state_ok(state, true) || !serve_ok(serve) || !out_ok(out)) return fail(PP_E_NULL, "pp_selfplay_rollout");
     if (!policy_ok(policy_a, false) || !policy_ok(policy_b, false)) return fail(PP_E_MODE, "pp_selfplay_rollout");
-    if (policy_a->precision != PP_PREC_F32 || policy_b->precision != PP_PREC_F32) return fail(PP_E_MODE, "pp_selfplay_rollout");
+    if (!prec_ok(policy_a) || !prec_ok(policy_b)) return fail(PP_E_MODE, "pp_selfplay_rollout");
+    const bool tc = uses_tc(policy_a) || uses_tc(policy_b);
+    if (tc && ((policy_a->kind == PP_POLICY_QNET && !uses_tc(policy_a)) || (policy_b->kind == PP_POLICY_QNET && !uses_tc(policy_b))))
+        return fail(PP_E_MODE, "pp_selfplay_rollout");                 // both QNet players on the same path
     if (ring && !ring_ok(ring)) return fail(PP_E_NULL, "pp_selfplay_rollout");
+    if (ring && ring->capacity < n) return fail(PP_E_SIZE, "pp_selfplay_rollout");     // one lock-step step must fit
     if (n == 0 || k == 0) return 0;
+    if (tc)
+        return ok_or(pp::selfplay_tc_launch(mode, n, k, *params, *state, *policy_a, *policy_b, seed, step_base, *serve,
+                                            quota, env_id_base, *out, ring, (cudaStream_t)stream), "pp_selfplay_rollout");
     return ok_or(pp::selfplay_launch(mode, n, k, *params, *state, *policy_a, *policy_b, seed, step_base, *serve, quota,
                                      env_id_base, *out, ring, (cudaStream_t)stream), "pp_selfplay_rollout");
 }
@@ -196,7 +208,7 @@ int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *pa
                           const float *host_weights_b, int32_t precision, int64_t chunk, int64_t max_steps,
                           unsigned long long *host_counters, int32_t *host_ep_log, int64_t ep_log_cap) {
     const char *fn = "pp_host_selfplay_eval";
-    if (!mode_ok(mode) || precision != PP_PREC_F32) return fail(PP_E_MODE, fn);
+    if (!mode_ok(mode) || (precision != PP_PREC_F32 && precision != PP_PREC_F16)) return fail(PP_E_MODE, fn);
     if (n <= 0 || quota <= 0 || chunk <= 0 || max_steps <= 0 || ep_log_cap < 0) return fail(PP_E_SIZE, fn);
     if (!params_ok(params)) return fail(PP_E_PARAM, fn);
     if (!host_pool_vx || !host_pool_vy || !host_pool_spin || !host_weights_a || !host_weights_b || !host_counters)
@@ -234,14 +246,16 @@ int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *pa
     PPServeSource src{PP_SERVE_POOL, quota, pvx, pvy, psp, 0};
     rc = pp::env_reset_launch(mode, n, *params, es, nullptr, src, 0, /*advance=*/0, st);     // serve 0 of every env
     if (rc) return fail(rc, fn);
-    PPPolicy pa{PP_POLICY_QNET, PP_PREC_F32, 0, 0.f, 0, wa, nullptr, nullptr};
-    PPPolicy pb{PP_POLICY_QNET, PP_PREC_F32, 0, 0.f, 0, wb, nullptr, nullptr};
+    PPPolicy pa{PP_POLICY_QNET, precision, 0, 0.f, 0, wa, nullptr, nullptr};
+    PPPolicy pb{PP_POLICY_QNET, precision, 0, 0.f, 0, wb, nullptr, nullptr};
     PPRolloutOut out{ctr, dlog, host_ep_log ? ep_log_cap : 0, ctr + 8, nullptr, nullptr, nullptr};
     unsigned long long *h = (unsigned long long *)g_cache.pinned;
     const unsigned long long want = (unsigned long long)n * (unsigned long long)quota;
     for (int64_t done_steps = 0; done_steps < max_steps; done_steps += chunk) {
         const int64_t k = (max_steps - done_steps) < chunk ? (max_steps - done_steps) : chunk;
-        rc = pp::selfplay_launch(mode, n, k, *params, es, pa, pb, 0, done_steps, src, quota, 0, out, nullptr, st);
+        rc = precision == PP_PREC_F16
+                 ? pp::selfplay_tc_launch(mode, n, k, *params, es, pa, pb, 0, done_steps, src, quota, 0, out, nullptr, st)
+                 : pp::selfplay_launch(mode, n, k, *params, es, pa, pb, 0, done_steps, src, quota, 0, out, nullptr, st);
         if (rc) return fail(rc, fn);
         CK(cudaMemcpyAsync(h, ctr, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

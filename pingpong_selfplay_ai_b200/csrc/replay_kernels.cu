@@ -1,7 +1,7 @@
 // replay_kernels.cu — K3: append transitions (oB, aB, rB, nB, done) to the replay ring
 // (memory.push of scripts/train_iterative.py:56-63,243), 62 bytes per row over five arrays.
 //
-// Rows are compacted per warp: ballot of the valid lanes, one atomicAdd on the ring cursor per warp,
+// *head advances by the number of rows WRITTEN.  Rows are compacted per warp: ballot of the valid lanes, one atomicAdd on the ring cursor per warp,
 // rank by popc.  A fully valid warp whose 32 slots do not wrap copies its 2 x 896 B of observations
 // with lane-contiguous (coalesced) accesses; otherwise each lane copies its own row.
 #include "pp_device.cuh"
@@ -15,7 +15,9 @@ replay_scatter_kernel(int64_t n, const PPReplayRing ring, const float *__restric
                       const uint8_t *__restrict__ valid) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool v = i < n && (valid == nullptr || valid[i] != 0);
+    // a batch larger than the ring: only its last `capacity` rows can survive sequential pushes, and skipping
+    // the others keeps concurrently written slots distinct (no torn rows)
+    const bool v = i < n && i >= n - ring.capacity && (valid == nullptr || valid[i] != 0);
     const unsigned m = __ballot_sync(0xffffffffu, v);
     if (m == 0) return;
     const int leader = __ffs(m) - 1;

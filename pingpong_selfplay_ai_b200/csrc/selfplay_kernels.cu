@@ -6,7 +6,7 @@
 //                     env state, both observations and all bookkeeping in registers and both weight
 //                     blobs in shared memory: nothing but the replay rows and the episode log touches
 //                     HBM between the first and last step of a launch.
-#include "pp_policy.cuh"
+#include "pp_rollout.cuh"
 #include "pp_host.h"
 
 namespace pp {
@@ -74,19 +74,19 @@ selfplay_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k
     const int64_t i = (int64_t)blockIdx.x * SP_THREADS + threadIdx.x;
     const bool valid = i < n;
     const int64_t ic = valid ? i : 0;
-    const int lane = threadIdx.x & 31;
-    Env<R> e = load_env<R>(s, ic);
-    int ep_idx = s.ep_idx[ic], ep_len = s.ep_len[ic];
+    Lane<R> L;
+    L.e = load_env<R>(s, ic);
+    L.ep_idx = s.ep_idx[ic]; L.ep_len = s.ep_len[ic];
     const uint32_t g = (uint32_t)(env_id_base + ic);
-    Tally tally;
+    const int64_t ring_t0 = ring_first_step(ring, n, k_steps);
 
 #pragma unroll 1
     for (int64_t t = 0; t < k_steps; ++t) {
-        const bool active = valid && !(quota > 0 && ep_idx >= quota);
+        const bool active = valid && !(quota > 0 && L.ep_idx >= quota);
         const uint32_t step = (uint32_t)(step_base + t);
         float oa[7], ob[7];
-        observe<R>(e, oa, ob);
-        int act_a = 1, act_b = 1, flags = 0;
+        observe<R>(L.e, oa, ob);
+        int act_a = 1, act_b = 1;
         // a warp whose envs are all frozen skips the policy work altogether
         if (__any_sync(0xffffffffu, active)) {
 #pragma unroll 1
@@ -98,53 +98,15 @@ selfplay_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k
                 if (p) act_b = a; else act_a = a;
             }
         }
-        if (active) {
-            flags = env_step<R>(c, e, act_a, act_b);
-            ep_len += 1;
-            tally.add_flags(flags);
-            if (out.actions_out)
-                reinterpret_cast<uchar2 *>(out.actions_out)[t * n + i] = make_uchar2((unsigned char)act_a, (unsigned char)act_b);
-        }
-        if (ring.head) {       // memory.push((oB, aB, rB, nB, done)), rows compacted per warp
-            const unsigned m = __ballot_sync(0xffffffffu, active);
-            if (m) {
-                unsigned long long base = 0;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) base = atomicAdd(ring.head, (unsigned long long)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (active) {
-                    const int64_t slot = (int64_t)((base + __popc(m & ((1u << lane) - 1u))) % (unsigned long long)ring.capacity);
-                    float na[7], nb[7];
-                    observe<R>(e, na, nb);
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) { ring.obs[slot * 7 + k] = ob[k]; ring.next_obs[slot * 7 + k] = nb[k]; }
-                    ring.act[slot] = (uint8_t)act_b;
-                    ring.rew[slot] = (flags & F_POINT_B) ? 1.0f : ((flags & F_POINT_A) ? -1.0f : 0.0f);
-                    ring.done[slot] = (uint8_t)(flags & F_DONE);
-                }
-            }
-        }
-        const bool fin = (flags & F_DONE) != 0;
-        log_episode(fin, out, (int)(env_id_base + i), ep_idx, e.sa, e.sb, ep_len);
-        if (fin) {
-            tally.episodes += 1;
-            if (e.sa > e.sb) tally.wins_a += 1; else tally.wins_b += 1;
-            tally.len_sum += (unsigned)ep_len;
-            ep_idx += 1;
-            if (!(quota > 0 && ep_idx >= quota)) {
-                R svx, svy, ssp;
-                next_serve<R>(params, src, n, i, env_id_base, ep_idx, svx, svy, ssp);
-                serve_env<R>(e, svx, svy, ssp);
-                ep_len = 0;
-            }
-        }
+        step_and_book<R>(c, params, L, valid, active, act_a, act_b, ob, t, n, i, env_id_base, src, quota, out, ring,
+                         ring.head != nullptr && t >= ring_t0);
     }
     if (valid) {
-        store_env<R>(s, i, e);
-        s.ep_idx[i] = ep_idx;
-        s.ep_len[i] = ep_len;
+        store_env<R>(s, i, L.e);
+        s.ep_idx[i] = L.ep_idx;
+        s.ep_len[i] = L.ep_len;
     }
-    if (out.counters) tally.flush(out.counters);
+    if (out.counters) L.tally.flush(out.counters);
 }
 
 int qnet_act_launch(int64_t n, const float *obs, const PPPolicy &pol, uint64_t seed, int64_t step_index,

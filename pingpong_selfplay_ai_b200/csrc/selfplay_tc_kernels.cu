@@ -1,0 +1,437 @@
+// selfplay_tc_kernels.cu — K2a on the 5th-generation tensor cores (PP_PREC_F16) and the fused self-play rollout
+// built on it.
+//
+// A *group* is 128 threads = 128 envs = the 128 rows (TMEM lanes) of one UMMA tile; a CTA holds four groups that
+// run independently (named barriers, one mbarrier each), so one group's epilogue overlaps the others' MMA round
+// trips, and there is one CTA per SM.  The QNet (models/qnet.py:71-75) of one player is three tcgen05.mma batches
+// with fp16 operands and fp32 accumulation in TMEM.  Activations AND weights are split x = x_hi + x_lo into two
+// fp16 numbers (22 significant bits) and every product is taken as hi*hi + lo*hi + hi*lo, so Q-values carry
+// ~fp32 accuracy (measured ~1e-6 relative) instead of fp16's 2^-12 — trained heads have |W| > 20, where a
+// single fp16 pass is off by 3e-2:
+//     L1  D[128x64] = X * W1h'^T + X * W1l'^T      X = [obs_hi(7) 1 | obs_lo(7) 1]   (2 MMAs, K = 16)
+//                                                  W1h' = [W1_hi ; b1_hi | W1_hi ; b1_lo], W1l' = [W1_lo ; 0 | 0]
+//     L2  D[128x64] = H1h*W2h^T + H1l*W2h^T + H1h*W2l^T (3 x 4 MMAs, K = 16 each) + X * B2'^T (bias via X's ones)
+//     L3  D[128x16] = same with the dueling heads, N = 16 (columns 0..3 = V, A0, A1, A2)
+// Between layers each thread reads ITS row of the accumulator (tcgen05.ld 32x32b), applies ReLU, splits and
+// stores the row as the next A operand.  Operands use the no-swizzle K-major canonical layout stored as
+// [K/8][rows][8 halves]: a thread's 16-byte chunk stores are contiguous across the warp (conflict-free) and the
+// descriptor strides are LBO = rows*16 B (next K chunk), SBO = 128 B (next 8-row core matrix).
+// L1 of both players is issued together; then player A's L2/L3 chain runs, then B's, sharing one H tile.
+// Both players' fp32 weight blobs arrive by one TMA bulk copy each (cp.async.bulk + mbarrier) into a staging
+// area and are converted once per launch into fp16 B-operand tiles that stay in shared memory for all k steps.
+// Env state, observations and bookkeeping never leave registers (same step_and_book as the CUDA-core kernel).
+#include <cuda_fp16.h>
+
+#include "pp_host.h"
+#include "pp_rollout.cuh"
+#include "tc_ptx.cuh"
+
+namespace pp {
+
+namespace {
+
+constexpr int G_ROWS = 128;                    // envs per group
+constexpr int CTA_GROUPS = 4;
+constexpr int TC_THREADS = G_ROWS * CTA_GROUPS;
+constexpr uint32_t A_LBO = G_ROWS * 16;        // A tiles are [K/8][128][16 B]
+constexpr uint32_t SBO = 128;
+
+// per-player weight tiles (bytes); every B tile is [K/8][N][16 B]; *H = fp16(w), *L = fp16(w - fp16(w))
+constexpr uint32_t W1_BYTES = 2 * 64 * 16, W2_BYTES = 8 * 64 * 16, B2_BYTES = 2 * 64 * 16, W3_BYTES = 8 * 16 * 16,
+                   B3_BYTES = 2 * 16 * 16;
+constexpr uint32_t W1H_OFF = 0, W1L_OFF = W1H_OFF + W1_BYTES, W2H_OFF = W1L_OFF + W1_BYTES, W2L_OFF = W2H_OFF + W2_BYTES,
+                   B2_OFF = W2L_OFF + W2_BYTES, W3H_OFF = B2_OFF + B2_BYTES, W3L_OFF = W3H_OFF + W3_BYTES,
+                   B3_OFF = W3L_OFF + W3_BYTES, PLAYER_W_BYTES = B3_OFF + B3_BYTES;              // 27136
+constexpr uint32_t X_BYTES = 2 * G_ROWS * 16, H_HALF = 8 * G_ROWS * 16, H_BYTES = 2 * H_HALF;    // 4096, 16384, 32768
+constexpr uint32_t GROUP_BYTES = 2 * X_BYTES + H_BYTES;                                          // 40960
+constexpr uint32_t BLOB_BYTES = PP_QNET_BLOB_FLOATS * 4;                                         // 19728
+
+template <int GROUPS> struct SmemMap {
+    static constexpr uint32_t W = 0;                                        // [2 players][PLAYER_W_BYTES]
+    static constexpr uint32_t GROUPS_OFF = 2 * PLAYER_W_BYTES;              // [GROUPS][GROUP_BYTES]; start: blob staging
+    static constexpr uint32_t CTRL = GROUPS_OFF + (GROUPS * GROUP_BYTES > 2 * BLOB_BYTES ? GROUPS * GROUP_BYTES : 2 * BLOB_BYTES);
+    static constexpr uint32_t TOTAL = CTRL + 64;                            // mbarriers + TMEM base
+};
+
+struct PlayerTiles {     // shared-memory (generic) pointers of one player's operands
+    uint8_t *w, *x, *h;
+};
+
+__device__ __forceinline__ float h2f(uint32_t packed, int hi) {
+    const __half2 v = *reinterpret_cast<const __half2 *>(&packed);
+    return hi ? __high2float(v) : __low2float(v);
+}
+
+// fp32 blob (staging) -> fp16 hi / lo B-operand tiles of one player.  All threads of the CTA.
+__device__ void build_weight_tiles(uint8_t *wt, const float *blob, int tid, int nthreads) {
+    auto H = [&](uint32_t off) { return reinterpret_cast<__half *>(wt + off); };
+    auto hi = [](float v) { return __float2half_rn(v); };
+    auto lo = [](float v) { return __float2half_rn(v - __half2float(__float2half_rn(v))); };
+    const __half zero = __float2half_rn(0.0f);
+    for (int idx = tid; idx < 2 * 64 * 8; idx += nthreads) {                 // [2][64][8]: k = 0..15
+        const int k = (idx >> 9) * 8 + (idx & 7), nn = (idx >> 3) & 63;
+        const bool bias_row = (k & 7) == 7;
+        const float w1 = bias_row ? 0.0f : blob[PP_QNET_W1T + (k & 7) * 64 + nn];
+        const float b1 = blob[PP_QNET_B1 + nn], b2v = blob[PP_QNET_B2 + nn];
+        H(W1H_OFF)[idx] = bias_row ? (k == 7 ? hi(b1) : lo(b1)) : hi(w1);      // obs_hi and obs_lo both meet W1_hi
+        H(W1L_OFF)[idx] = (!bias_row && k < 7) ? lo(w1) : zero;                // obs_hi * W1_lo
+        H(B2_OFF)[idx] = bias_row ? (k == 7 ? hi(b2v) : lo(b2v)) : zero;       // rides on X's ones columns 7, 15
+    }
+    for (int idx = tid; idx < 8 * 64 * 8; idx += nthreads) {                 // W2 [8][64][8]
+        const int k = (idx >> 9) * 8 + (idx & 7), nn = (idx >> 3) & 63;
+        const float w = blob[PP_QNET_W2T + k * 64 + nn];
+        H(W2H_OFF)[idx] = hi(w);
+        H(W2L_OFF)[idx] = lo(w);
+    }
+    for (int idx = tid; idx < 8 * 16 * 8; idx += nthreads) {                 // heads [8][16][8], columns 0..3 used
+        const int k = (idx >> 7) * 8 + (idx & 7), nn = (idx >> 3) & 15;
+        const float w = nn < 4 ? blob[PP_QNET_WHT + k * 4 + nn] : 0.0f;
+        H(W3H_OFF)[idx] = hi(w);
+        H(W3L_OFF)[idx] = lo(w);
+    }
+    for (int idx = tid; idx < 2 * 16 * 8; idx += nthreads) {                 // head biases [2][16][8]
+        const int k = (idx >> 7) * 8 + (idx & 7), nn = (idx >> 3) & 15;
+        const float bv = nn < 4 ? blob[PP_QNET_BH + nn] : 0.0f;
+        H(B3_OFF)[idx] = (k & 7) == 7 ? (k == 7 ? hi(bv) : lo(bv)) : zero;
+    }
+}
+
+// this thread's row of X = [obs_hi(7) 1 | obs_lo(7) 1]
+__device__ __forceinline__ void write_x_row(uint8_t *x, int row, const float (&o)[7]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = o[2 * j], b = j < 3 ? o[2 * j + 1] : 1.0f;
+        hi[j] = tc::pack_f16x2<false>(a, b);
+        const float ra = a - h2f(hi[j], 0), rb = j < 3 ? b - h2f(hi[j], 1) : 1.0f;
+        lo[j] = tc::pack_f16x2<false>(ra, rb);
+    }
+    *reinterpret_cast<uint4 *>(x + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4 *>(x + A_LBO + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// 8 accumulator columns -> ReLU -> (hi, lo) fp16 chunks of this thread's row
+__device__ __forceinline__ void split_store8(const uint32_t *r, uint8_t *h, int chunk, int row) {
+    uint32_t p[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = fmaxf(__uint_as_float(r[2 * j]), 0.0f), b = fmaxf(__uint_as_float(r[2 * j + 1]), 0.0f);
+        p[j] = tc::pack_f16x2<false>(a, b);
+        q[j] = tc::pack_f16x2<false>(a - h2f(p[j], 0), b - h2f(p[j], 1));
+    }
+    *reinterpret_cast<uint4 *>(h + chunk * A_LBO + row * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+    *reinterpret_cast<uint4 *>(h + H_HALF + chunk * A_LBO + row * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+}
+
+// accumulator row (64 fp32 columns at taddr) -> ReLU -> hi/lo fp16 -> this thread's row of the next A tiles
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *h, int row) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t r0[16], r1[16];
+        tc::tmem_ld16(taddr + half * 32, r0);
+        tc::tmem_ld16(taddr + half * 32 + 16, r1);
+        tc::tmem_ld_wait();
+        split_store8(r0, h, half * 4 + 0, row);
+        split_store8(r0 + 8, h, half * 4 + 1, row);
+        split_store8(r1, h, half * 4 + 2, row);
+        split_store8(r1 + 8, h, half * 4 + 3, row);
+    }
+}
+
+// MMA batches, issued by one thread per group
+__device__ __forceinline__ void issue_l1(uint32_t d, const PlayerTiles &p) {
+    const uint64_t x = tc::smem_desc(tc::smem_u32(p.x), A_LBO, SBO);
+    tc::umma_f16(d, x, tc::smem_desc(tc::smem_u32(p.w + W1H_OFF), 64 * 16, SBO), tc::idesc_f16(128, 64), false);
+    tc::umma_f16(d, x, tc::smem_desc(tc::smem_u32(p.w + W1L_OFF), 64 * 16, SBO), tc::idesc_f16(128, 64), true);
+}
+// D = Hh*Wh + Hl*Wh + Hh*Wl + X*B'   (N = 64 hidden layer or N = 16 heads)
+template <int N>
+__device__ __forceinline__ void issue_dense(uint32_t d, const PlayerTiles &p, uint32_t wh_off, uint32_t wl_off, uint32_t b_off) {
+    const uint32_t hh = tc::smem_u32(p.h), hl = hh + H_HALF, wh = tc::smem_u32(p.w + wh_off), wl = tc::smem_u32(p.w + wl_off);
+    constexpr uint32_t B_LBO = N * 16;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = pass == 1 ? hl : hh, b = pass == 2 ? wl : wh;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            tc::umma_f16(d, tc::smem_desc(a + j * 2 * A_LBO, A_LBO, SBO), tc::smem_desc(b + j * 2 * B_LBO, B_LBO, SBO),
+                         tc::idesc_f16(128, N), (pass | j) != 0);
+    }
+    tc::umma_f16(d, tc::smem_desc(tc::smem_u32(p.x), A_LBO, SBO), tc::smem_desc(tc::smem_u32(p.w + b_off), B_LBO, SBO),
+                 tc::idesc_f16(128, N), true);
+}
+
+__device__ __forceinline__ void dueling_q(uint32_t taddr, float (&q)[3]) {      // V + (A - mean(A))  models/qnet.py:75
+    uint32_t r[4];
+    tc::tmem_ld4(taddr, r);
+    tc::tmem_ld_wait();
+    const float v = __uint_as_float(r[0]), a0 = __uint_as_float(r[1]), a1 = __uint_as_float(r[2]), a2 = __uint_as_float(r[3]);
+    const float mean = __fdiv_rn(__fadd_rn(__fadd_rn(a0, a1), a2), 3.0f);
+    q[0] = __fadd_rn(v, __fsub_rn(a0, mean));
+    q[1] = __fadd_rn(v, __fsub_rn(a1, mean));
+    q[2] = __fadd_rn(v, __fsub_rn(a2, mean));
+}
+
+// Shared prologue: barriers, TMEM, weights.  Returns the TMEM base of the CTA.
+template <int GROUPS>
+__device__ __forceinline__ uint32_t tc_prologue(uint8_t *smem, const PPPolicy &pol_a, const PPPolicy &pol_b) {
+    using M = SmemMap<GROUPS>;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + M::CTRL);           // [0] weights, [1 + g] group g
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + M::CTRL + 32);
+    const int tid = threadIdx.x;
+    const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
+    if (tid == 0) {
+        for (int b = 0; b < 1 + GROUPS; ++b) tc::mbar_init(bars + b, 1);
+        tc::fence_mbar_init();
+    }
+    if (tid < 32) tc::tmem_alloc<GROUPS * 128>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    uint8_t *stage = smem + M::GROUPS_OFF;
+    if (tid == 0 && (qa || qb)) {
+        tc::mbar_expect_tx(bars, (qa ? BLOB_BYTES : 0) + (qb ? BLOB_BYTES : 0));
+        if (qa) tc::tma_bulk_g2s(stage, pol_a.weights, BLOB_BYTES, bars);
+        if (qb) tc::tma_bulk_g2s(stage + BLOB_BYTES, pol_b.weights, BLOB_BYTES, bars);
+    }
+    if (qa || qb) tc::mbar_wait(bars, 0);
+    if (qa) build_weight_tiles(smem + M::W, reinterpret_cast<const float *>(stage), tid, GROUPS * G_ROWS);
+    if (qb) build_weight_tiles(smem + M::W + PLAYER_W_BYTES, reinterpret_cast<const float *>(stage + BLOB_BYTES), tid, GROUPS * G_ROWS);
+    tc::fence_proxy_async();
+    __syncthreads();                              // staging (aliases the group tiles) is dead from here on
+    return tmem;
+}
+
+template <int GROUPS> __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc<GROUPS * 128>(tmem);
+}
+
+// One policy evaluation round for a group: X rows are already written.  Returns greedy Q of both players.
+struct GroupCtx {
+    PlayerTiles pa, pb;
+    uint64_t *bar;
+    uint32_t parity, d_a, d_b, bar_id, lane_addr;
+    int row;
+    bool qa, qb;
+};
+
+__device__ __forceinline__ void group_wait(GroupCtx &g) {
+    tc::mbar_wait(g.bar, g.parity);
+    g.parity ^= 1u;
+    tc::tc_fence_after();
+}
+
+// after the barrier that published the X rows: L1 (both players) -> per player: H1 -> L2 -> H2 -> L3 -> Q
+__device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
+    const bool issuer = g.row == 0;
+    if (issuer) {
+        tc::tc_fence_after();
+        if (g.qa) issue_l1(g.d_a, g.pa);
+        if (g.qb) issue_l1(g.d_b, g.pb);
+        tc::umma_commit(g.bar);
+    }
+    __syncwarp();
+    group_wait(g);
+#pragma unroll 1
+    for (int pl = 0; pl < 2; ++pl) {
+        if (!(pl ? g.qb : g.qa)) continue;
+        const PlayerTiles &p = pl ? g.pb : g.pa;
+        const uint32_t d = pl ? g.d_b : g.d_a;
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+            hidden_epilogue(d + g.lane_addr, p.h, g.row);
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            tc::bar_sync(g.bar_id, G_ROWS);
+            if (issuer) {
+                tc::tc_fence_after();
+                if (layer == 0) issue_dense<64>(d, p, W2H_OFF, W2L_OFF, B2_OFF);
+                else issue_dense<16>(d, p, W3H_OFF, W3L_OFF, B3_OFF);
+                tc::umma_commit(g.bar);
+            }
+            __syncwarp();
+            group_wait(g);
+        }
+        if (pl) dueling_q(d + g.lane_addr, q_b); else dueling_q(d + g.lane_addr, q_a);
+    }
+}
+
+__device__ __forceinline__ GroupCtx make_group(uint8_t *smem, uint32_t groups_off, uint32_t ctrl_off, uint32_t tmem, int grp,
+                                               int row, bool qa, bool qb) {
+    GroupCtx g;
+    uint8_t *gb = smem + groups_off + grp * GROUP_BYTES;
+    g.pa = PlayerTiles{smem, gb, gb + 2 * X_BYTES};                                // the H tile is shared: the
+    g.pb = PlayerTiles{smem + PLAYER_W_BYTES, gb + X_BYTES, gb + 2 * X_BYTES};    // players' chains run one after the other
+    g.bar = reinterpret_cast<uint64_t *>(smem + ctrl_off) + 1 + grp;
+    g.parity = 0;
+    g.d_a = tmem + grp * 128;
+    g.d_b = tmem + grp * 128 + 64;
+    g.bar_id = 1 + grp;
+    g.lane_addr = (uint32_t)((row >> 5) * 32) << 16;
+    g.row = row;
+    g.qa = qa; g.qb = qb;
+    return g;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------- standalone action selection
+// obs[n][7] -> Q -> action for ONE player (as player A of a one-group CTA); the debugging and Q-parity vehicle.
+__global__ void __launch_bounds__(G_ROWS)
+qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol, uint64_t seed, uint32_t step_index,
+                   int64_t env_id_base, uint32_t stream_id, uint8_t *__restrict__ actions, float *__restrict__ q_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    using M = SmemMap<1>;
+    PPPolicy none = pol;
+    none.kind = PP_POLICY_RANDOM;
+    const uint32_t tmem = tc_prologue<1>(smem, pol, none);
+    const int row = threadIdx.x;
+    GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, 0, row, true, false);
+    for (int64_t tile0 = (int64_t)blockIdx.x * G_ROWS; tile0 < n; tile0 += (int64_t)gridDim.x * G_ROWS) {
+        const int64_t i = tile0 + row;
+        float o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (i < n) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) o[k] = obs[i * 7 + k];
+        }
+        write_x_row(g.pa.x, row, o);
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        tc::bar_sync(g.bar_id, G_ROWS);
+        float q[3], unused[3];
+        group_forward(g, q, unused);
+        if (i < n) {
+            int a = argmax3(q);
+            a = explore(a, pol.eps_threshold, seed, (uint32_t)(env_id_base + i), step_index, stream_id);
+            actions[i] = (uint8_t)a;
+            if (q_out) { q_out[i * 3 + 0] = q[0]; q_out[i * 3 + 1] = q[1]; q_out[i * 3 + 2] = q[2]; }
+        }
+    }
+    tc_epilogue<1>(tmem);
+}
+
+// --------------------------------------------------------------------------------- fused self-play rollout
+// Work is split in units of warps (32 envs): `n_chunks` chunks of at most 16 warps, balanced to within one warp, so
+// every SM issues the same number of warp-steps whatever n is.  A CTA walks chunks blockIdx.x, + gridDim.x, ...
+template <typename R>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_steps, const PPPolicy pol_a,
+                   const PPPolicy pol_b, uint64_t seed, int64_t step_base, const PPServeSource src, int32_t quota,
+                   int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    using M = SmemMap<CTA_GROUPS>;
+    const uint32_t tmem = tc_prologue<CTA_GROUPS>(smem, pol_a, pol_b);
+    const int grp = threadIdx.x >> 7, row = threadIdx.x & 127, gw = row >> 5, lane = threadIdx.x & 31;
+    const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
+    GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, grp, row, qa, qb);
+    const EnvConsts<R> c(params);
+    const StatePtrs<R> s(st);
+    const int64_t total_warps = (n + 31) / 32;
+    const int64_t ring_t0 = ring_first_step(ring, n, k_steps);
+    Tally total;
+
+#pragma unroll 1
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t w_lo = chunk * total_warps / n_chunks, w_hi = (chunk + 1) * total_warps / n_chunks;
+        const int nw = (int)(w_hi - w_lo), base = nw / CTA_GROUPS, rem = nw % CTA_GROUPS;
+        const int my_warps = base + (grp < rem ? 1 : 0);                       // groups differ by at most one warp
+        if (my_warps == 0) continue;                                           // uniform per group
+        const int64_t i = (w_lo + grp * base + (grp < rem ? grp : rem) + gw) * 32 + lane;
+        const bool valid = gw < my_warps && i < n;
+        const int64_t ic = valid ? i : 0;
+        Lane<R> L;
+        L.e = load_env<R>(s, ic);
+        L.ep_idx = s.ep_idx[ic]; L.ep_len = s.ep_len[ic];
+        const uint32_t gid = (uint32_t)(env_id_base + ic);
+
+#pragma unroll 1
+        for (int64_t t = 0; t < k_steps; ++t) {
+            const bool active = valid && !(quota > 0 && L.ep_idx >= quota);
+            const uint32_t step = (uint32_t)(step_base + t);
+            float oa[7], ob[7];
+            observe<R>(L.e, oa, ob);
+            if (qa) write_x_row(g.pa.x, row, oa);
+            if (qb) write_x_row(g.pb.x, row, ob);
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            if (!tc::bar_red_or(g.bar_id, G_ROWS, active)) break;             // whole group frozen by the quota: for good
+            float q_a[3] = {0.f, 0.f, 0.f}, q_b[3] = {0.f, 0.f, 0.f};
+            if (qa || qb) group_forward(g, q_a, q_b);
+            int act_a, act_b;
+            if (pol_a.kind == PP_POLICY_RANDOM) act_a = random_action(seed, gid, step, STREAM_ACT_A);
+            else act_a = explore(qa ? argmax3(q_a) : follower_action(oa, pol_a.follower_tol), pol_a.eps_threshold, seed, gid, step, STREAM_ACT_A);
+            if (pol_b.kind == PP_POLICY_RANDOM) act_b = random_action(seed, gid, step, STREAM_ACT_B);
+            else act_b = explore(qb ? argmax3(q_b) : follower_action(ob, pol_b.follower_tol), pol_b.eps_threshold, seed, gid, step, STREAM_ACT_B);
+            if (gw < my_warps)        // warp-uniform: warps without envs skip the bookkeeping collectives entirely
+                step_and_book<R>(c, params, L, valid, active, act_a, act_b, ob, t, n, i, env_id_base, src, quota, out, ring,
+                                 ring.head != nullptr && t >= ring_t0);
+        }
+        if (valid) {
+            store_env<R>(s, i, L.e);
+            s.ep_idx[i] = L.ep_idx;
+            s.ep_len[i] = L.ep_len;
+        }
+        total.steps += L.tally.steps; total.episodes += L.tally.episodes; total.wins_a += L.tally.wins_a;
+        total.wins_b += L.tally.wins_b; total.pts_a += L.tally.pts_a; total.pts_b += L.tally.pts_b;
+        total.hits += L.tally.hits; total.len_sum += L.tally.len_sum;
+    }
+    if (out.counters) total.flush(out.counters);
+    tc_epilogue<CTA_GROUPS>(tmem);
+}
+
+// --------------------------------------------------------------------------------- launchers
+static int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sms = 148;
+    }
+    return sms;
+}
+
+int qnet_act_tc_launch(int64_t n, const float *obs, const PPPolicy &pol, uint64_t seed, int64_t step_index,
+                       int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out, cudaStream_t stream) {
+    constexpr int smem = (int)SmemMap<1>::TOTAL;
+    cudaError_t err = cudaFuncSetAttribute(qnet_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return (int)err;
+    const int64_t tiles = (n + G_ROWS - 1) / G_ROWS;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+    qnet_act_tc_kernel<<<blocks, G_ROWS, smem, stream>>>(n, obs, pol, seed, (uint32_t)step_index, env_id_base,
+                                                        (uint32_t)stream_id, actions, q_out);
+    return (int)cudaGetLastError();
+}
+
+int selfplay_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
+                       const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
+                       int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream) {
+    constexpr int smem = (int)SmemMap<CTA_GROUPS>::TOTAL;
+    PPReplayRing r{};
+    if (ring) r = *ring;
+    const int64_t total_warps = (n + 31) / 32;
+    const int64_t slots = (int64_t)sm_count();                                   // resident CTAs: 1 per SM
+    // chunks of <= 16 warps; a whole number of rounds over the resident CTAs once there is more than one round
+    int64_t n_chunks = (total_warps + CTA_GROUPS - 1) / CTA_GROUPS;              // small n: about 1 warp per group
+    if (n_chunks > slots) {
+        const int64_t rounds = (total_warps + slots * 16 - 1) / (slots * 16);
+        n_chunks = rounds * slots;
+    }
+    const unsigned blocks = (unsigned)(n_chunks < slots ? n_chunks : slots);
+    cudaError_t err;
+    if (mode == PP_MODE_F64) {
+        if ((err = cudaFuncSetAttribute(selfplay_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)err;
+        selfplay_tc_kernel<double><<<blocks, TC_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
+                                                                        env_id_base, out, r, n_chunks);
+    } else {
+        if ((err = cudaFuncSetAttribute(selfplay_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)err;
+        selfplay_tc_kernel<float><<<blocks, TC_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
+                                                                       env_id_base, out, r, n_chunks);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pp

@@ -176,7 +176,7 @@ class Policy:
 
     def __init__(self, kind, weights=None, eps=0.0, precision="f32", tol=0.02, device="cuda", num_envs=None):
         self.kind, self.eps, self.tol = kind, float(eps), float(tol)
-        self.precision = {"f32": _lib.PREC_F32, "bf16": _lib.PREC_BF16}[precision]
+        self.precision = {"f32": _lib.PREC_F32, "f16": _lib.PREC_F16}[precision]
         self.device = torch.device(device)
         self.weights = None if weights is None else weights.to(self.device, torch.float32).contiguous()
         self.h = self.c = None

@@ -132,7 +132,7 @@ class SelfPlayEngine:
 
 
 def host_selfplay_eval(env_kwargs: dict, n: int, quota: int, pool, weights_a, weights_b, mode="f64", chunk=64,
-                       max_steps=1 << 20, ep_log_cap=0):
+                       max_steps=1 << 20, ep_log_cap=0, precision="f32"):
     """eval_vs_model for n envs x quota episodes from HOST buffers through the C ABI (pp_host_selfplay_eval):
     serves [quota, n] x3 and the two packed QNet blobs are numpy arrays; returns (counters dict, ep_log)."""
     lib = _lib.load()
@@ -146,6 +146,7 @@ def host_selfplay_eval(env_kwargs: dict, n: int, quota: int, pool, weights_a, we
     log = np.zeros((max(ep_log_cap, 1), 4), np.int32) if ep_log_cap else None
     vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     _lib.check(lib.pp_host_selfplay_eval(_lib.MODE_F64 if mode == "f64" else _lib.MODE_F32, n, quota, C.byref(params),
-                                         vp(pvx), vp(pvy), vp(psp), vp(wa), vp(wb), _lib.PREC_F32, chunk, max_steps,
+                                         vp(pvx), vp(pvy), vp(psp), vp(wa), vp(wb),
+                                         {"f32": _lib.PREC_F32, "f16": _lib.PREC_F16}[precision], chunk, max_steps,
                                          vp(counters), vp(log), ep_log_cap), "pp_host_selfplay_eval")
     return dict(zip(COUNTER_NAMES, (int(v) for v in counters))), log

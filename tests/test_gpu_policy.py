@@ -114,3 +114,43 @@ def test_qnetrnn_partial_reset_mask_and_larger_batch():
         wq, _ = po.qnetrnn_forward(w, obs, h, c)
         assert np.abs(gu.np_of(q) - wq).max() <= 2e-6 * max(1.0, np.abs(wq).max()), t
     assert np.abs(gu.np_of(pol.h).T - h).max() < 2e-6 and np.abs(gu.np_of(pol.c).T - c).max() < 4e-6
+
+
+# ------------------------------------------------------------------------------------------ tensor-core path
+@pytest.mark.parametrize("name", ["seed0", "seed1", "ckpt_model5_1_fault_B"])
+@pytest.mark.parametrize("noisy", [False, True])
+def test_qnet_act_tensor_core_path_within_1e3_of_reference(qg, name, noisy):
+    """PP_PREC_F16 (tcgen05, fp16 operands, fp32 accumulation): Q within 1e-3 of the torch reference (north_star
+    tolerance for the reduced-precision path) and of the fp32 oracle; greedy action equal wherever the reference's
+    top-2 gap exceeds the tolerance."""
+    sd = gu.golden_sd(qg, name)
+    pol = pp.Policy.qnet(sd, noisy=noisy, precision="f16")
+    obs = torch.from_numpy(qg["obs"]).cuda()
+    act, q = pp.qnet_act(obs, pol, want_q=True)
+    q, act = gu.np_of(q), gu.np_of(act)
+    ref = qg[f"{name}/q_{'train' if noisy else 'eval'}"]
+    wq, wa = po.qnet_forward(po.qnet_weights_from_state_dict(sd, noisy=noisy), qg["obs"])
+    err = np.abs(q - ref).max()
+    print(f"tensor-core QNet {name} noisy={noisy}: max |dQ| = {err:.3e} (|Q| max {np.abs(ref).max():.2f})")
+    assert err <= 1e-3 and np.abs(q - wq).max() <= 1e-3
+    srt = np.sort(ref, axis=1)
+    clear = (srt[:, 2] - srt[:, 1]) > 2e-3
+    assert clear.mean() > 0.9 and np.array_equal(act[clear], ref.argmax(1)[clear])
+    assert (act == wa).mean() > 0.99
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 1000, 70001])
+def test_qnet_act_tensor_core_ragged_sizes_and_large_inputs(qg, n):
+    sd = gu.golden_sd(qg, "seed1")
+    pol = pp.Policy.qnet(sd, precision="f16")
+    rs = np.random.RandomState(n)
+    obs = rs.uniform(-1, 1, size=(n, 7)).astype(np.float32)
+    obs[:, 6] *= 40                                            # spin after hard hits
+    if n >= 1000:
+        obs[:7] = 0; obs[:7, :][np.arange(7), np.arange(7)] = 3e5        # beyond fp16 range: saturates, stays finite
+    act, q = pp.qnet_act(torch.from_numpy(obs).cuda(), pol, want_q=True)
+    q = gu.np_of(q)
+    wq, wa = po.qnet_forward(po.qnet_weights_from_state_dict(sd), obs)
+    assert np.isfinite(q).all()
+    lo = 7 if n >= 1000 else 0
+    assert np.abs(q[lo:] - wq[lo:]).max() <= 1e-3 * max(1.0, np.abs(wq[lo:]).max())

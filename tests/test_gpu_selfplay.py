@@ -150,17 +150,103 @@ def test_replay_scatter_compacts_valid_rows_and_wraps(n, cap):
     done = (rs.rand(n) < 0.1).astype(np.uint8); valid = (rs.rand(n) < 0.7).astype(np.uint8)
     ring = pp.ReplayRing(cap)
     ring.scatter(obs, act, rew, nxt, done, valid)
-    k = int(valid.sum())
-    assert int(ring.head.item()) == k
-    if k <= cap:
-        got = _sorted_rows(gu.np_of(ring.obs[:k]), gu.np_of(ring.act[:k]), gu.np_of(ring.rew[:k]),
-                           gu.np_of(ring.next_obs[:k]), gu.np_of(ring.done[:k]))
-        v = valid.astype(bool)
-        assert np.array_equal(got, _sorted_rows(obs[v], act[v], rew[v], nxt[v], done[v]))
-    ring.scatter(obs, act, rew, nxt, done)                     # all rows valid, wraps when n + k > cap
-    assert int(ring.head.item()) == k + n and len(ring) == min(k + n, cap)
+    # a batch larger than the ring keeps what sequential pushes would: among its last `cap` rows, the valid ones
+    v = valid.astype(bool) & (np.arange(n) >= n - cap)
+    k = int(v.sum())
+    assert int(ring.head.item()) == k and k <= cap
+    got = _sorted_rows(gu.np_of(ring.obs[:k]), gu.np_of(ring.act[:k]), gu.np_of(ring.rew[:k]),
+                       gu.np_of(ring.next_obs[:k]), gu.np_of(ring.done[:k]))
+    assert np.array_equal(got, _sorted_rows(obs[v], act[v], rew[v], nxt[v], done[v]))
+    ring.scatter(obs, act, rew, nxt, done)                     # all rows valid; wraps when k + min(n, cap) > cap
+    m = min(n, cap)
+    assert int(ring.head.item()) == k + m and len(ring) == min(k + m, cap)
     rows = _sorted_rows(obs, act, rew, nxt, done)
     live = _sorted_rows(gu.np_of(ring.obs[:len(ring)]), gu.np_of(ring.act[:len(ring)]), gu.np_of(ring.rew[:len(ring)]),
                         gu.np_of(ring.next_obs[:len(ring)]), gu.np_of(ring.done[:len(ring)]))
     present = {r.tobytes() for r in rows}
     assert all(r.tobytes() in present for r in live)           # every slot holds one complete pushed row
+    if n >= cap:                                               # the ring now holds exactly the last `cap` rows
+        assert np.array_equal(live, _sorted_rows(obs[n - cap:], act[n - cap:], rew[n - cap:], nxt[n - cap:], done[n - cap:]))
+
+
+def test_selfplay_ring_smaller_than_launch_keeps_last_steps(H, nets):
+    """capacity < n * k: only the last capacity / n lock-step steps are written, every slot a complete row."""
+    cfg = H["env_config_yaml"]
+    n, K = 512, 40
+    pool = gu.make_pool(3, n, 4, cfg, "f64")
+    env = pp.VecPongEnv2P(n, mode="f64", serve=pool, **cfg)
+    env.reset()
+    b = gu.oracle_batch_like(env, "f64")
+    ga, oa = _mk(("random", None, 0.0), nets, 0)
+    gb, ob = _mk(("qnet", "seed0", 0.1), nets, 1)
+    ring = pp.ReplayRing(n * 10 + 100)
+    pp.SelfPlayEngine(env, ga, gb, seed=5).run(K, ring=ring)
+    w = po.selfplay(po.make_params(cfg), b, oa, ob, K, pool, seed=5, replay_cap=n * K)["replay"]
+    assert int(ring.head.item()) == n * 10
+    last = {k: v[n * (K - 10):] for k, v in w.items()}
+    got = _sorted_rows(gu.np_of(ring.obs[:n * 10]), gu.np_of(ring.act[:n * 10]), gu.np_of(ring.rew[:n * 10]),
+                       gu.np_of(ring.next_obs[:n * 10]), gu.np_of(ring.done[:n * 10]))
+    assert np.array_equal(got, _sorted_rows(last["obs"], last["act"], last["rew"], last["next"], last["done"]))
+    with pytest.raises(pp.PongB200Error):
+        pp.SelfPlayEngine(env, ga, gb).run(2, ring=pp.ReplayRing(n - 1))
+
+
+# ------------------------------------------------------------------------------------------ tensor-core path
+@pytest.mark.parametrize("mode", ["f64", "f32"])
+@pytest.mark.parametrize("n", [1000, 5000])
+def test_selfplay_tensor_core_env_bit_exact_under_its_own_actions(H, nets, mode, n):
+    """PP_PREC_F16 fused kernel.  Actions come from reduced-precision Q-values, so they may differ from the oracle's
+    at near-ties; everything else must not: replaying the kernel's own action stream through the oracle env gives
+    the same state, counters and episode log bit for bit, and the actions agree with the fp32 oracle on the same
+    observations except at near-ties."""
+    cfg = H["env_config_yaml"]
+    K, depth, seed = 200, 6, 99
+    pool = gu.make_pool(21, n, depth, cfg, mode)
+    env = pp.VecPongEnv2P(n, mode=mode, serve=pool, env_id_base=123, **cfg)
+    env.reset()
+    b = gu.oracle_batch_like(env, mode)
+    b2 = b.copy()
+    pa = pp.Policy.qnet(nets["seed0"], precision="f16")
+    pb = pp.Policy.qnet(nets["ckpt_model5_1_fault_B"], eps=0.1, precision="f16")
+    eng = pp.SelfPlayEngine(env, pa, pb, seed=seed)
+    ring = pp.ReplayRing(n * K)
+    got = eng.run(K, ring=ring, log_cap=1 << 16, want_actions=True)
+    acts = gu.np_of(got["actions"])
+    want = po.rollout(po.make_params(cfg), b, acts, pool, env_id_base=123, log_cap=1 << 16)
+    gu.assert_state_equal(env, b)
+    assert np.array_equal(gu.np_of(env.counters), want["counters"]) and want["counters"][1] > 50
+    key = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]
+    assert np.array_equal(key(gu.np_of(got["ep_log"])[:env.ep_log_count()]), key(want["ep_log"]))
+    assert int(ring.head.item()) == n * K
+    # closed-loop fp32 oracle from the same start: until the first disagreement per env the actions must be equal
+    oa = _oracle_policy(po.POLICY_QNET, nets["seed0"]); ob = _oracle_policy(po.POLICY_QNET, nets["ckpt_model5_1_fault_B"], eps=0.1)
+    w = po.selfplay(po.make_params(cfg), b2, oa, ob, K, pool, seed=seed, env_id_base=123, want_actions=True)
+    same = (acts == w["actions"]).all(axis=2)                  # [K, n]
+    first_diff = np.where(same.all(axis=0), K, np.argmin(same, axis=0))
+    agree = first_diff.sum() / (K * n)
+    print(f"tensor-core closed loop: {100 * agree:.2f}% of env-steps before the first action disagreement")
+    assert agree > 0.9
+
+
+def test_selfplay_tensor_core_mixed_players_and_win_rates(H, nets):
+    """Follower / random opponents on the tensor-core path, and outcome statistics equal to the fp32 path's within
+    sampling noise (same serves, greedy QNets)."""
+    cfg = H["env_config_yaml"]
+    n, quota = 4096, 4
+    pool = gu.make_pool(6, n, quota, cfg, "f64")
+    res = {}
+    for prec in ("f32", "f16"):
+        env = pp.VecPongEnv2P(n, mode="f64", serve=pool, **cfg)
+        eng = pp.SelfPlayEngine(env, pp.Policy.qnet(nets["seed0"], precision=prec), pp.Policy.qnet(nets["seed1"], precision=prec), seed=3)
+        res[prec] = eng.evaluate(quota, chunk=96)
+        assert res[prec]["episodes"] == n * quota
+    assert abs(res["f32"]["win_rate_b"] - res["f16"]["win_rate_b"]) < 0.02
+    assert abs(res["f32"]["env_steps"] - res["f16"]["env_steps"]) < 0.03 * res["f32"]["env_steps"]
+    for a in (pp.Policy.follower(), pp.Policy.random()):
+        env = pp.VecPongEnv2P(n, mode="f64", serve=pool, **cfg)
+        env.reset()
+        b = gu.oracle_batch_like(env, "f64")
+        got = pp.SelfPlayEngine(env, a, pp.Policy.qnet(nets["seed1"], precision="f16"), seed=4).run(50, want_actions=True)
+        want = po.rollout(po.make_params(cfg), b, gu.np_of(got["actions"]), pool)
+        gu.assert_state_equal(env, b)
+        assert np.array_equal(gu.np_of(env.counters), want["counters"])
