@@ -143,8 +143,12 @@ def test_gloo_world_size_2_counters_and_grad_allreduce(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
     env = dict(os.environ, PP_ROOT=ROOT, OMP_NUM_THREADS="1")
+    import socket
+    with socket.socket() as sock:                      # a free rendezvous port (parallel test runs must not collide)
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok 0" in r.stdout and "ok 1" in r.stdout
