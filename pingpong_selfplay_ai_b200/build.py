@@ -66,7 +66,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), dep_t):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        extra = os.environ.get("PP_EXTRA_NVCC_FLAGS", "").split()          # e.g. -DPP_TC_TIMING for phase timers
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

@@ -143,7 +143,7 @@ int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, 
                         const PPServeSource *serve, int32_t quota, int64_t env_id_base, const PPRolloutOut *out,
                         const PPReplayRing *ring, void *stream) {
     if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_selfplay_rollout");
-    if (n < 0 || k < 0) return fail(PP_E_SIZE, "pp_selfplay_rollout");
+    if (n < 0 || k < 0 || k > 0x7fffffff) return fail(PP_E_SIZE, "pp_selfplay_rollout");
     if (!params_ok(params)) return fail(PP_E_PARAM, "pp_selfplay_rollout");
     if (!state_ok(state, true) || !serve_ok(serve) || !out_ok(out)) return fail(PP_E_NULL, "pp_selfplay_rollout");
     if (!policy_ok(policy_a, false) || !policy_ok(policy_b, false)) return fail(PP_E_MODE, "pp_selfplay_rollout");

@@ -210,6 +210,10 @@ struct Tally {
         pts_b += (flags & F_POINT_B) ? 1u : 0u;
         hits += (flags & F_HIT) ? 1u : 0u;
     }
+    __device__ __forceinline__ void add(const Tally &o) {
+        steps += o.steps; episodes += o.episodes; wins_a += o.wins_a; wins_b += o.wins_b;
+        pts_a += o.pts_a; pts_b += o.pts_b; hits += o.hits; len_sum += o.len_sum;
+    }
     __device__ __forceinline__ void flush(unsigned long long *counters) {
         unsigned v[7] = {steps, episodes, wins_a, wins_b, pts_a, pts_b, hits};
 #pragma unroll

@@ -18,12 +18,13 @@ __device__ __forceinline__ int64_t ring_first_step(const PPReplayRing &ring, int
     return ring.head ? k_steps - ring.capacity / n : 0;
 }
 
-// Called by ALL lanes of a warp.  `ob` = player B's observation the action was chosen from.
-template <typename R>
-__device__ __forceinline__ void step_and_book(const EnvConsts<R> &c, const PPParams &params, Lane<R> &L, bool valid, bool active,
-                                              int act_a, int act_b, const float (&ob)[7], int64_t t, int64_t n, int64_t i,
-                                              int64_t env_id_base, const PPServeSource &src, int32_t quota,
-                                              const PPRolloutOut &out, const PPReplayRing &ring, bool ring_on) {
+// Called by ALL lanes of a warp.  `ob` = player B's observation the action was chosen from; `serve(ep, vx, vy, spin)`
+// yields the serve of episode `ep` of this env.
+template <typename R, typename ServeFn>
+__device__ __forceinline__ void step_and_book(const EnvConsts<R> &c, Lane<R> &L, bool active, int act_a, int act_b,
+                                              const float (&ob)[7], int64_t t, int64_t n, int64_t i, int64_t env_id_base,
+                                              int32_t quota, const PPRolloutOut &out, const PPReplayRing &ring, bool ring_on,
+                                              ServeFn &&serve) {
     const int lane = threadIdx.x & 31;
     int flags = 0;
     if (active) {
@@ -61,12 +62,11 @@ __device__ __forceinline__ void step_and_book(const EnvConsts<R> &c, const PPPar
         L.ep_idx += 1;
         if (!(quota > 0 && L.ep_idx >= quota)) {
             R svx, svy, ssp;
-            next_serve<R>(params, src, n, i, env_id_base, L.ep_idx, svx, svy, ssp);
+            serve(L.ep_idx, svx, svy, ssp);
             serve_env<R>(L.e, svx, svy, ssp);
             L.ep_len = 0;
         }
     }
-    (void)valid;
 }
 
 }  // namespace pp

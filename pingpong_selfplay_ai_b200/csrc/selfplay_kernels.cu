@@ -98,8 +98,9 @@ selfplay_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k
                 if (p) act_b = a; else act_a = a;
             }
         }
-        step_and_book<R>(c, params, L, valid, active, act_a, act_b, ob, t, n, i, env_id_base, src, quota, out, ring,
-                         ring.head != nullptr && t >= ring_t0);
+        step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
+                         ring.head != nullptr && t >= ring_t0,
+                         [&](int ep, R &vx, R &vy, R &sp) { next_serve<R>(params, src, n, i, env_id_base, ep, vx, vy, sp); });
     }
     if (valid) {
         store_env<R>(s, i, L.e);

@@ -32,7 +32,6 @@ namespace {
 
 constexpr int G_ROWS = 128;                    // envs per group
 constexpr int CTA_GROUPS = 4;
-constexpr int TC_THREADS = G_ROWS * CTA_GROUPS;
 constexpr uint32_t A_LBO = G_ROWS * 16;        // A tiles are [K/8][128][16 B]
 constexpr uint32_t SBO = 128;
 
@@ -110,14 +109,15 @@ __device__ __forceinline__ void write_x_row(uint8_t *x, int row, const float (&o
     *reinterpret_cast<uint4 *>(x + A_LBO + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// 8 accumulator columns -> ReLU -> (hi, lo) fp16 chunks of this thread's row
+// 8 accumulator columns -> ReLU -> (hi, lo) fp16 chunks of this thread's row.  hi = rz(relu(x)) <= relu(x), so for
+// x >= 0 the residual x - hi is >= 0 and for x < 0 it is x < 0: one more ReLU-convert yields lo = relu(x) - hi.
 __device__ __forceinline__ void split_store8(const uint32_t *r, uint8_t *h, int chunk, int row) {
     uint32_t p[4], q[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float a = fmaxf(__uint_as_float(r[2 * j]), 0.0f), b = fmaxf(__uint_as_float(r[2 * j + 1]), 0.0f);
-        p[j] = tc::pack_f16x2<false>(a, b);
-        q[j] = tc::pack_f16x2<false>(a - h2f(p[j], 0), b - h2f(p[j], 1));
+        const float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+        p[j] = tc::pack_f16x2_rz_relu(a, b);
+        q[j] = tc::pack_f16x2<true>(a - h2f(p[j], 0), b - h2f(p[j], 1));
     }
     *reinterpret_cast<uint4 *>(h + chunk * A_LBO + row * 16) = make_uint4(p[0], p[1], p[2], p[3]);
     *reinterpret_cast<uint4 *>(h + H_HALF + chunk * A_LBO + row * 16) = make_uint4(q[0], q[1], q[2], q[3]);
@@ -173,9 +173,8 @@ __device__ __forceinline__ void dueling_q(uint32_t taddr, float (&q)[3]) {      
 }
 
 // Shared prologue: barriers, TMEM, weights.  Returns the TMEM base of the CTA.
-template <int GROUPS>
+template <int GROUPS, typename M>
 __device__ __forceinline__ uint32_t tc_prologue(uint8_t *smem, const PPPolicy &pol_a, const PPPolicy &pol_b) {
-    using M = SmemMap<GROUPS>;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + M::CTRL);           // [0] weights, [1 + g] group g
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + M::CTRL + 32);
     const int tid = threadIdx.x;
@@ -215,7 +214,7 @@ struct GroupCtx {
     uint64_t *bar;
     uint32_t parity, d_a, d_b, bar_id, lane_addr;
     int row;
-    bool qa, qb;
+    bool qa, qb, issuer_warp;
 };
 
 __device__ __forceinline__ void group_wait(GroupCtx &g) {
@@ -224,16 +223,18 @@ __device__ __forceinline__ void group_wait(GroupCtx &g) {
     tc::tc_fence_after();
 }
 
-// after the barrier that published the X rows: L1 (both players) -> per player: H1 -> L2 -> H2 -> L3 -> Q
+// after the barrier that published the X rows: L1 (both players) -> per player: H1 -> L2 -> H2 -> L3 -> Q.
+// Self-issuing variant (an elected lane of the group's first warp issues): used by the standalone kernel.
 __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
-    const bool issuer = g.row == 0;
-    if (issuer) {
-        tc::tc_fence_after();
-        if (g.qa) issue_l1(g.d_a, g.pa);
-        if (g.qb) issue_l1(g.d_b, g.pb);
-        tc::umma_commit(g.bar);
+    if (g.issuer_warp) {                      // warp-uniform branch
+        if (tc::elect_one()) {
+            tc::tc_fence_after();
+            if (g.qa) issue_l1(g.d_a, g.pa);
+            if (g.qb) issue_l1(g.d_b, g.pb);
+            tc::umma_commit(g.bar);
+        }
+        __syncwarp();
     }
-    __syncwarp();
     group_wait(g);
 #pragma unroll 1
     for (int pl = 0; pl < 2; ++pl) {
@@ -246,19 +247,23 @@ __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], floa
             tc::fence_proxy_async();
             tc::tc_fence_before();
             tc::bar_sync(g.bar_id, G_ROWS);
-            if (issuer) {
-                tc::tc_fence_after();
-                if (layer == 0) issue_dense<64>(d, p, W2H_OFF, W2L_OFF, B2_OFF);
-                else issue_dense<16>(d, p, W3H_OFF, W3L_OFF, B3_OFF);
-                tc::umma_commit(g.bar);
+            if (g.issuer_warp) {
+                if (tc::elect_one()) {
+                    tc::tc_fence_after();
+                    if (layer == 0) issue_dense<64>(d, p, W2H_OFF, W2L_OFF, B2_OFF);
+                    else issue_dense<16>(d, p, W3H_OFF, W3L_OFF, B3_OFF);
+                    tc::umma_commit(g.bar);
+                }
+                __syncwarp();
             }
-            __syncwarp();
             group_wait(g);
         }
         if (pl) dueling_q(d + g.lane_addr, q_b); else dueling_q(d + g.lane_addr, q_a);
     }
 }
 
+// `grp` and `tmem` must be warp-uniform VALUES THE COMPILER CAN SEE as uniform (shfl broadcasts), so that the UMMA
+// descriptors derived from them live in uniform registers instead of being re-broadcast before every MMA.
 __device__ __forceinline__ GroupCtx make_group(uint8_t *smem, uint32_t groups_off, uint32_t ctrl_off, uint32_t tmem, int grp,
                                                int row, bool qa, bool qb) {
     GroupCtx g;
@@ -273,6 +278,7 @@ __device__ __forceinline__ GroupCtx make_group(uint8_t *smem, uint32_t groups_of
     g.lane_addr = (uint32_t)((row >> 5) * 32) << 16;
     g.row = row;
     g.qa = qa; g.qb = qb;
+    g.issuer_warp = __shfl_sync(0xffffffffu, (row >> 5) == 0 ? 1 : 0, 0) != 0;
     return g;
 }
 
@@ -287,7 +293,7 @@ qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol,
     using M = SmemMap<1>;
     PPPolicy none = pol;
     none.kind = PP_POLICY_RANDOM;
-    const uint32_t tmem = tc_prologue<1>(smem, pol, none);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tc_prologue<1, SmemMap<1>>(smem, pol, none), 0);
     const int row = threadIdx.x;
     GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, 0, row, true, false);
     for (int64_t tile0 = (int64_t)blockIdx.x * G_ROWS; tile0 < n; tile0 += (int64_t)gridDim.x * G_ROWS) {
@@ -314,23 +320,39 @@ qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol,
 }
 
 // --------------------------------------------------------------------------------- fused self-play rollout
+// 16 warps = 4 groups per CTA, one CTA per SM; an elected lane of each group's first warp issues that group's MMAs.
+// (A dedicated issuer warp fed through ready / done mbarriers was measured 27% SLOWER: one thread then serialises
+// the MMA issue of all four groups, and tcgen05.mma issue is paced by the operand reads, ~1000 cycles per batch.)
 // Work is split in units of warps (32 envs): `n_chunks` chunks of at most 16 warps, balanced to within one warp, so
 // every SM issues the same number of warp-steps whatever n is.  A CTA walks chunks blockIdx.x, + gridDim.x, ...
+constexpr int TC_FUSED_THREADS = G_ROWS * CTA_GROUPS;
+struct FusedMap {
+    static constexpr uint32_t W = 0, GROUPS_OFF = 2 * PLAYER_W_BYTES;
+    static constexpr uint32_t SERVE_OFF = GROUPS_OFF + CTA_GROUPS * GROUP_BYTES;       // next serve per thread: 3 doubles
+    static constexpr uint32_t CTRL = SERVE_OFF + TC_FUSED_THREADS * 24;                // mbarriers + TMEM base
+    static constexpr uint32_t TOTAL = CTRL + 64;
+};
+static_assert(FusedMap::TOTAL <= 232448, "shared memory of the fused tensor-core kernel exceeds 227 KB");
+static_assert(2 * BLOB_BYTES <= CTA_GROUPS * GROUP_BYTES, "weight staging must fit in the group tiles");
+
 template <typename R>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_FUSED_THREADS, 1)
 selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_steps, const PPPolicy pol_a,
                    const PPPolicy pol_b, uint64_t seed, int64_t step_base, const PPServeSource src, int32_t quota,
                    int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks) {
     extern __shared__ __align__(128) uint8_t smem[];
-    using M = SmemMap<CTA_GROUPS>;
-    const uint32_t tmem = tc_prologue<CTA_GROUPS>(smem, pol_a, pol_b);
-    const int grp = threadIdx.x >> 7, row = threadIdx.x & 127, gw = row >> 5, lane = threadIdx.x & 31;
+    using M = FusedMap;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tc_prologue<CTA_GROUPS, M>(smem, pol_a, pol_b), 0);
+    const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler too
+    const int grp = warp_id >> 2, gw = warp_id & 3, row = threadIdx.x & 127, lane = threadIdx.x & 31;
     const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
     GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, grp, row, qa, qb);
+    double *serve_slot = reinterpret_cast<double *>(smem + M::SERVE_OFF) + threadIdx.x * 3;
     const EnvConsts<R> c(params);
     const StatePtrs<R> s(st);
     const int64_t total_warps = (n + 31) / 32;
     const int64_t ring_t0 = ring_first_step(ring, n, k_steps);
+    const bool prefetch_serves = src.kind == PP_SERVE_PHILOX;
     Tally total;
 
 #pragma unroll 1
@@ -346,11 +368,19 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
         L.e = load_env<R>(s, ic);
         L.ep_idx = s.ep_idx[ic]; L.ep_len = s.ep_len[ic];
         const uint32_t gid = (uint32_t)(env_id_base + ic);
+        bool have_next = false;
 
 #pragma unroll 1
         for (int64_t t = 0; t < k_steps; ++t) {
             const bool active = valid && !(quota > 0 && L.ep_idx >= quota);
             const uint32_t step = (uint32_t)(step_base + t);
+            // Every 8 steps each thread that used up its prefetched serve draws the next one NOW, all lanes and warps of
+            // the group together, instead of alone inside the divergent episode-end branch (where one finishing lane
+            // would hold up its warp, and the warp its group, on almost every step).
+            if ((t & 7) == 0 && prefetch_serves && active && !have_next && !(quota > 0 && L.ep_idx + 1 >= quota)) {
+                philox_serve(params, src.seed, gid, (uint32_t)(L.ep_idx + 1), serve_slot[0], serve_slot[1], serve_slot[2]);
+                have_next = true;
+            }
             float oa[7], ob[7];
             observe<R>(L.e, oa, ob);
             if (qa) write_x_row(g.pa.x, row, oa);
@@ -365,18 +395,21 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
             else act_a = explore(qa ? argmax3(q_a) : follower_action(oa, pol_a.follower_tol), pol_a.eps_threshold, seed, gid, step, STREAM_ACT_A);
             if (pol_b.kind == PP_POLICY_RANDOM) act_b = random_action(seed, gid, step, STREAM_ACT_B);
             else act_b = explore(qb ? argmax3(q_b) : follower_action(ob, pol_b.follower_tol), pol_b.eps_threshold, seed, gid, step, STREAM_ACT_B);
-            if (gw < my_warps)        // warp-uniform: warps without envs skip the bookkeeping collectives entirely
-                step_and_book<R>(c, params, L, valid, active, act_a, act_b, ob, t, n, i, env_id_base, src, quota, out, ring,
-                                 ring.head != nullptr && t >= ring_t0);
+            if (gw < my_warps) {      // warp-uniform: warps without envs skip the bookkeeping collectives entirely
+                auto serve = [&](int ep, R &vx, R &vy, R &sp) {
+                    if (have_next) { vx = (R)serve_slot[0]; vy = (R)serve_slot[1]; sp = (R)serve_slot[2]; have_next = false; }
+                    else next_serve<R>(params, src, n, i, env_id_base, ep, vx, vy, sp);
+                };
+                step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
+                                 ring.head != nullptr && t >= ring_t0, serve);
+            }
         }
         if (valid) {
             store_env<R>(s, i, L.e);
             s.ep_idx[i] = L.ep_idx;
             s.ep_len[i] = L.ep_len;
         }
-        total.steps += L.tally.steps; total.episodes += L.tally.episodes; total.wins_a += L.tally.wins_a;
-        total.wins_b += L.tally.wins_b; total.pts_a += L.tally.pts_a; total.pts_b += L.tally.pts_b;
-        total.hits += L.tally.hits; total.len_sum += L.tally.len_sum;
+        total.add(L.tally);
     }
     if (out.counters) total.flush(out.counters);
     tc_epilogue<CTA_GROUPS>(tmem);
@@ -409,7 +442,7 @@ int qnet_act_tc_launch(int64_t n, const float *obs, const PPPolicy &pol, uint64_
 int selfplay_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
                        const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
                        int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream) {
-    constexpr int smem = (int)SmemMap<CTA_GROUPS>::TOTAL;
+    constexpr int smem = (int)FusedMap::TOTAL;
     PPReplayRing r{};
     if (ring) r = *ring;
     const int64_t total_warps = (n + 31) / 32;
@@ -424,11 +457,11 @@ int selfplay_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const 
     cudaError_t err;
     if (mode == PP_MODE_F64) {
         if ((err = cudaFuncSetAttribute(selfplay_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)err;
-        selfplay_tc_kernel<double><<<blocks, TC_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
+        selfplay_tc_kernel<double><<<blocks, TC_FUSED_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
                                                                         env_id_base, out, r, n_chunks);
     } else {
         if ((err = cudaFuncSetAttribute(selfplay_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)err;
-        selfplay_tc_kernel<float><<<blocks, TC_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
+        selfplay_tc_kernel<float><<<blocks, TC_FUSED_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
                                                                        env_id_base, out, r, n_chunks);
     }
     return (int)cudaGetLastError();
