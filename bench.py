@@ -238,7 +238,9 @@ def main():
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--lockstep", type=int, default=64, help="lock-step env steps per launch")
     ap.add_argument("--mode", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--precision", default="f32", choices=["f32", "f16"])
+    ap.add_argument("--precision", default="f16", choices=["f32", "f16"],
+                    help="QNet path: f16 = tcgen05 tensor cores (fp16 hi/lo operands, fp32 accumulate, ~1e-6 of fp32); "
+                         "f32 = CUDA-core fmaf chain, bit-identical to the oracle")
     ap.add_argument("--ref-steps", type=int, default=1500, help="reference arm: env-steps per process per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -315,7 +317,7 @@ def main():
                      "paddle_hits": int(total[6].item())},
     }
     tf = value / world * FLOP_PER_ENV_STEP / 1e12
-    line["roofline"] = {"bound": "tensor", "kernel": "selfplay_kernel", "achieved": tf, "peak": peaks["bf16_sustained"],
+    line["roofline"] = {"bound": "tensor", "kernel": "selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel", "achieved": tf, "peak": peaks["bf16_sustained"],
                         "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"], "traffic": None,
                         "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                         "note": "algorithmic 19200 FLOP per env-step (both players' QNet) x env-steps per launch / "
@@ -392,10 +394,10 @@ def measure_e2e(pp, net_a, net_b, args):
     rt = np.float64 if args.mode == "f64" else np.float32
     pool = ((speed * np.cos(ang)).astype(rt), (speed * np.sin(ang)).astype(rt), rs.uniform(-5, 5, size=(quota, n)).astype(rt))
     wa, wb = pp.pack_qnet(net_a).numpy(), pp.pack_qnet(net_b).numpy()
-    pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep)      # warm-up (allocations)
+    pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep, precision=args.precision)  # warm-up
     reps, steps_total, t0 = 3, 0, time.perf_counter()
     for _ in range(reps):
-        c, _ = pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep)
+        c, _ = pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep, precision=args.precision)
         steps_total += c["env_steps"]
     wall = time.perf_counter() - t0
     h2d = 3 * quota * n * np.dtype(rt).itemsize + 2 * wa.nbytes
