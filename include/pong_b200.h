@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 2
+#define PP_ABI_VERSION 3
 
 enum { PP_MODE_F64 = 0, PP_MODE_F32 = 1 };
 
@@ -81,13 +81,22 @@ typedef struct PPEnvState {
  * MT19937 (envs/my_pong_env_2p.py:98-111), which cannot be reproduced on the device:
  *   PP_SERVE_POOL    host-generated queue, real[depth][n]; env i's j-th episode uses row j % depth
  *   PP_SERVE_PHILOX  Philox4x32-10 keyed by (seed; global env id, episode index): same formula,
- *                    distribution-equal, and independent of how envs are sharded over GPUs. */
-enum { PP_SERVE_POOL = 0, PP_SERVE_PHILOX = 1 };
+ *                    distribution-equal, and independent of how envs are sharded over GPUs.
+ *   PP_SERVE_QUEUE   evaluation mode: the pool is ONE queue of queue_total serves (flat index q = j * n + i, the
+ *                    same memory as a [depth][n] pool) and an env that finishes an episode claims the next
+ *                    unplayed serve with an atomic on *queue_head instead of waiting for its own next one.  Every
+ *                    serve is still played exactly once and an episode depends on nothing but its serve and the
+ *                    (greedy) players, so counters and episode-log rows (env = q % n, episode = q / n) equal
+ *                    those of the fixed per-env quota — without the lock-step tail in which finished envs
+ *                    idle.  ep_idx holds q; pass quota = queue_total; *queue_head starts at n. */
+enum { PP_SERVE_POOL = 0, PP_SERVE_PHILOX = 1, PP_SERVE_QUEUE = 2 };
 typedef struct PPServeSource {
     int32_t kind;
     int32_t depth;
     const void *pool_vx, *pool_vy, *pool_spin;
     uint64_t seed;
+    unsigned long long *queue_head;
+    int64_t queue_total;
 } PPServeSource;
 
 /* A player.  Replaces the per-step `model(torch.tensor(obs).unsqueeze(0)).argmax(1).item()` of

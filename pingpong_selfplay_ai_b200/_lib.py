@@ -13,9 +13,9 @@ from . import build as _build
 
 c_i32, c_i64, c_u64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_void_p
 
-PP_ABI_VERSION = 2
+PP_ABI_VERSION = 3
 MODE_F64, MODE_F32 = 0, 1
-SERVE_POOL, SERVE_PHILOX = 0, 1
+SERVE_POOL, SERVE_PHILOX, SERVE_QUEUE = 0, 1, 2
 POLICY_QNET, POLICY_QNETRNN, POLICY_FOLLOWER, POLICY_RANDOM = 0, 1, 2, 3
 PREC_F32, PREC_F16 = 0, 1
 STREAM_ACT_A, STREAM_ACT_B = 1, 2
@@ -43,7 +43,7 @@ class PPEnvState(C.Structure):
 
 class PPServeSource(C.Structure):
     _fields_ = [("kind", c_i32), ("depth", c_i32), ("pool_vx", c_vp), ("pool_vy", c_vp), ("pool_spin", c_vp),
-                ("seed", c_u64)]
+                ("seed", c_u64), ("queue_head", c_vp), ("queue_total", c_i64)]
 
 
 class PPPolicy(C.Structure):

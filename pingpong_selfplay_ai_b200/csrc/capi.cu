@@ -29,6 +29,7 @@ bool params_ok(const PPParams *p) { return p && p->speed_scale_every > 0 && p->m
 bool serve_ok(const PPServeSource *s) {
     if (!s) return false;
     if (s->kind == PP_SERVE_POOL) return s->depth > 0 && s->pool_vx && s->pool_vy && s->pool_spin;
+    if (s->kind == PP_SERVE_QUEUE) return s->queue_total > 0 && s->queue_total < 0x7fffffff && s->queue_head && s->pool_vx && s->pool_vy && s->pool_spin;
     return s->kind == PP_SERVE_PHILOX;
 }
 bool policy_ok(const PPPolicy *p, bool allow_rnn) {
@@ -107,6 +108,7 @@ int pp_env_rollout(int mode, int64_t n, int64_t k, const PPParams *params, const
     if (n < 0 || k < 0) return fail(PP_E_SIZE, "pp_env_rollout");
     if (!params_ok(params)) return fail(PP_E_PARAM, "pp_env_rollout");
     if (!state_ok(state, true) || !actions || !serve_ok(serve) || !out_ok(out)) return fail(PP_E_NULL, "pp_env_rollout");
+    if (serve->kind == PP_SERVE_QUEUE) return fail(PP_E_MODE, "pp_env_rollout");      // the queue is an evaluation mode
     if (reinterpret_cast<uintptr_t>(actions) & 1u) return fail(PP_E_ALIGN, "pp_env_rollout");
     if (n == 0 || k == 0) return 0;
     return ok_or(pp::env_rollout_launch(mode, n, k, *params, *state, actions, *serve, quota, env_id_base, *out,
@@ -153,6 +155,7 @@ int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, 
         return fail(PP_E_MODE, "pp_selfplay_rollout");                 // both QNet players on the same path
     if (ring && !ring_ok(ring)) return fail(PP_E_NULL, "pp_selfplay_rollout");
     if (ring && ring->capacity < n) return fail(PP_E_SIZE, "pp_selfplay_rollout");     // one lock-step step must fit
+    if (serve->kind == PP_SERVE_QUEUE && (int64_t)quota != serve->queue_total) return fail(PP_E_SIZE, "pp_selfplay_rollout");
     if (n == 0 || k == 0) return 0;
     if (tc)
         return ok_or(pp::selfplay_tc_launch(mode, n, k, *params, *state, *policy_a, *policy_b, seed, step_base, *serve,
@@ -219,7 +222,7 @@ int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *pa
     const size_t blob_bytes = align_up(PP_QNET_BLOB_FLOATS * sizeof(float), 256);
     const size_t log_bytes = align_up((size_t)(host_ep_log ? ep_log_cap : 0) * 16, 256);
     const size_t dev_bytes = 3 * pool_bytes + 7 * real_bytes + 5 * int_bytes + 2 * blob_bytes + 256 + log_bytes;
-    int rc = ensure(g_cache, dev_bytes, 256);
+    int rc = ensure(g_cache, dev_bytes, 256);                 // pinned: counters[8] + log count + queue head
     if (rc) return fail(rc, fn);
     cudaStream_t st = g_cache.stream;
     char *d = (char *)g_cache.dev;
@@ -242,25 +245,29 @@ int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *pa
     CK(cudaMemcpyAsync(wa, host_weights_a, PP_QNET_BLOB_FLOATS * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(wb, host_weights_b, PP_QNET_BLOB_FLOATS * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctr, 0, 256, st));
-    CK(cudaMemsetAsync(es.ep_idx, 0, (size_t)n * 4, st));
-    PPServeSource src{PP_SERVE_POOL, quota, pvx, pvy, psp, 0};
-    rc = pp::env_reset_launch(mode, n, *params, es, nullptr, src, 0, /*advance=*/0, st);     // serve 0 of every env
+    // The n x quota serves form ONE queue (PP_SERVE_QUEUE): an env that finishes an episode claims the next unplayed
+    // serve, so no env idles while others still have episodes to play; outcomes per serve are unchanged.  The whole
+    // evaluation is a single launch: every group leaves the step loop once the queue is drained and its envs are done.
+    unsigned long long *h = (unsigned long long *)g_cache.pinned;
+    const int64_t total = (int64_t)n * quota;
+    if (total >= 0x7fffffff) return fail(PP_E_SIZE, fn);
+    h[16] = (unsigned long long)n;                                        // queue_head: serves 0..n-1 are taken at reset
+    unsigned long long *qhead = ctr + 16;
+    CK(cudaMemcpyAsync(qhead, h + 16, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    PPServeSource src{PP_SERVE_QUEUE, quota, pvx, pvy, psp, 0, qhead, total};
+    rc = pp::env_reset_launch(mode, n, *params, es, nullptr, src, 0, /*advance=*/0, st);     // env i starts on serve i
     if (rc) return fail(rc, fn);
     PPPolicy pa{PP_POLICY_QNET, precision, 0, 0.f, 0, wa, nullptr, nullptr};
     PPPolicy pb{PP_POLICY_QNET, precision, 0, 0.f, 0, wb, nullptr, nullptr};
     PPRolloutOut out{ctr, dlog, host_ep_log ? ep_log_cap : 0, ctr + 8, nullptr, nullptr, nullptr};
-    unsigned long long *h = (unsigned long long *)g_cache.pinned;
-    const unsigned long long want = (unsigned long long)n * (unsigned long long)quota;
-    for (int64_t done_steps = 0; done_steps < max_steps; done_steps += chunk) {
-        const int64_t k = (max_steps - done_steps) < chunk ? (max_steps - done_steps) : chunk;
-        rc = precision == PP_PREC_F16
-                 ? pp::selfplay_tc_launch(mode, n, k, *params, es, pa, pb, 0, done_steps, src, quota, 0, out, nullptr, st)
-                 : pp::selfplay_launch(mode, n, k, *params, es, pa, pb, 0, done_steps, src, quota, 0, out, nullptr, st);
-        if (rc) return fail(rc, fn);
-        CK(cudaMemcpyAsync(h, ctr, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (h[1] >= want) break;                     // every env has played its quota
-    }
+    const int64_t k = max_steps < 0x7fffffff ? max_steps : 0x7ffffffe;
+    (void)chunk;                                                          // kept in the ABI; one launch needs no chunks
+    rc = precision == PP_PREC_F16
+             ? pp::selfplay_tc_launch(mode, n, k, *params, es, pa, pb, 0, 0, src, (int32_t)total, 0, out, nullptr, st)
+             : pp::selfplay_launch(mode, n, k, *params, es, pa, pb, 0, 0, src, (int32_t)total, 0, out, nullptr, st);
+    if (rc) return fail(rc, fn);
+    CK(cudaMemcpyAsync(h, ctr, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     memcpy(host_counters, h, 8 * sizeof(unsigned long long));
     if (host_ep_log) {
         const unsigned long long rows = h[8] < (unsigned long long)ep_log_cap ? h[8] : (unsigned long long)ep_log_cap;

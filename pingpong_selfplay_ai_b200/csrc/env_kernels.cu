@@ -144,7 +144,9 @@ reset_kernel(const PPParams params, const PPEnvState st, int64_t n, const uint8_
     R svx, svy, ssp;
     if (FROM_SOURCE) {
         int ep = s.ep_idx[i] + (advance ? 1 : 0);
+        if (src.kind == PP_SERVE_QUEUE) ep = i < src.queue_total ? (int)i : 0x7fffffff;   // env i starts on serve i
         s.ep_idx[i] = ep;
+        if (ep == 0x7fffffff) return;
         next_serve<R>(params, src, n, i, env_id_base, ep, svx, svy, ssp);
     } else {
         svx = vx[i]; svy = vy[i]; ssp = spin[i];
@@ -204,7 +206,7 @@ rollout_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_
                 ti[0 * n + i] = e.sa; ti[1 * n + i] = e.sb; ti[2 * n + i] = e.bounce; ti[3 * n + i] = flags;
             }
             const bool fin = (flags & F_DONE) != 0;
-            log_episode(fin, out, (int)(env_id_base + i), ep_idx, e.sa, e.sb, ep_len);
+            log_episode(fin, __ballot_sync(0xffffffffu, fin), out, (int)(env_id_base + i), ep_idx, e.sa, e.sb, ep_len);
             if (fin) {
                 tally.episodes += 1;
                 if (e.sa > e.sb) tally.wins_a += 1; else tally.wins_b += 1;

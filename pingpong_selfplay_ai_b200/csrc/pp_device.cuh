@@ -188,14 +188,25 @@ static __device__ __noinline__ void philox_serve(const PPParams &p, uint64_t see
 template <typename R>
 __device__ __forceinline__ void next_serve(const PPParams &p, const PPServeSource &src, int64_t n, int64_t i,
                                            int64_t env_id_base, int ep, R &vx, R &vy, R &spin) {
-    if (src.kind == PP_SERVE_POOL) {
-        const int64_t j = (int64_t)(ep % src.depth) * n + i;
+    if (src.kind != PP_SERVE_PHILOX) {
+        const int64_t j = src.kind == PP_SERVE_QUEUE ? (int64_t)ep : (int64_t)(ep % src.depth) * n + i;
         vx = ((const R *)src.pool_vx)[j]; vy = ((const R *)src.pool_vy)[j]; spin = ((const R *)src.pool_spin)[j];
     } else {
         double dvx, dvy, ds;
         philox_serve(p, src.seed, (uint32_t)(env_id_base + i), (uint32_t)ep, dvx, dvy, ds);
         vx = (R)dvx; vy = (R)dvy; spin = (R)ds;
     }
+}
+
+// PP_SERVE_QUEUE: the finishing lanes of a warp (ballot m) claim the next unplayed serves with one atomic.
+// Returns the claimed queue index, or INT32_MAX when the queue is exhausted (the env is frozen for good).
+__device__ __forceinline__ int claim_serves(bool fin, unsigned m, const PPServeSource &src) {
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(src.queue_head, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const unsigned long long q = base + __popc(m & ((1u << lane) - 1u));
+    return (fin && q < (unsigned long long)src.queue_total) ? (int)q : 0x7fffffff;
 }
 
 // Warp-aggregated bookkeeping of a lock-step step: per-thread counters stay in registers and are
@@ -228,10 +239,9 @@ struct Tally {
     }
 };
 
-// Called by ALL lanes of a warp (done = this lane finished an episode this step).
-__device__ __forceinline__ void log_episode(bool done, const PPRolloutOut &out, int env_id, int ep_idx, int sa, int sb,
-                                            int ep_len) {
-    const unsigned m = __ballot_sync(0xffffffffu, done);
+// Called by ALL lanes of a warp (done = this lane finished an episode this step, m = ballot of done).
+__device__ __forceinline__ void log_episode(bool done, unsigned m, const PPRolloutOut &out, int env_id, int ep_idx, int sa,
+                                            int sb, int ep_len) {
     if (m == 0 || out.ep_log_count == nullptr) return;
     const int lane = threadIdx.x & 31;
     unsigned long long base = 0;

@@ -24,7 +24,7 @@ template <typename R, typename ServeFn>
 __device__ __forceinline__ void step_and_book(const EnvConsts<R> &c, Lane<R> &L, bool active, int act_a, int act_b,
                                               const float (&ob)[7], int64_t t, int64_t n, int64_t i, int64_t env_id_base,
                                               int32_t quota, const PPRolloutOut &out, const PPReplayRing &ring, bool ring_on,
-                                              ServeFn &&serve) {
+                                              const PPServeSource &src, ServeFn &&serve) {
     const int lane = threadIdx.x & 31;
     int flags = 0;
     if (active) {
@@ -54,12 +54,17 @@ __device__ __forceinline__ void step_and_book(const EnvConsts<R> &c, Lane<R> &L,
         }
     }
     const bool fin = (flags & F_DONE) != 0;
-    log_episode(fin, out, (int)(env_id_base + i), L.ep_idx, L.e.sa, L.e.sb, L.ep_len);
+    const unsigned m_fin = __ballot_sync(0xffffffffu, fin);
+    const bool queue = src.kind == PP_SERVE_QUEUE;
+    if (queue) log_episode(fin, m_fin, out, (int)(env_id_base + L.ep_idx % n), (int)(L.ep_idx / n), L.e.sa, L.e.sb, L.ep_len);
+    else log_episode(fin, m_fin, out, (int)(env_id_base + i), L.ep_idx, L.e.sa, L.e.sb, L.ep_len);
+    int claimed = 0;
+    if (queue && m_fin) claimed = claim_serves(fin, m_fin, src);               // warp-uniform branch
     if (fin) {
         L.tally.episodes += 1;
         if (L.e.sa > L.e.sb) L.tally.wins_a += 1; else L.tally.wins_b += 1;
         L.tally.len_sum += (unsigned)L.ep_len;
-        L.ep_idx += 1;
+        L.ep_idx = queue ? claimed : L.ep_idx + 1;
         if (!(quota > 0 && L.ep_idx >= quota)) {
             R svx, svy, ssp;
             serve(L.ep_idx, svx, svy, ssp);

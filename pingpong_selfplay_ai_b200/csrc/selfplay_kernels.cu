@@ -87,8 +87,9 @@ selfplay_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k
         float oa[7], ob[7];
         observe<R>(L.e, oa, ob);
         int act_a = 1, act_b = 1;
-        // a warp whose envs are all frozen skips the policy work altogether
-        if (__any_sync(0xffffffffu, active)) {
+        // a warp whose envs are all frozen by the quota is finished (frozen envs stay frozen within a launch)
+        if (!__any_sync(0xffffffffu, active)) break;
+        {
 #pragma unroll 1
             for (int p = 0; p < 2; ++p) {          // one copy of the MLP code serves both players
                 float o[7];
@@ -99,7 +100,7 @@ selfplay_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k
             }
         }
         step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
-                         ring.head != nullptr && t >= ring_t0,
+                         ring.head != nullptr && t >= ring_t0, src,
                          [&](int ep, R &vx, R &vy, R &sp) { next_serve<R>(params, src, n, i, env_id_base, ep, vx, vy, sp); });
     }
     if (valid) {

@@ -401,7 +401,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
                     else next_serve<R>(params, src, n, i, env_id_base, ep, vx, vy, sp);
                 };
                 step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
-                                 ring.head != nullptr && t >= ring_t0, serve);
+                                 ring.head != nullptr && t >= ring_t0, src, serve);
             }
         }
         if (valid) {

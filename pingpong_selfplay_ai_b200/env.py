@@ -119,13 +119,13 @@ class VecPongEnv2P:
             if serve != "philox":
                 raise ValueError("serve must be 'philox' or a (vx, vy, spin) pool")
             self._pool = None
-            self.serve = _lib.PPServeSource(_lib.SERVE_PHILOX, 0, None, None, None, self.seed)
+            self.serve = _lib.PPServeSource(_lib.SERVE_PHILOX, 0, None, None, None, self.seed, None, 0)
         else:
             pool = serve if isinstance(serve, ServePool) else ServePool(*serve, self.device, self.real_dtype)
             if pool.vx.shape[1] != self.n or pool.vx.dtype != self.real_dtype:
                 raise ValueError("serve pool must be [depth, num_envs] in the env's real dtype")
             self._pool = pool
-            self.serve = _lib.PPServeSource(_lib.SERVE_POOL, pool.depth, _ptr(pool.vx), _ptr(pool.vy), _ptr(pool.spin), 0)
+            self.serve = _lib.PPServeSource(_lib.SERVE_POOL, pool.depth, _ptr(pool.vx), _ptr(pool.vy), _ptr(pool.spin), 0, None, 0)
 
     # ------------------------------------------------------------------ reset / step
     def _mask_ptr(self, mask):
@@ -197,10 +197,14 @@ class VecPongEnv2P:
         return (self.obs_a, self.obs_b), (self.reward_a, self.reward_b), self.done, {}
 
     # ------------------------------------------------------------------ multi-step
-    def make_rollout_out(self, k=0, log_cap=0, want_actions=False, trace=False):
+    def make_rollout_out(self, k=0, log_cap=0, want_actions=False, trace=False, ep_log=None):
+        """Per-launch outputs.  `ep_log` (int32 [cap, 4]) may be passed in to keep appending to one log over several
+        launches (the log cursor `_ep_log_count` is never reset by a launch)."""
         n, dev = self.n, self.device
+        if ep_log is not None:
+            log_cap = int(ep_log.shape[0])
         bufs = dict(
-            ep_log=torch.zeros(max(log_cap, 1), 4, dtype=torch.int32, device=dev) if log_cap else None,
+            ep_log=ep_log if ep_log is not None else (torch.zeros(max(log_cap, 1), 4, dtype=torch.int32, device=dev) if log_cap else None),
             actions=torch.zeros(k, n, 2, dtype=torch.uint8, device=dev) if want_actions else None,
             trace_real=torch.zeros(k, 7, n, dtype=self.real_dtype, device=dev) if trace else None,
             trace_int=torch.zeros(k, 4, n, dtype=torch.int32, device=dev) if trace else None)

@@ -94,37 +94,61 @@ class SelfPlayEngine:
         self.step_base = 0
         self.lib = _lib.load()
 
-    def run(self, k: int, quota: int = 0, ring: ReplayRing | None = None, log_cap: int = 0, want_actions: bool = False):
+    def run(self, k: int, quota: int = 0, ring: ReplayRing | None = None, log_cap: int = 0, want_actions: bool = False,
+            serve=None, ep_log=None):
         env = self.env
-        out, bufs = env.make_rollout_out(k, log_cap, want_actions, False)
+        out, bufs = env.make_rollout_out(k, log_cap, want_actions, False, ep_log)
         pa, pb = self.pa.struct(), self.pb.struct()
         rs = ring.struct() if ring is not None else None
+        serve = env.serve if serve is None else serve
         with torch.cuda.device(env.device):
             _lib.check(self.lib.pp_selfplay_rollout(
                 env.mode_id, env.n, int(k), C.byref(env.params), C.byref(env.state), C.byref(pa), C.byref(pb),
-                self.seed, self.step_base, C.byref(env.serve), int(quota), env.env_id_base, C.byref(out),
+                self.seed, self.step_base, C.byref(serve), int(quota), env.env_id_base, C.byref(out),
                 C.byref(rs) if rs is not None else None, _stream_ptr(env.device)), "pp_selfplay_rollout")
         self.step_base += int(k)
         env._served_once = True
         return bufs
 
-    def evaluate(self, episodes_per_env: int, chunk: int = 64, max_steps: int = 1 << 20) -> dict:
-        """eval_vs_model (scripts/train_iterative.py:171-181) in lock step: every env plays exactly
-        `episodes_per_env` episodes (a fixed quota per env, so short games are not over-sampled) and is frozen
-        afterwards.  Returns the counters and win rates."""
+    def _deterministic_players(self) -> bool:
+        return all(p.kind != _lib.POLICY_RANDOM and p.eps == 0.0 for p in (self.pa, self.pb))
+
+    def evaluate(self, episodes_per_env: int, chunk: int = 64, max_steps: int = 1 << 20, work_stealing: bool = True,
+                 log_cap: int = 0) -> dict:
+        """eval_vs_model (scripts/train_iterative.py:171-181) in lock step: num_envs x `episodes_per_env` episodes, a
+        fixed number per env so that short games are not over-sampled.
+        With a serve pool and deterministic players the serves form one queue (PP_SERVE_QUEUE): an env that finishes
+        claims the next unplayed serve, the evaluation is ONE launch, and counters / episode log equal those of the
+        per-env quota (an episode depends only on its serve and the players).  Otherwise every env plays its own
+        quota and is frozen afterwards, in launches of `chunk` steps."""
         env = self.env
         env.counters.zero_()
-        env.ep_idx.zero_()
-        env._served_once = False
-        env.reset()
+        env._ep_log_count.zero_()
         want = env.n * int(episodes_per_env)
-        steps = 0
-        while steps < max_steps:
-            self.run(chunk, quota=episodes_per_env)
-            steps += chunk
-            if int(env.counters[1].item()) >= want:
-                break
+        pool = env._pool
+        if work_stealing and pool is not None and pool.depth >= episodes_per_env and self._deterministic_players():
+            head = torch.full((1,), env.n, dtype=torch.int64, device=env.device)
+            src = _lib.PPServeSource(_lib.SERVE_QUEUE, pool.depth, _ptr(pool.vx), _ptr(pool.vy), _ptr(pool.spin), 0,
+                                     _ptr(head), want)
+            with torch.cuda.device(env.device):
+                _lib.check(self.lib.pp_env_reset(env.mode_id, env.n, C.byref(env.params), C.byref(env.state), None,
+                                                 C.byref(src), env.env_id_base, 0, _stream_ptr(env.device)), "pp_env_reset")
+            bufs = self.run(min(int(max_steps), 0x7ffffffe), quota=want, serve=src, log_cap=log_cap)
+            steps = None
+        else:
+            env.ep_idx.zero_()
+            env._served_once = False
+            env.reset()
+            steps, bufs = 0, None
+            log = torch.zeros(log_cap, 4, dtype=torch.int32, device=env.device) if log_cap else None
+            while steps < max_steps:
+                bufs = self.run(chunk, quota=episodes_per_env, ep_log=log)
+                steps += chunk
+                if int(env.counters[1].item()) >= want:
+                    break
         c = env.read_counters()
+        if log_cap:
+            c["ep_log"] = bufs["ep_log"][:min(env.ep_log_count(), log_cap)]
         c["win_rate_b"] = c["wins_b"] / max(c["episodes"], 1)
         c["win_rate_a"] = c["wins_a"] / max(c["episodes"], 1)
         c["lockstep_steps"] = steps

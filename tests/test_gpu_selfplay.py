@@ -94,7 +94,7 @@ def test_selfplay_quota_freezes_envs_and_matches_oracle(H, nets):
     ga, oa = _mk(("qnet", "seed0", 0.0), nets, 0)
     gb, ob = _mk(("qnet", "seed1", 0.0), nets, 1)
     eng = pp.SelfPlayEngine(env, ga, gb, seed=1)
-    res = eng.evaluate(quota, chunk=128)
+    res = eng.evaluate(quota, chunk=128, work_stealing=False)
     assert res["episodes"] == n * quota and int(env.ep_idx.min().item()) == quota
     b = po.EnvBatch(n, "f64")
     b.serve(pool[0][0], pool[1][0], pool[2][0])
@@ -250,3 +250,28 @@ def test_selfplay_tensor_core_mixed_players_and_win_rates(H, nets):
         want = po.rollout(po.make_params(cfg), b, gu.np_of(got["actions"]), pool)
         gu.assert_state_equal(env, b)
         assert np.array_equal(gu.np_of(env.counters), want["counters"])
+
+
+@pytest.mark.parametrize("prec", ["f32", "f16"])
+def test_evaluate_serve_queue_equals_fixed_quota(H, nets, prec):
+    """PP_SERVE_QUEUE (work stealing over the n x quota serves, one launch) gives the counters and per-episode records
+    of the fixed per-env quota: each serve is played exactly once and an episode depends only on its serve."""
+    cfg = H["env_config_yaml"]
+    n, quota = 3000, 5
+    pool = gu.make_pool(9, n, quota, cfg, "f64")
+    res = {}
+    for ws in (False, True):
+        env = pp.VecPongEnv2P(n, mode="f64", serve=pool, **cfg)
+        eng = pp.SelfPlayEngine(env, pp.Policy.qnet(nets["seed0"], precision=prec), pp.Policy.qnet(nets["seed1"], precision=prec))
+        res[ws] = eng.evaluate(quota, chunk=128, work_stealing=ws, log_cap=n * quota)
+        assert res[ws]["episodes"] == n * quota
+    key = lambda t: gu.np_of(t)[np.lexsort((gu.np_of(t)[:, 1], gu.np_of(t)[:, 0]))]
+    for k in pp.COUNTER_NAMES:
+        assert res[True][k] == res[False][k], k
+    assert np.array_equal(key(res[True]["ep_log"]), key(res[False]["ep_log"]))
+    if prec == "f32":
+        b = po.EnvBatch(n, "f64")
+        b.serve(pool[0][0], pool[1][0], pool[2][0])
+        w = po.selfplay(po.make_params(cfg), b, _oracle_policy(po.POLICY_QNET, nets["seed0"]),
+                        _oracle_policy(po.POLICY_QNET, nets["seed1"]), 4096, pool, quota=quota, log_cap=n * quota)
+        assert np.array_equal(key(res[True]["ep_log"]), w["ep_log"][np.lexsort((w["ep_log"][:, 1], w["ep_log"][:, 0]))])
