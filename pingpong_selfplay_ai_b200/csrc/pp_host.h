@@ -30,6 +30,9 @@ int qnet_act_tc_launch(int64_t n, const float *obs, const PPPolicy &pol, uint64_
 int selfplay_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
                        const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
                        int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream);
+int selfplay_rnn_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
+                        const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
+                        int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream);
 int replay_scatter_launch(int64_t n, const PPReplayRing &ring, const float *obs, const uint8_t *act, const float *rew,
                           const float *next_obs, const uint8_t *done, const uint8_t *valid, cudaStream_t stream);
 

@@ -275,3 +275,65 @@ def test_evaluate_serve_queue_equals_fixed_quota(H, nets, prec):
         w = po.selfplay(po.make_params(cfg), b, _oracle_policy(po.POLICY_QNET, nets["seed0"]),
                         _oracle_policy(po.POLICY_QNET, nets["seed1"]), 4096, pool, quota=quota, log_cap=n * quota)
         assert np.array_equal(key(res[True]["ep_log"]), w["ep_log"][np.lexsort((w["ep_log"][:, 1], w["ep_log"][:, 0]))])
+
+
+# ------------------------------------------------------------------------------------------ recurrent players
+def _rnn_teacher_forced_check(cfg, n, K, pol_kinds, mode="f64", quota=0):
+    """Fused QNetRNN self-play (config 4 shape): replay the kernel's own action stream through the oracle env (state,
+    counters bit-exact) while the oracle QNetRNN, fed the same observations and carrying its own (h, c) with the
+    reference's reset-at-episode-start rule, must pick the same greedy actions except at near-ties."""
+    torch.manual_seed(11); net_a = pp.QNetRNN()
+    torch.manual_seed(12); net_b = pp.QNetRNN()
+    depth = 6
+    pool = gu.make_pool(31, n, depth, cfg, mode)
+    env = pp.VecPongEnv2P(n, mode=mode, serve=pool, **cfg)
+    env.reset()
+    b = gu.oracle_batch_like(env, mode)
+    mk = {"rnn_a": lambda: pp.Policy.qnetrnn(net_a, num_envs=n), "rnn_b": lambda: pp.Policy.qnetrnn(net_b, num_envs=n),
+          "follower": lambda: pp.Policy.follower(), "random": lambda: pp.Policy.random()}
+    pa, pb = mk[pol_kinds[0]](), mk[pol_kinds[1]]()
+    for p in (pa, pb):
+        if p.h is not None:
+            p.h.fill_(3.0); p.c.fill_(-2.0)                     # garbage: the first step of an episode must zero it
+    eng = pp.SelfPlayEngine(env, pa, pb, seed=5)
+    acts = np.concatenate([gu.np_of(eng.run(k, want_actions=True, quota=quota)["actions"]) for k in (K // 2, K - K // 2)])
+    p = po.make_params(cfg)
+    wts = {"rnn_a": po.qnetrnn_weights_from_state_dict(net_a.state_dict()), "rnn_b": po.qnetrnn_weights_from_state_dict(net_b.state_dict())}
+    hc = {k: (np.zeros((n, 128), np.float32), np.zeros((n, 128), np.float32)) for k in wts}
+    fresh = np.ones(n, bool)
+    checked = agree = 0
+    counters = np.zeros(8, np.int64)
+    for t in range(K):
+        oa, ob = po.observe(b)
+        live = ~((quota > 0) & (b.ep_idx >= quota)) if quota else np.ones(n, bool)
+        for side, (kind, obs) in enumerate(zip(pol_kinds, (oa, ob))):
+            if kind not in wts:
+                continue
+            h, c = hc[kind]
+            h[fresh] = 0; c[fresh] = 0
+            hh, cc = h.copy(), c.copy()
+            q, a = po.qnetrnn_forward(wts[kind], obs, hh, cc)
+            h[live], c[live] = hh[live], cc[live]                # frozen envs do not advance
+            srt = np.sort(q, axis=1)
+            clear = ((srt[:, 2] - srt[:, 1]) > 1e-4) & live
+            checked += clear.sum(); agree += (acts[t, clear, side] == a[clear]).sum()
+        ep_before = b.ep_idx.copy()
+        out = po.rollout(p, b, acts[t:t + 1], pool, quota=quota)
+        counters += out["counters"]
+        fresh = np.where(live, b.ep_idx != ep_before, fresh)
+    gu.assert_state_equal(env, b)
+    assert np.array_equal(gu.np_of(env.counters), counters) and counters[1] > 0
+    assert checked > 0.9 * K * n * sum(k in wts for k in pol_kinds) * (0.5 if quota else 1.0)
+    assert agree >= checked - max(2, checked // 2000), (agree, checked)      # fp32 exp/tanh differ in the last ulps only
+    for kind, pol in (("rnn_a", pa), ("rnn_b", pb)):
+        if pol.h is not None and kind in pol_kinds and not quota:
+            assert np.abs(gu.np_of(pol.h).T - hc[kind][0]).max() < 1e-4
+
+
+@pytest.mark.parametrize("kinds", [("rnn_a", "rnn_b"), ("follower", "rnn_b"), ("rnn_a", "random")])
+def test_selfplay_qnetrnn_rollout_teacher_forced(H, kinds):
+    _rnn_teacher_forced_check(H["env_config_rnn_yaml"], 200, 70, kinds)
+
+
+def test_selfplay_qnetrnn_quota_and_f32_mode(H):
+    _rnn_teacher_forced_check(H["env_config_rnn_yaml"], 130, 90, ("rnn_a", "rnn_b"), mode="f32", quota=2)

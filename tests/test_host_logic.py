@@ -90,7 +90,7 @@ def test_pack_qnetrnn_layout_and_mirror_outputs():
 def test_noisy_linear_statistics_and_reset():
     torch.manual_seed(0)
     lin = pp.NoisyLinear(64, 3)
-    assert float(lin.weight_sigma[0, 0]) == pytest.approx(0.017) and lin.weight_mu.abs().max() <= 1 / 8
+    assert float(lin.weight_sigma[0, 0].detach()) == pytest.approx(0.017) and lin.weight_mu.abs().max() <= 1 / 8
     e0 = lin.weight_epsilon.clone()
     lin.reset_noise()
     assert not torch.equal(e0, lin.weight_epsilon)
