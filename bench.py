@@ -220,8 +220,13 @@ def run_reference(args, rank: int):
 
 
 def workload_config(args, world):
-    return {"workload": "configs[2]: self-play eval, random-init QNet A vs QNet B, 65536 lock-step PongEnv2P envs per GPU, "
-                        "fused obs->QNet->argmax + env step, greedy, auto-reset (Philox serves), config.yaml env params",
+    if getattr(args, "workload", "qnet") == "rnn":
+        wl = ("configs[3] shape: QNetRNN (LSTM) A vs B rollout with per-env hidden state, fused obs->QNetRNN->argmax + env "
+              "step, greedy, auto-reset (Philox serves), config.yaml env params")
+    else:
+        wl = ("configs[2]: self-play eval, random-init QNet A vs QNet B, 65536 lock-step PongEnv2P envs per GPU, "
+              "fused obs->QNet->argmax + env step, greedy, auto-reset (Philox serves), config.yaml env params")
+    return {"workload": wl,
             "envs_per_gpu": args.envs, "lockstep_steps_per_launch": args.lockstep, "env_mode": args.mode,
             "qnet_precision": args.precision, "parallelism": f"env-slab dp{world}",
             "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event brackets); "
@@ -241,6 +246,9 @@ def main():
     ap.add_argument("--precision", default="f16", choices=["f32", "f16"],
                     help="QNet path: f16 = tcgen05 tensor cores (fp16 hi/lo operands, fp32 accumulate, ~1e-6 of fp32); "
                          "f32 = CUDA-core fmaf chain, bit-identical to the oracle")
+    ap.add_argument("--workload", default="qnet", choices=["qnet", "rnn", "train"],
+                    help="qnet = configs[2] (the headline); rnn = configs[3] shape: QNetRNN A vs B with per-env (h, c); "
+                         "train = configs[4] shape: epsilon-greedy rollout + replay scatter + PER Double-DQN updates + grad all-reduce")
     ap.add_argument("--ref-steps", type=int, default=1500, help="reference arm: env-steps per process per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -271,15 +279,26 @@ def main():
 
     n, k = args.envs, args.lockstep
     lo = rank * n
-    torch.manual_seed(0); net_a = pp.QNet()
-    torch.manual_seed(1); net_b = pp.QNet()
     env = pp.VecPongEnv2P(n, device=dev, mode=args.mode, serve="philox", seed=2026, env_id_base=lo, **ENV_CFG)
     env.reset()
-    pa = pp.Policy.qnet(net_a, device=dev, precision=args.precision)
-    pb = pp.Policy.qnet(net_b, device=dev, precision=args.precision)
+    if args.workload == "rnn":
+        torch.manual_seed(0); net_a = pp.QNetRNN()
+        torch.manual_seed(1); net_b = pp.QNetRNN()
+        pa = pp.Policy.qnetrnn(net_a, num_envs=n, device=dev)
+        pb = pp.Policy.qnetrnn(net_b, num_envs=n, device=dev)
+        args.no_e2e = args.no_k1 = True
+        args.precision = "f32"
+    else:
+        torch.manual_seed(0); net_a = pp.QNet()
+        torch.manual_seed(1); net_b = pp.QNet()
+        pa = pp.Policy.qnet(net_a, device=dev, precision=args.precision)
+        pb = pp.Policy.qnet(net_b, device=dev, precision=args.precision)
     eng = pp.SelfPlayEngine(env, pa, pb, seed=7)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    if args.workload == "train":
+        run_train_workload(pp, ppd, args, env, net_a, net_b, dev, rank, world)
+        return
     for _ in range(args.warmup):
         eng.run(k)
     torch.cuda.synchronize()
@@ -316,11 +335,12 @@ def main():
         "outcomes": {"episodes": int(total[1].item()), "wins_a": int(total[2].item()), "wins_b": int(total[3].item()),
                      "paddle_hits": int(total[6].item())},
     }
-    tf = value / world * FLOP_PER_ENV_STEP / 1e12
-    line["roofline"] = {"bound": "tensor", "kernel": "selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel", "achieved": tf, "peak": peaks["bf16_sustained"],
+    flop = 626432 if args.workload == "rnn" else FLOP_PER_ENV_STEP
+    tf = value / world * flop / 1e12
+    line["roofline"] = {"bound": "tensor", "kernel": "selfplay_rnn_kernel" if args.workload == "rnn" else ("selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel"), "achieved": tf, "peak": peaks["bf16_sustained"],
                         "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"], "traffic": None,
                         "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
-                        "note": "algorithmic 19200 FLOP per env-step (both players' QNet) x env-steps per launch / "
+                        "note": f"algorithmic {flop} FLOP per env-step (both players' net) x env-steps per launch / "
                                 "CUDA-event launch time, per GPU"}
 
     if rank == 0 and not args.no_k1:
@@ -333,6 +353,36 @@ def main():
         line.update(cpu_baseline)
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def run_train_workload(pp, ppd, args, env, net_a, net_b, dev, rank, world):
+    """configs[4] shape per GPU: one training generation chunk loop (rollout with replay rows, prioritised batches,
+    Double-DQN on the heads, gradient and counter all-reduce).  One bench step = one chunk of `--lockstep` steps followed
+    by 4 updates of batch 256 per rank.  Prints its own JSON line (not the headline metric)."""
+    n, k = args.envs, args.lockstep
+    trainer = pp.DQNTrainer(net_b, batch_size=256, device=dev)
+    eng = pp.SelfPlayEngine(env, pp.Policy.qnet(net_a, noisy=True, precision=args.precision, device=dev),
+                            pp.Policy.qnet(net_b, noisy=True, eps=0.5, precision=args.precision, device=dev), seed=7)
+    ring = pp.ReplayRing(max(1 << 20, n * k), device=dev)
+    sampler = pp.PrioritizedSampler(ring)
+    pp.train_generation(eng, trainer, ring, sampler, k * args.warmup, chunk=k, updates_per_chunk=4, epsilon=0.5, precision=args.precision)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    out = pp.train_generation(eng, trainer, ring, sampler, k * args.steps, chunk=k, updates_per_chunk=4, epsilon=0.5, precision=args.precision)
+    torch.cuda.synchronize()
+    wall = ppd.max_over_ranks(time.perf_counter() - t0, dev)
+    if rank == 0:
+        print(json.dumps({"metric": "training-mode env-steps/sec (rollout + replay + DQN updates)", "value": out["env_steps"] / wall,
+                          "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+                          "updates_per_s": out["updates"] / wall, "mean_loss": out["mean_loss"], "epsilon": out["epsilon"],
+                          "config": {"workload": "configs[4] shape: train generation chunk loop", "envs_per_gpu": n,
+                                     "lockstep_steps_per_chunk": k, "updates_per_chunk": 4, "batch_per_rank": 256,
+                                     "replay_capacity": ring.capacity, "qnet_precision": args.precision}}), flush=True)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -1,0 +1,160 @@
+"""Training-mode host logic around the device rollout: prioritised replay sampling and the batched Double-DQN
+update of scripts/train_iterative.py, with gradients averaged over env slabs (ranks).
+
+    reference                                              here
+    PrioritizedReplay.push / sample / update_priorities    PrioritizedSampler (device tensors; rows are written by the
+      scripts/train_iterative.py:49-76                       fused rollout kernel / pp_replay_scatter into ReplayRing)
+    train_step  :132-168                                   DQNTrainer.update
+    rollout + train loop  :233-261                         train_generation
+
+The rollout (env step + both players' actions + replay rows) runs in libpong_b200.so; what is here is PyTorch
+on the device for the 520 trainable head parameters, plus the NCCL all-reduce of their gradients.
+
+How the reference's sequential schedule maps to n lock-step envs ("training semantics do not batch 1:1"):
+  * the reference does one gradient step per env step; here `updates_per_chunk` gradient steps follow every chunk
+    of `chunk` lock-step steps (n * chunk new transitions), each on `batch_size` rows PER RANK;
+  * NoisyNet noise of B is resampled per action there (:125) and per chunk here (the packed weights of a launch are
+    mu + sigma * eps for one draw); player A keeps the noise it was built with, as in the reference;
+  * epsilon decays per episode there (:261); here epsilon = max(min, decay ** (episodes finished / n)), i.e. every env
+    follows the reference's schedule on average.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+
+from . import dist as ppd
+from .policy import Policy, QNet, pack_qnet
+from .selfplay import ReplayRing, SelfPlayEngine
+
+
+class PrioritizedSampler:
+    """Proportional prioritised replay over a ReplayRing (alpha 0.6; new rows get the current maximum priority;
+    priorities become |TD| + 1e-6 after a sample is trained on) — scripts/train_iterative.py:49-76 on the device."""
+
+    def __init__(self, ring: ReplayRing, alpha: float = 0.6):
+        self.ring, self.alpha = ring, float(alpha)
+        self.prios = torch.zeros(ring.capacity, dtype=torch.float32, device=ring.obs.device)
+        self.seen = 0                                   # ring.head at the last note_new_rows()
+
+    def __len__(self):
+        return min(self.seen, self.ring.capacity)
+
+    def note_new_rows(self) -> int:
+        """Give the rows written since the last call the maximum priority (:57,62).  Returns their number."""
+        head = int(self.ring.head.item())
+        new = head - self.seen
+        if new <= 0:
+            return 0
+        cap = self.ring.capacity
+        max_p = float(self.prios.max().item()) if self.seen > 0 else 1.0
+        max_p = max_p if max_p > 0 else 1.0
+        if new >= cap:
+            self.prios.fill_(max_p)
+        else:
+            lo, hi = self.seen % cap, head % cap
+            if lo < hi:
+                self.prios[lo:hi] = max_p
+            else:
+                self.prios[lo:] = max_p
+                self.prios[:hi] = max_p
+        self.seen = head
+        return new
+
+    def sample(self, batch_size: int, beta: float, generator=None):
+        """-> (idx int64[bs], importance weights f32[bs]) — :64-73."""
+        size = len(self)
+        if size == 0:
+            raise RuntimeError("sampling from an empty replay ring")
+        probs = self.prios[:size].pow(self.alpha)
+        probs = probs / probs.sum()
+        idx = torch.multinomial(probs, batch_size, replacement=True, generator=generator)
+        w = (size * probs[idx]).pow(-beta)
+        return idx, w / w.max()
+
+    def update_priorities(self, idx, td_abs):
+        self.prios[idx] = td_abs.detach().abs().to(torch.float32) + 1e-6           # :74-76
+
+
+class DQNTrainer:
+    """Double-DQN on the NoisyNet heads of player B (features frozen) — scripts/train_iterative.py:93-104,132-168."""
+
+    def __init__(self, model_b: QNet, gamma: float = 0.99, lr: float = 2.5e-4, batch_size: int = 256,
+                 target_update_interval: int = 1000, beta_start: float = 0.4, beta_frames: int = 100000, device="cuda"):
+        self.device = torch.device(device)
+        self.model = model_b.to(self.device)
+        for p in self.model.features.parameters():                                   # :97
+            p.requires_grad = False
+        self.target = copy.deepcopy(self.model)
+        self.target.eval()                                                             # :100
+        self.head_params = list(self.model.fc_V.parameters()) + list(self.model.fc_A.parameters())
+        self.opt = torch.optim.Adam(self.head_params, lr=lr)                         # :101-104
+        self.gamma, self.batch_size, self.target_update_interval = gamma, batch_size, target_update_interval
+        self.beta_start, self.beta_frames = beta_start, beta_frames
+        self.frame_idx = self.train_steps = 0
+
+    def update(self, sampler: PrioritizedSampler, generator=None) -> float | None:
+        """One train_step().  Returns the loss, or None while the ring holds fewer than batch_size rows (:134-135)."""
+        if len(sampler) < self.batch_size:
+            return None
+        ring = sampler.ring
+        self.frame_idx += 1
+        beta = min(1.0, self.beta_start + self.frame_idx * (1.0 - self.beta_start) / self.beta_frames)
+        idx, iw = sampler.sample(self.batch_size, beta, generator)
+        self.model.reset_noise()                                                       # :142-143
+        self.target.reset_noise()
+        s, ns = ring.obs[idx], ring.next_obs[idx]
+        a = ring.act[idx].to(torch.int64)
+        r, d = ring.rew[idx], ring.done[idx] != 0
+        q = self.model(s).gather(1, a.unsqueeze(1)).squeeze(1)                         # :152
+        with torch.no_grad():
+            na = self.model(ns).argmax(1, keepdim=True)                                # :154
+            nq = self.target(ns).gather(1, na).squeeze(1)                              # :155
+        targets = r + self.gamma * nq * (~d)                                           # :156
+        td = q - targets
+        loss = (iw * td.pow(2)).mean()                                                 # :158
+        self.opt.zero_grad(set_to_none=False)
+        loss.backward()
+        ppd.allreduce_mean_grads(self.head_params)                                     # one NCCL all-reduce of 520 floats
+        self.opt.step()
+        sampler.update_priorities(idx, td)                                             # :163-164
+        self.train_steps += 1
+        if self.train_steps % self.target_update_interval == 0:                        # :166-168
+            self.target.load_state_dict(self.model.state_dict())
+        return float(loss.detach())
+
+
+def train_generation(engine: SelfPlayEngine, trainer: DQNTrainer, ring: ReplayRing, sampler: PrioritizedSampler,
+                     lockstep_steps: int, chunk: int = 16, updates_per_chunk: int = 4, epsilon: float = 1.0,
+                     epsilon_decay: float = 0.995, min_epsilon: float = 0.02, precision: str = "f32") -> dict:
+    """The rollout + train loop of one generation (scripts/train_iterative.py:233-261) for the engine's slab:
+    B (epsilon-greedy, train-mode NoisyNet weights of `trainer.model`) learns against the engine's player A.
+    Returns the slab's counters summed over ranks, the final epsilon and the number of updates."""
+    env = engine.env
+    env.counters.zero_()
+    dev = env.device
+    eps0, losses, done_steps = float(epsilon), [], 0
+    if engine.pb.weights is None:
+        engine.pb = Policy.qnet(trainer.model, noisy=True, eps=epsilon, precision=precision, device=dev)
+    while done_steps < lockstep_steps:
+        k = min(chunk, lockstep_steps - done_steps)
+        trainer.model.reset_noise()                                                    # B's noise: one draw per chunk
+        engine.pb.set_weights(pack_qnet(trainer.model, noisy=True))
+        engine.pb.eps = epsilon
+        engine.run(k, ring=ring)
+        done_steps += k
+        sampler.note_new_rows()
+        for _ in range(updates_per_chunk):
+            loss = trainer.update(sampler)
+            if loss is not None:
+                losses.append(loss)
+        episodes = int(ppd.allreduce_counters(env.counters)[1].item())
+        world = torch.distributed.get_world_size() if ppd.is_parallel() else 1
+        epsilon = max(min_epsilon, eps0 * epsilon_decay ** (episodes / (env.n * world)))     # :261, per env on average
+    total = ppd.allreduce_counters(env.counters)
+    out = dict(zip(("env_steps", "episodes", "wins_a", "wins_b", "points_a", "points_b", "paddle_hits", "ep_len_sum"),
+                   total.tolist()))
+    out.update(epsilon=epsilon, updates=len(losses), mean_loss=(sum(losses) / len(losses) if losses else None),
+               train_steps=trainer.train_steps)
+    return out

@@ -337,3 +337,38 @@ def test_selfplay_qnetrnn_rollout_teacher_forced(H, kinds):
 
 def test_selfplay_qnetrnn_quota_and_f32_mode(H):
     _rnn_teacher_forced_check(H["env_config_rnn_yaml"], 130, 90, ("rnn_a", "rnn_b"), mode="f32", quota=2)
+
+
+# ------------------------------------------------------------------------------------------ training mode
+@pytest.mark.parametrize("prec", ["f32", "f16"])
+def test_train_generation_rollout_replay_and_updates(H, prec):
+    """Config 5 shape on one slab: epsilon-greedy rollout of the learning player B (train-mode NoisyNet weights) writes
+    replay rows on the device, prioritised batches train the heads only, the target net syncs, epsilon decays."""
+    cfg = H["env_config_yaml"]
+    n, steps = 2048, 96
+    torch.manual_seed(0); net_a = pp.QNet()
+    torch.manual_seed(1); net_b = pp.QNet()
+    before = {k: v.clone() for k, v in net_b.state_dict().items()}
+    env = pp.VecPongEnv2P(n, mode="f64", serve="philox", seed=5, **cfg)
+    env.reset()
+    trainer = pp.DQNTrainer(net_b, batch_size=256, target_update_interval=8, lr=1e-3)
+    eng = pp.SelfPlayEngine(env, pp.Policy.qnet(net_a, noisy=True, precision=prec),
+                            pp.Policy.qnet(net_b, noisy=True, eps=1.0, precision=prec), seed=3)
+    ring = pp.ReplayRing(n * 64)
+    sampler = pp.PrioritizedSampler(ring)
+    out = pp.train_generation(eng, trainer, ring, sampler, steps, chunk=16, updates_per_chunk=3, epsilon=1.0,
+                              epsilon_decay=0.9, min_epsilon=0.02, precision=prec)
+    assert out["env_steps"] == n * steps and int(ring.head.item()) == n * steps and len(sampler) == ring.capacity
+    assert out["updates"] == 6 * 3 and trainer.train_steps == 18 and out["mean_loss"] > 0
+    assert 0.02 <= out["epsilon"] < 1.0 and out["episodes"] > n
+    after = trainer.model.state_dict()
+    for k in before:
+        same = torch.equal(before[k].to(after[k].device), after[k])
+        assert same == (k.startswith("features") or k.endswith("epsilon") and False), k     # heads (and their noise) move, features do not
+    for p, q in zip(trainer.model.parameters(), trainer.target.parameters()):
+        assert torch.allclose(p, q, atol=5e-3)                                               # synced at update 16, two Adam steps ago
+    # the ring holds B's view: rewards in {-1, 0, +1}, actions in {0, 1, 2}, done only with a non-zero reward
+    rew, done, act = gu.np_of(ring.rew), gu.np_of(ring.done), gu.np_of(ring.act)
+    assert set(np.unique(rew)) <= {-1.0, 0.0, 1.0} and act.max() <= 2 and np.all(rew[done != 0] != 0)
+    # epsilon = 1.0 at the start: B's first actions are uniform over {0, 1, 2}
+    assert 0.3 < (act == 1).mean() < 0.45
