@@ -443,7 +443,7 @@ def measure_e2e(pp, net_a, net_b, args):
     ang = np.radians(np.where(rs.rand(quota, n) < 0.5, rs.uniform(-60, -30, size=(quota, n)), rs.uniform(30, 60, size=(quota, n))))
     rt = np.float64 if args.mode == "f64" else np.float32
     pool = ((speed * np.cos(ang)).astype(rt), (speed * np.sin(ang)).astype(rt), rs.uniform(-5, 5, size=(quota, n)).astype(rt))
-    wa, wb = pp.pack_qnet(net_a).numpy(), pp.pack_qnet(net_b).numpy()
+    wa, wb = pp.pack_qnet(net_a).cpu().numpy(), pp.pack_qnet(net_b).cpu().numpy()
     pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep, precision=args.precision)  # warm-up
     reps, steps_total, t0 = 3, 0, time.perf_counter()
     for _ in range(reps):

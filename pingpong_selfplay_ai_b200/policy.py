@@ -116,7 +116,8 @@ class QNetRNN(_NoisyNet):
 # ----------------------------------------------------------------------------------------- packing
 def _sd(obj):
     sd = obj.state_dict() if isinstance(obj, nn.Module) else obj
-    return {k: (v.detach().to("cpu", torch.float32) if torch.is_tensor(v) else torch.as_tensor(np.asarray(v), dtype=torch.float32))
+    # tensors stay on their device (packing a CUDA model is a handful of device kernels, no host round trip)
+    return {k: (v.detach().to(torch.float32) if torch.is_tensor(v) else torch.as_tensor(np.asarray(v), dtype=torch.float32))
             for k, v in sd.items()}
 
 
@@ -129,7 +130,7 @@ def _noisy(sd, prefix, noisy):
 
 
 def pack_qnet(model_or_state_dict, noisy: bool = False) -> torch.Tensor:
-    """Effective fp32 weights of a QNet -> the k-major blob of include/pong_b200.h (PP_QNET_*), on the CPU.
+    """Effective fp32 weights of a QNet -> the k-major blob of include/pong_b200.h (PP_QNET_*), on the model's device.
     noisy=False is eval mode (mu); noisy=True is the train-mode forward the reference's training script plays
     with (scripts/train_iterative.py never calls .eval() on modelA / modelB)."""
     sd = _sd(model_or_state_dict)
@@ -145,7 +146,7 @@ def pack_qnet(model_or_state_dict, noisy: bool = False) -> torch.Tensor:
 
 
 def pack_qnetrnn(model_or_state_dict, noisy: bool = False) -> torch.Tensor:
-    """QNetRNN (default dims 7-64-128 / LSTM 128 / head 128) -> the PP_RNN_* blob, on the CPU.  The gate matrix
+    """QNetRNN (default dims 7-64-128 / LSTM 128 / head 128) -> the PP_RNN_* blob, on the model's device.  The gate matrix
     is [W_ih^T ; W_hh^T] (k-major, 256 rows) with columns ordered unit*4 + gate (gates i, f, g, o)."""
     sd = _sd(model_or_state_dict)
     wf1, wf2 = sd["features_extractor.0.weight"], sd["features_extractor.2.weight"]

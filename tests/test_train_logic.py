@@ -64,7 +64,8 @@ def test_dqn_update_equals_reference_train_step_restated():
         torch.manual_seed(100 + step)
         beta = min(1.0, 0.4 + step * (1.0 - 0.4) / 100000)
         probs = ref_prios[:3000] ** 0.6; probs = probs / probs.sum()
-        idxs = torch.multinomial(probs, 256, replacement=True)
+        cdf = probs.cumsum(0)                                  # np.random.choice(p=probs): inverse CDF
+        idxs = torch.searchsorted(cdf, torch.rand(256) * cdf[-1], right=True).clamp(max=2999)
         iw = (3000 * probs[idxs]) ** (-beta); iw = iw / iw.max()
         ref_model.reset_noise(); ref_target.reset_noise()
         st, a, r = ring.obs[idxs], ring.act[idxs].long(), ring.rew[idxs]
@@ -79,7 +80,7 @@ def test_dqn_update_equals_reference_train_step_restated():
         ref_prios[idxs] = (q_vals - targets).detach().abs() + 1e-6
         if step % 2 == 0:
             ref_target.load_state_dict(ref_model.state_dict())
-        assert loss == pytest.approx(float(ref_loss), rel=1e-6)
+        assert float(loss) == pytest.approx(float(ref_loss.detach()), rel=1e-6)
         for p, q in zip(tr.model.state_dict().values(), ref_model.state_dict().values()):
             assert torch.equal(p, q)
         for p, q in zip(tr.target.state_dict().values(), ref_target.state_dict().values()):
