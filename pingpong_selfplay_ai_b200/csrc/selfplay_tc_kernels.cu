@@ -12,11 +12,15 @@
 //                                                  W1h' = [W1_hi ; b1_hi | W1_hi ; b1_lo], W1l' = [W1_lo ; 0 | 0]
 //     L2  D[128x64] = H1h*W2h^T + H1l*W2h^T + H1h*W2l^T (3 x 4 MMAs, K = 16 each) + X * B2'^T (bias via X's ones)
 //     L3  D[128x16] = same with the dueling heads, N = 16 (columns 0..3 = V, A0, A1, A2)
-// Between layers each thread reads ITS row of the accumulator (tcgen05.ld 32x32b), applies ReLU, splits and
-// stores the row as the next A operand.  Operands use the no-swizzle K-major canonical layout stored as
+// Between layers each thread reads ITS row of the accumulator (tcgen05.ld 32x32b), applies ReLU, splits and writes
+// the row back to TENSOR MEMORY (tcgen05.st) as the next A operand: hidden activations never touch shared memory,
+// the MMAs read A from TMEM (two fp16 per 32-bit column) and only the small weight tiles from shared memory.  A
+// group owns 128 TMEM columns, used as two 64-column regions that ping-pong between accumulator and A operand:
+//     L1 -> R0;  epilogue R0 -> H1 in R1;  L2 (A = R1) -> R0;  epilogue R0 -> H2 in R1;  L3 (A = R1) -> R0[0..15]
+// The shared-memory operands (X rows, weight tiles) use the no-swizzle K-major canonical layout stored as
 // [K/8][rows][8 halves]: a thread's 16-byte chunk stores are contiguous across the warp (conflict-free) and the
 // descriptor strides are LBO = rows*16 B (next K chunk), SBO = 128 B (next 8-row core matrix).
-// L1 of both players is issued together; then player A's L2/L3 chain runs, then B's, sharing one H tile.
+// The two players' chains run one after the other in the same two regions.
 // Both players' fp32 weight blobs arrive by one TMA bulk copy each (cp.async.bulk + mbarrier) into a staging
 // area and are converted once per launch into fp16 B-operand tiles that stay in shared memory for all k steps.
 // Env state, observations and bookkeeping never leave registers (same step_and_book as the CUDA-core kernel).
@@ -41,8 +45,9 @@ constexpr uint32_t W1_BYTES = 2 * 64 * 16, W2_BYTES = 8 * 64 * 16, B2_BYTES = 2 
 constexpr uint32_t W1H_OFF = 0, W1L_OFF = W1H_OFF + W1_BYTES, W2H_OFF = W1L_OFF + W1_BYTES, W2L_OFF = W2H_OFF + W2_BYTES,
                    B2_OFF = W2L_OFF + W2_BYTES, W3H_OFF = B2_OFF + B2_BYTES, W3L_OFF = W3H_OFF + W3_BYTES,
                    B3_OFF = W3L_OFF + W3_BYTES, PLAYER_W_BYTES = B3_OFF + B3_BYTES;              // 27136
-constexpr uint32_t X_BYTES = 2 * G_ROWS * 16, H_HALF = 8 * G_ROWS * 16, H_BYTES = 2 * H_HALF;    // 4096, 16384, 32768
-constexpr uint32_t GROUP_BYTES = 2 * X_BYTES + H_BYTES;                                          // 40960
+constexpr uint32_t X_BYTES = 2 * G_ROWS * 16;                                                    // 4096
+constexpr uint32_t GROUP_BYTES = 2 * X_BYTES;                                                    // X rows of both players
+constexpr uint32_t TM_R1 = 64, TM_LO = 32;      // TMEM columns: region R1 = R0 + 64; inside R1: hi at +0, lo at +32
 constexpr uint32_t BLOB_BYTES = PP_QNET_BLOB_FLOATS * 4;                                         // 19728
 
 template <int GROUPS> struct SmemMap {
@@ -53,7 +58,7 @@ template <int GROUPS> struct SmemMap {
 };
 
 struct PlayerTiles {     // shared-memory (generic) pointers of one player's operands
-    uint8_t *w, *x, *h;
+    uint8_t *w, *x;
 };
 
 __device__ __forceinline__ float h2f(uint32_t packed, int hi) {
@@ -109,53 +114,49 @@ __device__ __forceinline__ void write_x_row(uint8_t *x, int row, const float (&o
     *reinterpret_cast<uint4 *>(x + A_LBO + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// 8 accumulator columns -> ReLU -> (hi, lo) fp16 chunks of this thread's row.  hi = rz(relu(x)) <= relu(x), so for
-// x >= 0 the residual x - hi is >= 0 and for x < 0 it is x < 0: one more ReLU-convert yields lo = relu(x) - hi.
-__device__ __forceinline__ void split_store8(const uint32_t *r, uint8_t *h, int chunk, int row) {
-    uint32_t p[4], q[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
-        p[j] = tc::pack_f16x2_rz_relu(a, b);
-        q[j] = tc::pack_f16x2<true>(a - h2f(p[j], 0), b - h2f(p[j], 1));
-    }
-    *reinterpret_cast<uint4 *>(h + chunk * A_LBO + row * 16) = make_uint4(p[0], p[1], p[2], p[3]);
-    *reinterpret_cast<uint4 *>(h + H_HALF + chunk * A_LBO + row * 16) = make_uint4(q[0], q[1], q[2], q[3]);
-}
-
-// accumulator row (64 fp32 columns at taddr) -> ReLU -> hi/lo fp16 -> this thread's row of the next A tiles
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *h, int row) {
+// Accumulator row (64 fp32 columns at `src`) -> ReLU -> hi/lo fp16 -> this thread's row of the next A operand in
+// TMEM (`dst`: 32 columns of packed hi pairs, then 32 columns of packed lo pairs).  hi = rz(relu(x)) <= relu(x), so
+// for x >= 0 the residual x - hi is >= 0 and for x < 0 it is x < 0: one more ReLU-convert yields lo = relu(x) - hi.
+__device__ __forceinline__ void hidden_epilogue(uint32_t src, uint32_t dst) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-        uint32_t r0[16], r1[16];
-        tc::tmem_ld16(taddr + half * 32, r0);
-        tc::tmem_ld16(taddr + half * 32 + 16, r1);
+        uint32_t r0[16], r1[16], hi[16], lo[16];
+        tc::tmem_ld16(src + half * 32, r0);
+        tc::tmem_ld16(src + half * 32 + 16, r1);
         tc::tmem_ld_wait();
-        split_store8(r0, h, half * 4 + 0, row);
-        split_store8(r0 + 8, h, half * 4 + 1, row);
-        split_store8(r1, h, half * 4 + 2, row);
-        split_store8(r1 + 8, h, half * 4 + 3, row);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = __uint_as_float(r0[2 * j]), b = __uint_as_float(r0[2 * j + 1]);
+            hi[j] = tc::pack_f16x2_rz_relu(a, b);
+            lo[j] = tc::pack_f16x2<true>(a - h2f(hi[j], 0), b - h2f(hi[j], 1));
+            const float c = __uint_as_float(r1[2 * j]), d = __uint_as_float(r1[2 * j + 1]);
+            hi[8 + j] = tc::pack_f16x2_rz_relu(c, d);
+            lo[8 + j] = tc::pack_f16x2<true>(c - h2f(hi[8 + j], 0), d - h2f(hi[8 + j], 1));
+        }
+        tc::tmem_st16(dst + half * 16, hi);
+        tc::tmem_st16(dst + TM_LO + half * 16, lo);
     }
+    tc::tmem_st_wait();
 }
 
-// MMA batches, issued by one thread per group
+// MMA batches, issued by one thread per group.  d / a_tm are TMEM addresses with lane 0.
 __device__ __forceinline__ void issue_l1(uint32_t d, const PlayerTiles &p) {
     const uint64_t x = tc::smem_desc(tc::smem_u32(p.x), A_LBO, SBO);
     tc::umma_f16(d, x, tc::smem_desc(tc::smem_u32(p.w + W1H_OFF), 64 * 16, SBO), tc::idesc_f16(128, 64), false);
     tc::umma_f16(d, x, tc::smem_desc(tc::smem_u32(p.w + W1L_OFF), 64 * 16, SBO), tc::idesc_f16(128, 64), true);
 }
-// D = Hh*Wh + Hl*Wh + Hh*Wl + X*B'   (N = 64 hidden layer or N = 16 heads)
+// D = Hh*Wh + Hl*Wh + Hh*Wl + X*B'   (N = 64 hidden layer or N = 16 heads); H = [hi | lo] in TMEM at a_tm
 template <int N>
-__device__ __forceinline__ void issue_dense(uint32_t d, const PlayerTiles &p, uint32_t wh_off, uint32_t wl_off, uint32_t b_off) {
-    const uint32_t hh = tc::smem_u32(p.h), hl = hh + H_HALF, wh = tc::smem_u32(p.w + wh_off), wl = tc::smem_u32(p.w + wl_off);
+__device__ __forceinline__ void issue_dense(uint32_t d, uint32_t a_tm, const PlayerTiles &p, uint32_t wh_off, uint32_t wl_off,
+                                            uint32_t b_off) {
+    const uint32_t wh = tc::smem_u32(p.w + wh_off), wl = tc::smem_u32(p.w + wl_off);
     constexpr uint32_t B_LBO = N * 16;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = pass == 1 ? hl : hh, b = pass == 2 ? wl : wh;
+        const uint32_t a = pass == 1 ? a_tm + TM_LO : a_tm, b = pass == 2 ? wl : wh;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            tc::umma_f16(d, tc::smem_desc(a + j * 2 * A_LBO, A_LBO, SBO), tc::smem_desc(b + j * 2 * B_LBO, B_LBO, SBO),
-                         tc::idesc_f16(128, N), (pass | j) != 0);
+        for (int j = 0; j < 4; ++j)         // K = 16 per MMA = 8 TMEM columns of A, 2 shared-memory chunks of B
+            tc::umma_f16_ts(d, a + j * 8, tc::smem_desc(b + j * 2 * B_LBO, B_LBO, SBO), tc::idesc_f16(128, N), (pass | j) != 0);
     }
     tc::umma_f16(d, tc::smem_desc(tc::smem_u32(p.x), A_LBO, SBO), tc::smem_desc(tc::smem_u32(p.w + b_off), B_LBO, SBO),
                  tc::idesc_f16(128, N), true);
@@ -208,12 +209,11 @@ template <int GROUPS> __device__ __forceinline__ void tc_epilogue(uint32_t tmem)
     if (threadIdx.x < 32) tc::tmem_dealloc<GROUPS * 128>(tmem);
 }
 
-// One policy evaluation round for a group: X rows are already written.  Returns greedy Q of both players.
+// One policy evaluation round for a group: X rows are already written and published by a group barrier.
 struct GroupCtx {
     PlayerTiles pa, pb;
     uint64_t *bar;
-    uint32_t parity, d_a, d_b, bar_id, lane_addr;
-    int row;
+    uint32_t parity, r0, bar_id, lane_addr;      // r0: the group's first TMEM column (lane 0); R1 = r0 + TM_R1
     bool qa, qb, issuer_warp;
 };
 
@@ -223,42 +223,42 @@ __device__ __forceinline__ void group_wait(GroupCtx &g) {
     tc::tc_fence_after();
 }
 
-// after the barrier that published the X rows: L1 (both players) -> per player: H1 -> L2 -> H2 -> L3 -> Q.
-// Self-issuing variant (an elected lane of the group's first warp issues): used by the standalone kernel.
-__device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
+// 0 = L1, 1 = L2, 2 = L3 of player p; an elected lane of the group's first warp issues, everybody waits
+__device__ __forceinline__ void group_mma(GroupCtx &g, const PlayerTiles &p, int layer) {
     if (g.issuer_warp) {                      // warp-uniform branch
         if (tc::elect_one()) {
             tc::tc_fence_after();
-            if (g.qa) issue_l1(g.d_a, g.pa);
-            if (g.qb) issue_l1(g.d_b, g.pb);
+            if (layer == 0) issue_l1(g.r0, p);
+            else if (layer == 1) issue_dense<64>(g.r0, g.r0 + TM_R1, p, W2H_OFF, W2L_OFF, B2_OFF);
+            else issue_dense<16>(g.r0, g.r0 + TM_R1, p, W3H_OFF, W3L_OFF, B3_OFF);
             tc::umma_commit(g.bar);
         }
         __syncwarp();
     }
     group_wait(g);
+}
+
+// per QNet player: L1 -> H1 -> L2 -> H2 -> L3 -> Q, all in the group's two TMEM regions
+__device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
+    bool first = true;
 #pragma unroll 1
     for (int pl = 0; pl < 2; ++pl) {
         if (!(pl ? g.qb : g.qa)) continue;
         const PlayerTiles &p = pl ? g.pb : g.pa;
-        const uint32_t d = pl ? g.d_b : g.d_a;
-#pragma unroll 1
-        for (int layer = 0; layer < 2; ++layer) {
-            hidden_epilogue(d + g.lane_addr, p.h, g.row);
-            tc::fence_proxy_async();
+        if (!first) {                          // R0 still holds the first player's head outputs until everyone has read them
             tc::tc_fence_before();
             tc::bar_sync(g.bar_id, G_ROWS);
-            if (g.issuer_warp) {
-                if (tc::elect_one()) {
-                    tc::tc_fence_after();
-                    if (layer == 0) issue_dense<64>(d, p, W2H_OFF, W2L_OFF, B2_OFF);
-                    else issue_dense<16>(d, p, W3H_OFF, W3L_OFF, B3_OFF);
-                    tc::umma_commit(g.bar);
-                }
-                __syncwarp();
-            }
-            group_wait(g);
         }
-        if (pl) dueling_q(d + g.lane_addr, q_b); else dueling_q(d + g.lane_addr, q_a);
+        first = false;
+        group_mma(g, p, 0);
+#pragma unroll 1
+        for (int layer = 1; layer <= 2; ++layer) {
+            hidden_epilogue(g.r0 + g.lane_addr, g.r0 + TM_R1 + g.lane_addr);
+            tc::tc_fence_before();
+            tc::bar_sync(g.bar_id, G_ROWS);
+            group_mma(g, p, layer);
+        }
+        if (pl) dueling_q(g.r0 + g.lane_addr, q_b); else dueling_q(g.r0 + g.lane_addr, q_a);
     }
 }
 
@@ -268,15 +268,13 @@ __device__ __forceinline__ GroupCtx make_group(uint8_t *smem, uint32_t groups_of
                                                int row, bool qa, bool qb) {
     GroupCtx g;
     uint8_t *gb = smem + groups_off + grp * GROUP_BYTES;
-    g.pa = PlayerTiles{smem, gb, gb + 2 * X_BYTES};                                // the H tile is shared: the
-    g.pb = PlayerTiles{smem + PLAYER_W_BYTES, gb + X_BYTES, gb + 2 * X_BYTES};    // players' chains run one after the other
+    g.pa = PlayerTiles{smem, gb};
+    g.pb = PlayerTiles{smem + PLAYER_W_BYTES, gb + X_BYTES};
     g.bar = reinterpret_cast<uint64_t *>(smem + ctrl_off) + 1 + grp;
     g.parity = 0;
-    g.d_a = tmem + grp * 128;
-    g.d_b = tmem + grp * 128 + 64;
+    g.r0 = tmem + grp * 128;
     g.bar_id = 1 + grp;
     g.lane_addr = (uint32_t)((row >> 5) * 32) << 16;
-    g.row = row;
     g.qa = qa; g.qb = qb;
     g.issuer_warp = __shfl_sync(0xffffffffu, (row >> 5) == 0 ? 1 : 0, 0) != 0;
     return g;
@@ -333,7 +331,7 @@ struct FusedMap {
     static constexpr uint32_t TOTAL = CTRL + 64;
 };
 static_assert(FusedMap::TOTAL <= 232448, "shared memory of the fused tensor-core kernel exceeds 227 KB");
-static_assert(2 * BLOB_BYTES <= CTA_GROUPS * GROUP_BYTES, "weight staging must fit in the group tiles");
+static_assert(2 * BLOB_BYTES <= CTA_GROUPS * GROUP_BYTES + TC_FUSED_THREADS * 24, "weight staging aliases the X rows and serve slots");
 
 template <typename R>
 __global__ void __launch_bounds__(TC_FUSED_THREADS, 1)
