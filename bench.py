@@ -442,8 +442,14 @@ def measure_e2e(pp, net_a, net_b, args):
     speed = rs.uniform(0.03, 0.05, size=(quota, n))
     ang = np.radians(np.where(rs.rand(quota, n) < 0.5, rs.uniform(-60, -30, size=(quota, n)), rs.uniform(30, 60, size=(quota, n))))
     rt = np.float64 if args.mode == "f64" else np.float32
-    pool = ((speed * np.cos(ang)).astype(rt), (speed * np.sin(ang)).astype(rt), rs.uniform(-5, 5, size=(quota, n)).astype(rt))
-    wa, wb = pp.pack_qnet(net_a).cpu().numpy(), pp.pack_qnet(net_b).cpu().numpy()
+    def pinned(a):                                      # the step's inputs live in PINNED host memory (bench contract)
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+    keep = []
+    pool = tuple(pinned(a) for a in ((speed * np.cos(ang)).astype(rt), (speed * np.sin(ang)).astype(rt),
+                                     rs.uniform(-5, 5, size=(quota, n)).astype(rt)))
+    wa, wb = pinned(pp.pack_qnet(net_a).cpu().numpy()), pinned(pp.pack_qnet(net_b).cpu().numpy())
     pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep, precision=args.precision)  # warm-up
     reps, steps_total, t0 = 3, 0, time.perf_counter()
     for _ in range(reps):
@@ -452,7 +458,8 @@ def measure_e2e(pp, net_a, net_b, args):
     wall = time.perf_counter() - t0
     h2d = 3 * quota * n * np.dtype(rt).itemsize + 2 * wa.nbytes
     return {"value": steps_total / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 72,
-            "call": "pp_host_selfplay_eval (eval_vs_model for 65536 envs x 8 episodes each, host numpy buffers)",
+            "call": "pp_host_selfplay_eval (eval_vs_model for 65536 envs x 8 episodes each; pinned host numpy buffers in, "
+                    "counters out; serve queue, one launch)",
             "episodes_per_call": int(c["episodes"]), "env_steps_per_call": int(c["env_steps"]), "ms_per_call": 1e3 * wall / reps}
 
 
