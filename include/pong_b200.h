@@ -112,7 +112,8 @@ typedef struct PPPolicy {
     uint64_t eps_threshold;     /* explore iff (uint64)philox.x < eps_threshold; floor(eps * 2^32), 0 = greedy */
     float follower_tol;         /* tests/arena.py:213                                                       */
     int32_t reserved;
-    const float *weights;       /* packed blob, see PP_QNET_* / PP_RNN_* offsets                            */
+    const float *weights;       /* packed blob, see PP_QNET_* / PP_RNN_* offsets (QNetRNN with PP_PREC_F16: the
+                                 * fp16 image PP_RNNTC_*)                                                     */
     float *h, *c;               /* QNetRNN only: [n][128] each, zeroed by the engine at episode start       */
 } PPPolicy;
 
@@ -131,6 +132,28 @@ enum {
     PP_RNN_WF1T = 0, PP_RNN_BF1 = 448, PP_RNN_WF2T = 512, PP_RNN_BF2 = 8704, PP_RNN_WGT = 8832,
     PP_RNN_BG = 139904, PP_RNN_WST = 140416, PP_RNN_BS = 156800, PP_RNN_WHT = 156928, PP_RNN_BH = 157440,
     PP_RNN_BLOB_FLOATS = 157444
+};
+
+/* QNetRNN image for the tensor-core path (precision PP_PREC_F16): fp16 B-operand tiles in the order the kernel
+ * streams them through shared memory with TMA, one "stage" per bulk copy.  Every tile is K-major, no swizzle,
+ * [K/8][N][8 halves]; *H = fp16(w), *L = fp16(w - fp16(w)); a bias tile is [2][N][8] with the bias split hi / lo in
+ * rows k = 7 / 15 (it multiplies the ones columns of the observation tile).  Offsets in BYTES:
+ *   S0   W1H[2][64][8] W1L[2][64][8]                       features.0 (obs hi/lo, bias in rows 7/15)
+ *   S1   WF2H[8][128][8] BF2[2][128][8]     S2  WF2L[8][128][8]        features.2   64 -> 128
+ *   per quarter q = 0..3 (units 32q..32q+31), K rows 64c..64c+63 of [W_ih^T ; W_hh^T], column = gate*32 + unit%32:
+ *        GH(q,c) c = 0..3: WGH[8][128][8] (GH(q,0) is followed by its bias tile BG[2][128][8] = b_ih + b_hh),
+ *        then GL(q,c) c = 0..3: WGL[8][128][8]
+ *   WS0  WSH k<64 + BS[2][128][8]   WS1  WSH k>=64   WS2  WSL k<64   WS3  WSL k>=64      fc_shared_head 128 -> 128
+ *   HD   WHH[16][16][8] WHL[16][16][8] BH[2][16][8]        dueling heads, columns 0..3 = V, A0, A1, A2 */
+enum {
+    PP_RNNTC_TILE = 16384, PP_RNNTC_BIAS = 4096,
+    PP_RNNTC_S0 = 0, PP_RNNTC_S0_BYTES = 4096,
+    PP_RNNTC_S1 = 4096, PP_RNNTC_S1_BYTES = 20480,
+    PP_RNNTC_S2 = 24576, PP_RNNTC_S2_BYTES = 16384,
+    PP_RNNTC_G = 40960, PP_RNNTC_GQ_BYTES = 135168,       /* per quarter: 20480 + 7 * 16384 */
+    PP_RNNTC_WS = 581632, PP_RNNTC_WS_BYTES = 69632,
+    PP_RNNTC_HD = 651264, PP_RNNTC_HD_BYTES = 8704,
+    PP_RNNTC_BLOB_BYTES = 659968, PP_RNNTC_STAGES = 40, PP_RNNTC_SLOT_BYTES = 20480
 };
 
 /* Per-call outputs of the multi-step kernels.  counters[8] (accumulated with atomics, never reset

@@ -22,6 +22,7 @@ STREAM_ACT_A, STREAM_ACT_B = 1, 2
 
 QNET_BLOB_FLOATS = 4932
 QNET_OFF = dict(W1T=0, B1=448, W2T=512, B2=4608, WHT=4672, BH=4928)
+RNNTC_BLOB_BYTES = 659968
 RNN_BLOB_FLOATS = 157444
 RNN_OFF = dict(WF1T=0, BF1=448, WF2T=512, BF2=8704, WGT=8832, BG=139904, WST=140416, BS=156800, WHT=156928,
                BH=157440)

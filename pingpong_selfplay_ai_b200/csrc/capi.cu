@@ -133,9 +133,12 @@ int pp_qnetrnn_act(int64_t n, const float *obs, const PPPolicy *policy, const ui
                    int64_t step_index, int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out, void *stream) {
     if (n < 0) return fail(PP_E_SIZE, "pp_qnetrnn_act");
     if (!obs || !actions) return fail(PP_E_NULL, "pp_qnetrnn_act");
-    if (!policy_ok(policy, true) || policy->kind != PP_POLICY_QNETRNN || policy->precision != PP_PREC_F32)
+    if (!policy_ok(policy, true) || policy->kind != PP_POLICY_QNETRNN || !prec_ok(policy))
         return fail(PP_E_MODE, "pp_qnetrnn_act");
     if (n == 0) return 0;
+    if (policy->precision == PP_PREC_F16)        // weights = the fp16 stage image PP_RNNTC_*
+        return ok_or(pp::qnetrnn_act_tc_launch(n, obs, *policy, reset_mask, seed, step_index, env_id_base, stream_id,
+                                               actions, q_out, (cudaStream_t)stream), "pp_qnetrnn_act");
     return ok_or(pp::qnetrnn_act_launch(n, obs, *policy, reset_mask, seed, step_index, env_id_base, stream_id, actions,
                                         q_out, (cudaStream_t)stream), "pp_qnetrnn_act");
 }

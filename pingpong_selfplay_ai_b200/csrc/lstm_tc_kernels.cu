@@ -1,0 +1,460 @@
+// lstm_tc_kernels.cu — K2b on the tensor cores: one QNetRNN step (models/qnet_rnn.py:107-144, seq_len 1) for a
+// 128-env tile per CTA, every layer a tcgen05.mma batch with fp32 accumulation in TMEM (PP_PREC_F16).
+//
+// Roles: 4 compute warps (thread = env = TMEM lane) + 1 issuer warp whose elected lane streams the weight image
+// PP_RNNTC_* from L2 through a 4-slot shared-memory ring with TMA bulk copies AND issues every MMA.  The two sides
+// meet only at mbarriers:  ready (128 arrivals: "my operand rows are written"), done[2] (tcgen05.commit: "accumulator
+// buffer b is complete"), dfree[2] (128 arrivals: "buffer b has been drained").
+//
+// Tensor memory (all 512 columns of the SM):
+//     [  0,128) A_hi   gate operand [f2 | h_prev] (fp16 pairs), later the shared-head output s      (K = 256)
+//     [128,256) A_lo   low halves of the same
+//     [256,384) D0     accumulator buffer 0          [384,512) D1   accumulator buffer 1 (its first 64 columns also
+//                                                                    hold F1 hi/lo, the operand of features.2)
+// Per player-step:  L1 (X*W1 -> D0) -> F1 -> features.2 (-> D0, N = 128) -> f2 into A | h_prev staged into A ->
+// gates in four quarters of 32 units (N = 128 = 4 gates x 32, K = 256), double-buffered D0/D1 so the LSTM cell of
+// quarter q runs on the CUDA cores while the tensor core computes quarter q+1 -> h_new as an fp16 hi/lo A tile in
+// shared memory -> shared head (-> D0) -> s into A -> dueling heads (-> D1[0..15]) -> Q.
+// Activations and weights are split hi/lo everywhere and every product is taken as hi*hi + lo*hi + hi*lo (with fp16-
+// rounded gate weights alone the reference's trained checkpoint drifts to 1.3e-3 relative after 12 carried steps).
+// The 640 KB weight image is what L2 has to deliver to every SM on every player-step.  sigmoid / tanh use ex2.approx +
+// rcp.approx (error ~1e-6, far inside the 1e-3 budget).
+#include "pp_host.h"
+#include "pp_rollout.cuh"
+#include "tc_tiles.cuh"
+
+namespace pp {
+
+#ifdef PP_TC_TIMING
+// debug build: cycles per phase, summed over the launch.  issuer: 0 player-steps 1 wait_ready 2 fill(empty) 3 full wait
+// 4 wait_dfree 5 total;  worker (thread 0): 8 wait_done 9 h staging 10 cell 11 relu_split 12 total
+__device__ unsigned long long g_rt_timing[16];
+#define RT_T0(v) long long v = clock64()
+#define RT_ADD(slot, since) atomicAdd(&g_rt_timing[slot], (unsigned long long)(clock64() - (since)))
+#else
+#define RT_T0(v)
+#define RT_ADD(slot, since)
+#endif
+
+namespace {
+
+constexpr int RT_ROWS = 128, RT_THREADS = RT_ROWS + 32, RT_ISSUER_WARP = RT_ROWS / 32;
+constexpr uint32_t RT_SLOTS = 4, RT_SLOT = PP_RNNTC_SLOT_BYTES;
+constexpr uint32_t SM_RING = 0, SM_HNEW = SM_RING + RT_SLOTS * RT_SLOT, SM_HNEW_LO = SM_HNEW + 32768,
+                   SM_X = SM_HNEW + 65536, SM_CTRL = SM_X + 4096, SM_TOTAL = SM_CTRL + 128;
+// control block: full[4] empty[4] ready done[2] dfree[2] (13 mbarriers), TMEM base
+constexpr uint32_t B_FULL = 0, B_EMPTY = 4, B_READY = 8, B_DONE = 9, B_DFREE = 11, CTRL_TMEM = 13 * 8;
+// TMEM columns
+constexpr uint32_t T_AHI = 0, T_ALO = 128, T_D0 = 256, T_D1 = 384, T_FHI = 384, T_FLO = 416;
+
+__device__ __forceinline__ void stage_info(int i, uint32_t &off, uint32_t &bytes) {
+    if (i == 0) { off = PP_RNNTC_S0; bytes = PP_RNNTC_S0_BYTES; }
+    else if (i == 1) { off = PP_RNNTC_S1; bytes = PP_RNNTC_S1_BYTES; }
+    else if (i == 2) { off = PP_RNNTC_S2; bytes = PP_RNNTC_S2_BYTES; }
+    else if (i < 35) {                            // per quarter: hi c = 0..3 (the first carries the bias tile), lo c = 0..3
+        const int q = (i - 3) >> 3, c = (i - 3) & 7;
+        off = PP_RNNTC_G + q * PP_RNNTC_GQ_BYTES + (c == 0 ? 0 : PP_RNNTC_TILE + PP_RNNTC_BIAS + (c - 1) * PP_RNNTC_TILE);
+        bytes = c == 0 ? PP_RNNTC_TILE + PP_RNNTC_BIAS : PP_RNNTC_TILE;
+    } else if (i < 39) {
+        const int c = i - 35;
+        off = PP_RNNTC_WS + (c == 0 ? 0 : PP_RNNTC_TILE + PP_RNNTC_BIAS + (c - 1) * PP_RNNTC_TILE);
+        bytes = c == 0 ? PP_RNNTC_TILE + PP_RNNTC_BIAS : PP_RNNTC_TILE;
+    } else { off = PP_RNNTC_HD; bytes = PP_RNNTC_HD_BYTES; }
+}
+
+// ------------------------------------------------------------------------------------------ issuer side
+struct Issuer {
+    uint8_t *smem;
+    uint64_t *bars;
+    uint32_t tm;                 // TMEM base
+    long long prod, cons, total; // global stage counters over the whole launch (24 per player-step)
+    uint32_t ready_par, dfree_par;
+    const uint8_t *img_a, *img_b;  // weight images of the player-step sequence: even player-steps a, odd b
+
+    __device__ __forceinline__ const uint8_t *image(long long stage) const { return ((stage / PP_RNNTC_STAGES) & 1) ? img_b : img_a; }
+
+    __device__ __forceinline__ void fill() {            // keep up to RT_SLOTS stages in flight
+        while (prod < total && prod < cons + RT_SLOTS) {
+            const uint32_t slot = (uint32_t)(prod % RT_SLOTS), round = (uint32_t)((prod / RT_SLOTS) & 1);
+            { RT_T0(t_); tc::mbar_wait(bars + B_EMPTY + slot, round ^ 1u); RT_ADD(2, t_); }   // first round passes at once
+            uint32_t off, bytes;
+            stage_info((int)(prod % PP_RNNTC_STAGES), off, bytes);
+            tc::mbar_expect_tx(bars + B_FULL + slot, bytes);
+            tc::tma_bulk_g2s(smem + SM_RING + slot * RT_SLOT, image(prod) + off, bytes, bars + B_FULL + slot);
+            ++prod;
+        }
+    }
+    __device__ __forceinline__ uint32_t acquire() {     // shared-memory address of the next stage, landed
+        fill();
+        const uint32_t slot = (uint32_t)(cons % RT_SLOTS), round = (uint32_t)((cons / RT_SLOTS) & 1);
+        { RT_T0(t_); tc::mbar_wait(bars + B_FULL + slot, round); RT_ADD(3, t_); }
+        return tc::smem_u32(smem + SM_RING + slot * RT_SLOT);
+    }
+    __device__ __forceinline__ void release() {         // the slot is free once the MMAs issued so far have read it
+        tc::umma_commit(bars + B_EMPTY + (uint32_t)(cons % RT_SLOTS));
+        ++cons;
+    }
+    __device__ __forceinline__ void wait_ready() {
+        { RT_T0(t_); tc::mbar_wait(bars + B_READY, ready_par); RT_ADD(1, t_); }
+        ready_par ^= 1u;
+        tc::tc_fence_after();
+    }
+    __device__ __forceinline__ void wait_dfree(int b) {
+        { RT_T0(t_); tc::mbar_wait(bars + B_DFREE + b, (dfree_par >> b) & 1u); RT_ADD(4, t_); }
+        dfree_par ^= 1u << b;
+        tc::tc_fence_after();
+    }
+    __device__ __forceinline__ void done(int b) { tc::umma_commit(bars + B_DONE + b); }
+};
+
+template <int N> __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tm, uint32_t b_sm, bool acc) {
+    tc::umma_f16_ts(d, a_tm, tc::smem_desc(b_sm, N * 16, SBO), tc::idesc_f16(128, N), acc);
+}
+template <int N> __device__ __forceinline__ void mma_ss(uint32_t d, uint32_t a_sm, uint32_t b_sm, bool acc) {
+    tc::umma_f16(d, tc::smem_desc(a_sm, A_LBO, SBO), tc::smem_desc(b_sm, N * 16, SBO), tc::idesc_f16(128, N), acc);
+}
+
+// one player-step of MMA work (called by the elected lane of the issuer warp)
+__device__ __forceinline__ void issue_player_step(Issuer &is) {
+    const uint32_t tm = is.tm, x = tc::smem_u32(is.smem + SM_X);
+    const uint32_t hh = tc::smem_u32(is.smem + SM_HNEW), hl = tc::smem_u32(is.smem + SM_HNEW_LO);
+    constexpr uint32_t KS128 = 2 * 128 * 16, KS64 = 2 * 64 * 16, KS16 = 2 * 16 * 16;      // B bytes per K = 16 step
+    uint32_t a;
+    // ---- L1: D0[0..63] = X * W1h' + X * W1l'
+    is.wait_ready();
+    a = is.acquire();
+    mma_ss<64>(tm + T_D0, x, a, false);
+    mma_ss<64>(tm + T_D0, x, a + 2048, true);
+    is.release();
+    is.done(0);
+    // ---- features.2: D0[0..127] = F1h*Wh + F1l*Wh + X*B + F1h*Wl
+    is.wait_ready();
+    a = is.acquire();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mma_ts<128>(tm + T_D0, tm + T_FHI + j * 8, a + j * KS128, j > 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mma_ts<128>(tm + T_D0, tm + T_FLO + j * 8, a + j * KS128, true);
+    mma_ss<128>(tm + T_D0, x, a + PP_RNNTC_TILE, true);
+    is.release();
+    a = is.acquire();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mma_ts<128>(tm + T_D0, tm + T_FHI + j * 8, a + j * KS128, true);
+    is.release();
+    is.done(0);
+    // ---- gates, four quarters of 32 units, K = 256 in four stages of 64
+    is.wait_ready();
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        if (q >= 2) is.wait_dfree(q & 1);
+        const uint32_t d = tm + ((q & 1) ? T_D1 : T_D0);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            a = is.acquire();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_ts<128>(d, tm + T_AHI + (c * 4 + j) * 8, a + j * KS128, (c | j) != 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_ts<128>(d, tm + T_ALO + (c * 4 + j) * 8, a + j * KS128, true);
+            if (c == 0) mma_ss<128>(d, x, a + PP_RNNTC_TILE, true);
+            is.release();
+        }
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {                   // A_hi * W_lo
+            a = is.acquire();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_ts<128>(d, tm + T_AHI + (c * 4 + j) * 8, a + j * KS128, true);
+            is.release();
+        }
+        is.done(q & 1);
+    }
+    // ---- shared head: D0[0..127] = Hh*Wsh + Hl*Wsh + X*B + Hh*Wsl   (A = h_new tile in shared memory, K = 128)
+    is.wait_ready();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        a = is.acquire();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_ss<128>(tm + T_D0, hh + (c * 4 + j) * 2 * A_LBO, a + j * KS128, (c | j) != 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_ss<128>(tm + T_D0, hl + (c * 4 + j) * 2 * A_LBO, a + j * KS128, true);
+        if (c == 0) mma_ss<128>(tm + T_D0, x, a + PP_RNNTC_TILE, true);
+        is.release();
+    }
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        a = is.acquire();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_ss<128>(tm + T_D0, hh + (c * 4 + j) * 2 * A_LBO, a + j * KS128, true);
+        is.release();
+    }
+    is.done(0);
+    // ---- dueling heads: D1[0..15] = Sh*Whh + Sl*Whh + Sh*Whl + X*B     (K = 128, N = 16)
+    is.wait_ready();
+    a = is.acquire();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mma_ts<16>(tm + T_D1, tm + T_AHI + j * 8, a + j * KS16, j > 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mma_ts<16>(tm + T_D1, tm + T_ALO + j * 8, a + j * KS16, true);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mma_ts<16>(tm + T_D1, tm + T_AHI + j * 8, a + 4096 + j * KS16, true);
+    mma_ss<16>(tm + T_D1, x, a + 8192, true);
+    is.release();
+    is.done(1);
+    (void)KS64;
+}
+
+// ------------------------------------------------------------------------------------------ compute side
+struct Worker {
+    uint8_t *smem;
+    uint64_t *bars;
+    uint32_t tm;             // TMEM base + this warp's lane offset
+    uint32_t done_par;       // bit b = parity of done[b]
+    int row;
+
+    __device__ __forceinline__ void publish(bool smem_rows) {       // my operand rows are written
+        if (smem_rows) tc::fence_proxy_async();
+        tc::tc_fence_before();
+        tc::mbar_arrive(bars + B_READY);
+    }
+    __device__ __forceinline__ void wait_done(int b) {
+        { RT_T0(t_); tc::mbar_wait(bars + B_DONE + b, (done_par >> b) & 1u); if (row == 0) RT_ADD(8, t_); }
+        done_par ^= 1u << b;
+        tc::tc_fence_after();
+    }
+    __device__ __forceinline__ void drained(int b) {
+        tc::tc_fence_before();
+        tc::mbar_arrive(bars + B_DFREE + b);
+    }
+};
+
+// NCOLS accumulator columns at src -> ReLU -> hi/lo fp16 pairs -> TMEM at dst_hi / dst_lo (NCOLS / 2 columns each)
+template <int NCOLS> __device__ __forceinline__ void relu_split_to_tmem(uint32_t src, uint32_t dst_hi, uint32_t dst_lo) {
+#pragma unroll
+    for (int blk = 0; blk < NCOLS / 32; ++blk) {
+        uint32_t r0[16], r1[16], hi[16], lo[16];
+        tc::tmem_ld16(src + blk * 32, r0);
+        tc::tmem_ld16(src + blk * 32 + 16, r1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = __uint_as_float(r0[2 * j]), b = __uint_as_float(r0[2 * j + 1]);
+            hi[j] = tc::pack_f16x2_rz_relu(a, b);
+            lo[j] = tc::pack_f16x2<true>(a - h2f(hi[j], 0), b - h2f(hi[j], 1));
+            const float c = __uint_as_float(r1[2 * j]), d = __uint_as_float(r1[2 * j + 1]);
+            hi[8 + j] = tc::pack_f16x2_rz_relu(c, d);
+            lo[8 + j] = tc::pack_f16x2<true>(c - h2f(hi[8 + j], 0), d - h2f(hi[8 + j], 1));
+        }
+        tc::tmem_st16(dst_hi + blk * 16, hi);
+        tc::tmem_st16(dst_lo + blk * 16, lo);
+    }
+    tc::tmem_st_wait();
+}
+
+__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float fast_tanh(float v) { return 2.0f * fast_sigmoid(2.0f * v) - 1.0f; }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+
+// One player-step for this thread's env.  obs: its observation; fresh: episode start ((h, c) = 0 before the step);
+// gh / gc: the player's (h, c) in global memory, ENV-major [n][128] fp32 (a thread streams its own 512-byte rows
+// with 16-byte accesses); live: the env exists and is not frozen.
+__device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs)[7], bool fresh, bool live, float *__restrict__ gh,
+                                                    float *__restrict__ gc, int64_t env, float (&q)[3]) {
+    const uint32_t tm = w.tm;
+    const int row = w.row;
+    const bool carry = live && !fresh;
+    const float4 *h4 = reinterpret_cast<const float4 *>(gh + (size_t)env * 128);
+    float4 *hs4 = reinterpret_cast<float4 *>(gh + (size_t)env * 128), *cs4 = reinterpret_cast<float4 *>(gc + (size_t)env * 128);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- X row; h_prev -> A (columns 64..127 of the hi / lo halves)
+    write_x_row(w.smem + SM_X, row, obs);
+    RT_T0(th_);
+#pragma unroll 1
+    for (int blk = 0; blk < 4; ++blk) {                 // 32 units per block: 8 x 16-byte loads in flight, 16 packed pairs
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = carry ? h4[blk * 8 + j] : zero4;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            hi[2 * j] = tc::pack_f16x2<false>(v[j].x, v[j].y);
+            lo[2 * j] = tc::pack_f16x2<false>(v[j].x - h2f(hi[2 * j], 0), v[j].y - h2f(hi[2 * j], 1));
+            hi[2 * j + 1] = tc::pack_f16x2<false>(v[j].z, v[j].w);
+            lo[2 * j + 1] = tc::pack_f16x2<false>(v[j].z - h2f(hi[2 * j + 1], 0), v[j].w - h2f(hi[2 * j + 1], 1));
+        }
+        tc::tmem_st16(tm + T_AHI + 64 + blk * 16, hi);
+        tc::tmem_st16(tm + T_ALO + 64 + blk * 16, lo);
+    }
+    tc::tmem_st_wait();
+    if (row == 0) RT_ADD(9, th_);
+    w.publish(true);
+    // ---- F1
+    w.wait_done(0);
+    relu_split_to_tmem<64>(tm + T_D0, tm + T_FHI, tm + T_FLO);
+    w.publish(false);
+    // ---- f2 -> A columns 0..63
+    w.wait_done(0);
+    relu_split_to_tmem<128>(tm + T_D0, tm + T_AHI, tm + T_ALO);
+    w.publish(false);
+    // ---- LSTM cell, quarter by quarter (i, f, g, o at columns 0, 32, 64, 96 of the buffer; 8 units at a time).
+    // The quarter's 32 c_prev values are requested BEFORE waiting for its gates, so the loads ride under the MMAs.
+    uint8_t *hn = w.smem + SM_HNEW;
+#pragma unroll 1
+    for (int qt = 0; qt < 4; ++qt) {
+        float4 cp[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cp[j] = carry ? cs4[qt * 8 + j] : zero4;
+        w.wait_done(qt & 1);
+        const uint32_t d = tm + ((qt & 1) ? T_D1 : T_D0);
+        RT_T0(tc_);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            uint32_t gi[8], gf[8], gg[8], go[8];
+            tmem_ld8(d + 8 * b, gi);
+            tmem_ld8(d + 32 + 8 * b, gf);
+            tmem_ld8(d + 64 + 8 * b, gg);
+            tmem_ld8(d + 96 + 8 * b, go);
+            tc::tmem_ld_wait();
+            const float cprev[8] = {cp[2 * b].x, cp[2 * b].y, cp[2 * b].z, cp[2 * b].w,
+                                    cp[2 * b + 1].x, cp[2 * b + 1].y, cp[2 * b + 1].z, cp[2 * b + 1].w};
+            float hv[8], cv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float ig = fast_sigmoid(__uint_as_float(gi[e])), fg = fast_sigmoid(__uint_as_float(gf[e]));
+                const float g2 = fast_tanh(__uint_as_float(gg[e])), og = fast_sigmoid(__uint_as_float(go[e]));
+                cv[e] = __fadd_rn(__fmul_rn(fg, cprev[e]), __fmul_rn(ig, g2));
+                hv[e] = __fmul_rn(og, fast_tanh(cv[e]));
+            }
+            if (live) {
+                const int v4 = qt * 8 + 2 * b;
+                cs4[v4] = make_float4(cv[0], cv[1], cv[2], cv[3]); cs4[v4 + 1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+                hs4[v4] = make_float4(hv[0], hv[1], hv[2], hv[3]); hs4[v4 + 1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            }
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ph[j] = tc::pack_f16x2<false>(hv[2 * j], hv[2 * j + 1]);
+                pl[j] = tc::pack_f16x2<false>(hv[2 * j] - h2f(ph[j], 0), hv[2 * j + 1] - h2f(ph[j], 1));
+            }
+            const int chunk = qt * 4 + b;
+            *reinterpret_cast<uint4 *>(hn + chunk * A_LBO + row * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4 *>(hn + 32768 + chunk * A_LBO + row * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
+        if (row == 0) RT_ADD(10, tc_);
+        if (qt < 2) w.drained(qt & 1);
+    }
+    w.publish(true);
+    // ---- shared head -> s into A columns 0..63
+    w.wait_done(0);
+    relu_split_to_tmem<128>(tm + T_D0, tm + T_AHI, tm + T_ALO);
+    w.publish(false);
+    // ---- Q
+    w.wait_done(1);
+    dueling_q(tm + T_D1, q);
+}
+
+__device__ __forceinline__ uint32_t rnn_tc_prologue(uint8_t *smem, int warp_id) {
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_CTRL);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_CTRL + CTRL_TMEM);
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < RT_SLOTS; ++s) { tc::mbar_init(bars + B_FULL + s, 1); tc::mbar_init(bars + B_EMPTY + s, 1); }
+        tc::mbar_init(bars + B_READY, RT_ROWS);
+        tc::mbar_init(bars + B_DONE, 1); tc::mbar_init(bars + B_DONE + 1, 1);
+        tc::mbar_init(bars + B_DFREE, RT_ROWS); tc::mbar_init(bars + B_DFREE + 1, RT_ROWS);
+        tc::fence_mbar_init();
+    }
+    if (warp_id == RT_ISSUER_WARP) tc::tmem_alloc<512>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    return __shfl_sync(0xffffffffu, *tmem_slot, 0);
+}
+
+}  // namespace
+
+// standalone: obs[n][7] -> Q -> action for one recurrent player, (h, c) carried in global memory
+__global__ void __launch_bounds__(RT_THREADS, 1)
+qnetrnn_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol, const uint8_t *__restrict__ reset_mask,
+                      uint64_t seed, uint32_t step_index, int64_t env_id_base, uint32_t stream_id,
+                      uint8_t *__restrict__ actions, float *__restrict__ q_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const uint32_t tm = rnn_tc_prologue(smem, warp_id);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_CTRL);
+    const int64_t tiles = (n + RT_ROWS - 1) / RT_ROWS;
+    int64_t my_tiles = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) ++my_tiles;
+    if (warp_id == RT_ISSUER_WARP) {
+        if (tc::elect_one()) {
+            Issuer is{smem, bars, tm, 0, 0, my_tiles * PP_RNNTC_STAGES, 0u, 0u,
+                      reinterpret_cast<const uint8_t *>(pol.weights), reinterpret_cast<const uint8_t *>(pol.weights)};
+            for (int64_t t = 0; t < my_tiles; ++t) {
+                RT_T0(t_);
+                issue_player_step(is);
+                RT_ADD(5, t_);
+            }
+        }
+        __syncwarp();
+    } else {
+        Worker w{smem, bars, tm + ((uint32_t)(warp_id * 32) << 16), 0u, (int)threadIdx.x};
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int64_t i = t * RT_ROWS + threadIdx.x;
+            const bool live = i < n;
+            const int64_t ic = live ? i : 0;
+            float o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) o[k] = obs[i * 7 + k];
+            }
+            const bool fresh = live && reset_mask && reset_mask[i];
+            float q[3];
+            RT_T0(t_);
+            compute_player_step(w, o, fresh, live, pol.h, pol.c, ic, q);
+            if (threadIdx.x == 0) RT_ADD(12, t_);
+            if (live) {
+                int a = argmax3(q);
+                a = explore(a, pol.eps_threshold, seed, (uint32_t)(env_id_base + i), step_index, stream_id);
+                actions[i] = (uint8_t)a;
+                if (q_out) { q_out[i * 3 + 0] = q[0]; q_out[i * 3 + 1] = q[1]; q_out[i * 3 + 2] = q[2]; }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp_id == RT_ISSUER_WARP) tc::tmem_dealloc<512>(tm);
+}
+
+#ifdef PP_TC_TIMING
+extern "C" int pp_debug_rt_timing(unsigned long long *host16, int reset) {
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(host16, g_rt_timing, sizeof(g_rt_timing));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_rt_timing, z, sizeof z); }
+    return (int)e;
+}
+#endif
+
+static int rt_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sms = 148;
+    }
+    return sms;
+}
+
+int qnetrnn_act_tc_launch(int64_t n, const float *obs, const PPPolicy &pol, const uint8_t *reset_mask, uint64_t seed,
+                          int64_t step_index, int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out,
+                          cudaStream_t stream) {
+    cudaError_t err = cudaFuncSetAttribute(qnetrnn_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (err != cudaSuccess) return (int)err;
+    const int64_t tiles = (n + RT_ROWS - 1) / RT_ROWS;
+    const unsigned blocks = (unsigned)(tiles < rt_sm_count() ? tiles : rt_sm_count());
+    qnetrnn_act_tc_kernel<<<blocks, RT_THREADS, SM_TOTAL, stream>>>(n, obs, pol, reset_mask, seed, (uint32_t)step_index,
+                                                                    env_id_base, (uint32_t)stream_id, actions, q_out);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pp

@@ -28,7 +28,7 @@
 
 #include "pp_host.h"
 #include "pp_rollout.cuh"
-#include "tc_ptx.cuh"
+#include "tc_tiles.cuh"
 
 namespace pp {
 
@@ -36,8 +36,6 @@ namespace {
 
 constexpr int G_ROWS = 128;                    // envs per group
 constexpr int CTA_GROUPS = 4;
-constexpr uint32_t A_LBO = G_ROWS * 16;        // A tiles are [K/8][128][16 B]
-constexpr uint32_t SBO = 128;
 
 // per-player weight tiles (bytes); every B tile is [K/8][N][16 B]; *H = fp16(w), *L = fp16(w - fp16(w))
 constexpr uint32_t W1_BYTES = 2 * 64 * 16, W2_BYTES = 8 * 64 * 16, B2_BYTES = 2 * 64 * 16, W3_BYTES = 8 * 16 * 16,
@@ -60,11 +58,6 @@ template <int GROUPS> struct SmemMap {
 struct PlayerTiles {     // shared-memory (generic) pointers of one player's operands
     uint8_t *w, *x;
 };
-
-__device__ __forceinline__ float h2f(uint32_t packed, int hi) {
-    const __half2 v = *reinterpret_cast<const __half2 *>(&packed);
-    return hi ? __high2float(v) : __low2float(v);
-}
 
 // fp32 blob (staging) -> fp16 hi / lo B-operand tiles of one player.  All threads of the CTA.
 __device__ void build_weight_tiles(uint8_t *wt, const float *blob, int tid, int nthreads) {
@@ -98,20 +91,6 @@ __device__ void build_weight_tiles(uint8_t *wt, const float *blob, int tid, int 
         const float bv = nn < 4 ? blob[PP_QNET_BH + nn] : 0.0f;
         H(B3_OFF)[idx] = (k & 7) == 7 ? (k == 7 ? hi(bv) : lo(bv)) : zero;
     }
-}
-
-// this thread's row of X = [obs_hi(7) 1 | obs_lo(7) 1]
-__device__ __forceinline__ void write_x_row(uint8_t *x, int row, const float (&o)[7]) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float a = o[2 * j], b = j < 3 ? o[2 * j + 1] : 1.0f;
-        hi[j] = tc::pack_f16x2<false>(a, b);
-        const float ra = a - h2f(hi[j], 0), rb = j < 3 ? b - h2f(hi[j], 1) : 1.0f;
-        lo[j] = tc::pack_f16x2<false>(ra, rb);
-    }
-    *reinterpret_cast<uint4 *>(x + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4 *>(x + A_LBO + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // Accumulator row (64 fp32 columns at `src`) -> ReLU -> hi/lo fp16 -> this thread's row of the next A operand in
@@ -160,17 +139,6 @@ __device__ __forceinline__ void issue_dense(uint32_t d, uint32_t a_tm, const Pla
     }
     tc::umma_f16(d, tc::smem_desc(tc::smem_u32(p.x), A_LBO, SBO), tc::smem_desc(tc::smem_u32(p.w + b_off), B_LBO, SBO),
                  tc::idesc_f16(128, N), true);
-}
-
-__device__ __forceinline__ void dueling_q(uint32_t taddr, float (&q)[3]) {      // V + (A - mean(A))  models/qnet.py:75
-    uint32_t r[4];
-    tc::tmem_ld4(taddr, r);
-    tc::tmem_ld_wait();
-    const float v = __uint_as_float(r[0]), a0 = __uint_as_float(r[1]), a1 = __uint_as_float(r[2]), a2 = __uint_as_float(r[3]);
-    const float mean = __fdiv_rn(__fadd_rn(__fadd_rn(a0, a1), a2), 3.0f);
-    q[0] = __fadd_rn(v, __fsub_rn(a0, mean));
-    q[1] = __fadd_rn(v, __fsub_rn(a1, mean));
-    q[2] = __fadd_rn(v, __fsub_rn(a2, mean));
 }
 
 // Shared prologue: barriers, TMEM, weights.  Returns the TMEM base of the CTA.

@@ -167,6 +167,68 @@ def pack_qnetrnn(model_or_state_dict, noisy: bool = False) -> torch.Tensor:
     return blob
 
 
+def _tile_b(w_kn: torch.Tensor, part: str) -> torch.Tensor:
+    """[K, N] fp32 (k-major) -> fp16 B-operand tile [K/8][N][8], hi = fp16(w) or lo = fp16(w - hi)."""
+    hi = w_kn.to(torch.float16)
+    t = hi if part == "hi" else (w_kn - hi.to(torch.float32)).to(torch.float16)
+    k, n = t.shape
+    return t.reshape(k // 8, 8, n).permute(0, 2, 1).contiguous().reshape(-1)
+
+
+def _bias_tile(b: torch.Tensor, n: int) -> torch.Tensor:
+    """[2][n][8] tile: bias hi in row k = 7, lo in row k = 15 (they meet the ones columns of the obs tile)."""
+    t = torch.zeros(16, n, dtype=torch.float32, device=b.device)
+    hi = b.to(torch.float16).to(torch.float32)
+    t[7, :b.numel()] = hi
+    t[15, :b.numel()] = b - hi
+    return _tile_b(t, "hi")          # the two rows are already exact fp16 values
+
+
+def pack_qnetrnn_tc(model_or_state_dict, noisy: bool = False) -> torch.Tensor:
+    """QNetRNN -> the fp16 stage image PP_RNNTC_* of the tensor-core path (a uint8 tensor of PP_RNNTC_BLOB_BYTES)."""
+    sd = _sd(model_or_state_dict)
+    wf1, bf1 = sd["features_extractor.0.weight"], sd["features_extractor.0.bias"]          # [64, 7]
+    wf2, bf2 = sd["features_extractor.2.weight"], sd["features_extractor.2.bias"]          # [128, 64]
+    wih, whh = sd["lstm.weight_ih_l0"], sd["lstm.weight_hh_l0"]                            # [512, 128] each
+    if tuple(wf1.shape) != (64, 7) or tuple(wf2.shape) != (128, 64) or tuple(wih.shape) != (512, 128) or \
+            tuple(whh.shape) != (512, 128) or "lstm.weight_ih_l1" in sd:
+        raise ValueError("the device QNetRNN is the reference default 7-64-128 / 1-layer LSTM 128 / head 128")
+    ws, bs = _noisy(sd, "fc_shared_head.0", noisy)
+    wv, bv = _noisy(sd, "fc_V", noisy)
+    wa, ba = _noisy(sd, "fc_A", noisy)
+    dev = wf1.device
+    z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+    # S0: layer 1 with K = 16: rows 0..6 W1^T, 7 b_hi | rows 8..14 W1^T (meets obs_lo), 15 b_lo ; lo tile: W1_lo in rows 0..6
+    w1 = z(16, 64)
+    w1[0:7] = wf1.t(); w1[8:15] = wf1.t()
+    bh = bf1.to(torch.float16).to(torch.float32)
+    w1h = _tile_b(w1, "hi").clone().reshape(2, 64, 8)
+    w1h[0, :, 7] = bh.to(torch.float16); w1h[1, :, 7] = (bf1 - bh).to(torch.float16)
+    w1l_src = z(16, 64); w1l_src[0:7] = wf1.t()
+    w1l = _tile_b(w1l_src, "lo")
+    parts = [w1h.reshape(-1), w1l]
+    parts += [_tile_b(wf2.t().contiguous(), "hi"), _bias_tile(bf2, 128), _tile_b(wf2.t().contiguous(), "lo")]          # S1, S2
+    wcat = torch.cat([wih, whh], 1).t().contiguous()                                        # [256 k, 512 = gate*128 + unit]
+    bg = sd["lstm.bias_ih_l0"] + sd["lstm.bias_hh_l0"]
+    for q in range(4):
+        cols = torch.cat([torch.arange(g * 128 + 32 * q, g * 128 + 32 * q + 32) for g in range(4)]).to(dev)
+        wq = wcat[:, cols]                                                                   # [256, 128], column = gate*32 + unit%32
+        for c in range(4):
+            parts.append(_tile_b(wq[64 * c:64 * c + 64].contiguous(), "hi"))
+            if c == 0:
+                parts.append(_bias_tile(bg[cols], 128))
+        for c in range(4):
+            parts.append(_tile_b(wq[64 * c:64 * c + 64].contiguous(), "lo"))
+    wst = ws.t().contiguous()                                                                # [128 k, 128]
+    parts += [_tile_b(wst[:64].contiguous(), "hi"), _bias_tile(bs, 128), _tile_b(wst[64:].contiguous(), "hi"),
+              _tile_b(wst[:64].contiguous(), "lo"), _tile_b(wst[64:].contiguous(), "lo")]
+    wh = z(128, 16); wh[:, 0:1] = wv.t(); wh[:, 1:4] = wa.t()
+    parts += [_tile_b(wh, "hi"), _tile_b(wh, "lo"), _bias_tile(torch.cat([bv, ba]), 16)]
+    blob = torch.cat(parts).contiguous().view(torch.uint8)
+    assert blob.numel() == _lib.RNNTC_BLOB_BYTES, blob.numel()
+    return blob
+
+
 def eps_threshold(eps: float) -> int:
     """explore iff (uint64) philox.x < floor(eps * 2^32)"""
     return int(min(max(float(eps), 0.0), 1.0) * 4294967296.0)
@@ -184,8 +246,11 @@ class Policy:
         if kind == _lib.POLICY_QNETRNN:
             if num_envs is None:
                 raise ValueError("QNetRNN players carry per-env (h, c): pass num_envs")
-            self.h = torch.zeros(128, num_envs, dtype=torch.float32, device=self.device)
-            self.c = torch.zeros(128, num_envs, dtype=torch.float32, device=self.device)
+            # fp32 path: unit-major [128, n] (coalesced along the env index); tensor-core path: env-major [n, 128]
+            # (a thread streams its own 512-byte row).  `hidden()` returns either as [n, 128].
+            shape = (num_envs, 128) if self.precision == _lib.PREC_F16 else (128, num_envs)
+            self.h = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+            self.c = torch.zeros(*shape, dtype=torch.float32, device=self.device)
 
     @classmethod
     def qnet(cls, model_or_state_dict, noisy=False, **kw):
@@ -193,6 +258,10 @@ class Policy:
 
     @classmethod
     def qnetrnn(cls, model_or_state_dict, num_envs, noisy=False, **kw):
+        if kw.get("precision", "f32") == "f16":          # tensor-core path: the fp16 stage image instead of the fp32 blob
+            pol = cls(_lib.POLICY_QNETRNN, None, num_envs=num_envs, **kw)
+            pol.weights = pack_qnetrnn_tc(model_or_state_dict, noisy).to(pol.device).contiguous()
+            return pol
         return cls(_lib.POLICY_QNETRNN, pack_qnetrnn(model_or_state_dict, noisy), num_envs=num_envs, **kw)
 
     @classmethod
@@ -203,6 +272,12 @@ class Policy:
     @classmethod
     def random(cls, **kw):
         return cls(_lib.POLICY_RANDOM, **kw)
+
+    def hidden(self):
+        """(h, c) as [num_envs, 128] views, whatever the storage layout of the precision path."""
+        if self.h is None:
+            return None, None
+        return (self.h, self.c) if self.precision == _lib.PREC_F16 else (self.h.t(), self.c.t())
 
     def set_weights(self, blob):
         self.weights.copy_(blob.to(self.weights.device, torch.float32), non_blocking=True)

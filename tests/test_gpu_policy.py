@@ -154,3 +154,53 @@ def test_qnet_act_tensor_core_ragged_sizes_and_large_inputs(qg, n):
     assert np.isfinite(q).all()
     lo = 7 if n >= 1000 else 0
     assert np.abs(q[lo:] - wq[lo:]).max() <= 1e-3 * max(1.0, np.abs(wq[lo:]).max())
+
+
+@pytest.mark.parametrize("fname,name", [("qnetrnn_golden.npz", "seed0"), ("qnetrnn_ckpt_golden.npz", "rnn_agent_4_B")])
+@pytest.mark.parametrize("noisy", [False, True])
+def test_qnetrnn_act_tensor_core_path_carried_state(fname, name, noisy):
+    """PP_PREC_F16 QNetRNN (every layer on tcgen05, fp16 hi/lo activations, fp32 accumulation): 12 carried steps for
+    48 envs, Q within 1e-3 of the torch reference, (h, c) within 1e-3, reset mask honoured."""
+    g = dict(np.load(os.path.join(gu.GOLDEN, fname)))
+    sd = gu.golden_sd(g, name)
+    seq = g["seq"]
+    B, T = seq.shape[:2]
+    pol = pp.Policy.qnetrnn(sd, num_envs=B, noisy=noisy, precision="f16")
+    mode = "train" if noisy else "eval"
+    pol.h.fill_(7.0); pol.c.fill_(-3.0)
+    worst = 0.0
+    for t in range(T):
+        mask = torch.ones(B, dtype=torch.uint8, device="cuda") if t == 0 else None
+        act, q = pp.qnetrnn_act(torch.from_numpy(seq[:, t].copy()).cuda(), pol, reset_mask=mask, want_q=True)
+        ref = g[f"{name}/q_{mode}"][t]
+        err = np.abs(gu.np_of(q) - ref).max()
+        worst = max(worst, err / max(1.0, np.abs(ref).max()))
+        assert err <= 1e-3 * max(1.0, np.abs(ref).max()), (t, err)
+        srt = np.sort(ref, axis=1)
+        clear = (srt[:, 2] - srt[:, 1]) > 2e-3
+        assert np.array_equal(gu.np_of(act)[clear], ref.argmax(1)[clear]), t
+    print(f"tensor-core QNetRNN {name} noisy={noisy}: worst relative |dQ| = {worst:.3e}")
+    h_dev, c_dev = (gu.np_of(t) for t in pol.hidden())
+    assert np.abs(h_dev - g[f"{name}/h_{mode}"]).max() < 1e-3
+    assert np.abs(c_dev - g[f"{name}/c_{mode}"]).max() < 1e-3 * max(1.0, np.abs(g[f"{name}/c_{mode}"]).max())
+
+
+def test_qnetrnn_act_tensor_core_many_tiles_and_partial_reset():
+    torch.manual_seed(4)
+    net = pp.QNetRNN()
+    n = 128 * 150 + 37                                          # more tiles than SMs, ragged last tile
+    pol = pp.Policy.qnetrnn(net, num_envs=n, precision="f16")
+    w = po.qnetrnn_weights_from_state_dict(net.state_dict())
+    rs = np.random.RandomState(0)
+    h = np.zeros((n, 128), np.float32); c = np.zeros((n, 128), np.float32)
+    for t in range(3):
+        obs = rs.uniform(-1, 1, size=(n, 7)).astype(np.float32)
+        mask = (rs.rand(n) < 0.3).astype(np.uint8) if t else np.ones(n, np.uint8)
+        h[mask.astype(bool)] = 0; c[mask.astype(bool)] = 0
+        _, q = pp.qnetrnn_act(torch.from_numpy(obs).cuda(), pol, reset_mask=torch.from_numpy(mask).cuda(), want_q=True)
+        sub = slice(0, None, 97)                                 # the serial oracle on a sample of the envs
+        hs, cs = h[sub].copy(), c[sub].copy()
+        wq, _ = po.qnetrnn_forward(w, obs[sub], hs, cs)
+        assert np.abs(gu.np_of(q)[sub] - wq).max() <= 1e-3, t
+        h[:], c[:] = (gu.np_of(t) for t in pol.hidden())         # carry the device state forward for the next step
+        assert np.abs(h[sub] - hs).max() < 1e-3 and np.abs(c[sub] - cs).max() < 1e-3
