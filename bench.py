@@ -284,10 +284,9 @@ def main():
     if args.workload == "rnn":
         torch.manual_seed(0); net_a = pp.QNetRNN()
         torch.manual_seed(1); net_b = pp.QNetRNN()
-        pa = pp.Policy.qnetrnn(net_a, num_envs=n, device=dev)
-        pb = pp.Policy.qnetrnn(net_b, num_envs=n, device=dev)
+        pa = pp.Policy.qnetrnn(net_a, num_envs=n, device=dev, precision=args.precision)
+        pb = pp.Policy.qnetrnn(net_b, num_envs=n, device=dev, precision=args.precision)
         args.no_e2e = args.no_k1 = True
-        args.precision = "f32"
     else:
         torch.manual_seed(0); net_a = pp.QNet()
         torch.manual_seed(1); net_b = pp.QNet()
@@ -337,7 +336,7 @@ def main():
     }
     flop = 626432 if args.workload == "rnn" else FLOP_PER_ENV_STEP
     tf = value / world * flop / 1e12
-    line["roofline"] = {"bound": "tensor", "kernel": "selfplay_rnn_kernel" if args.workload == "rnn" else ("selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel"), "achieved": tf, "peak": peaks["bf16_sustained"],
+    line["roofline"] = {"bound": "tensor", "kernel": ("selfplay_rnn_tc_kernel" if args.precision == "f16" else "selfplay_rnn_kernel") if args.workload == "rnn" else ("selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel"), "achieved": tf, "peak": peaks["bf16_sustained"],
                         "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"], "traffic": None,
                         "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                         "note": f"algorithmic {flop} FLOP per env-step (both players' net) x env-steps per launch / "

@@ -157,7 +157,11 @@ int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, 
     // QNetRNN x QNet would need both weight sets resident: not built)
     if (rnn && (policy_a->kind == PP_POLICY_QNET || policy_b->kind == PP_POLICY_QNET)) return fail(PP_E_MODE, "pp_selfplay_rollout");
     if (!prec_ok(policy_a) || !prec_ok(policy_b)) return fail(PP_E_MODE, "pp_selfplay_rollout");
-    if (rnn && (policy_a->precision != PP_PREC_F32 || policy_b->precision != PP_PREC_F32)) return fail(PP_E_MODE, "pp_selfplay_rollout");
+    const bool rnn_tc = rnn && ((policy_a->kind == PP_POLICY_QNETRNN && policy_a->precision == PP_PREC_F16) ||
+                                (policy_b->kind == PP_POLICY_QNETRNN && policy_b->precision == PP_PREC_F16));
+    if (rnn_tc && ((policy_a->kind == PP_POLICY_QNETRNN && policy_a->precision != PP_PREC_F16) ||
+                   (policy_b->kind == PP_POLICY_QNETRNN && policy_b->precision != PP_PREC_F16)))
+        return fail(PP_E_MODE, "pp_selfplay_rollout");                 // both recurrent players on the same path
     const bool tc = uses_tc(policy_a) || uses_tc(policy_b);
     if (tc && ((policy_a->kind == PP_POLICY_QNET && !uses_tc(policy_a)) || (policy_b->kind == PP_POLICY_QNET && !uses_tc(policy_b))))
         return fail(PP_E_MODE, "pp_selfplay_rollout");                 // both QNet players on the same path
@@ -165,6 +169,9 @@ int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, 
     if (ring && ring->capacity < n) return fail(PP_E_SIZE, "pp_selfplay_rollout");     // one lock-step step must fit
     if (serve->kind == PP_SERVE_QUEUE && (int64_t)quota != serve->queue_total) return fail(PP_E_SIZE, "pp_selfplay_rollout");
     if (n == 0 || k == 0) return 0;
+    if (rnn_tc)
+        return ok_or(pp::selfplay_rnn_tc_launch(mode, n, k, *params, *state, *policy_a, *policy_b, seed, step_base, *serve,
+                                                quota, env_id_base, *out, ring, (cudaStream_t)stream), "pp_selfplay_rollout");
     if (rnn)
         return ok_or(pp::selfplay_rnn_launch(mode, n, k, *params, *state, *policy_a, *policy_b, seed, step_base, *serve,
                                              quota, env_id_base, *out, ring, (cudaStream_t)stream), "pp_selfplay_rollout");

@@ -38,12 +38,15 @@ __device__ unsigned long long g_rt_timing[16];
 
 namespace {
 
-constexpr int RT_ROWS = 128, RT_THREADS = RT_ROWS + 32, RT_ISSUER_WARP = RT_ROWS / 32;
+// RT_HALVES threads share one env row (same TMEM lane, different columns): more warps per scheduler for the epilogues
+constexpr int RT_ROWS = 128, RT_HALVES = 2, RT_WORKERS = RT_ROWS * RT_HALVES, RT_THREADS = RT_WORKERS + 32,
+              RT_ISSUER_WARP = RT_WORKERS / 32;
 constexpr uint32_t RT_SLOTS = 4, RT_SLOT = PP_RNNTC_SLOT_BYTES;
 constexpr uint32_t SM_RING = 0, SM_HNEW = SM_RING + RT_SLOTS * RT_SLOT, SM_HNEW_LO = SM_HNEW + 32768,
-                   SM_X = SM_HNEW + 65536, SM_CTRL = SM_X + 4096, SM_TOTAL = SM_CTRL + 128;
-// control block: full[4] empty[4] ready done[2] dfree[2] (13 mbarriers), TMEM base
-constexpr uint32_t B_FULL = 0, B_EMPTY = 4, B_READY = 8, B_DONE = 9, B_DFREE = 11, CTRL_TMEM = 13 * 8;
+                   SM_X = SM_HNEW + 65536, SM_CTRL = SM_X + 4096, SM_FLAGS = SM_CTRL + 128, SM_TOTAL = SM_FLAGS + 2 * RT_ROWS;
+// control block: full[4] empty[4] ready done[2] dfree[2] step (14 mbarriers), TMEM base, stop flag; then per-row flags
+constexpr uint32_t B_FULL = 0, B_EMPTY = 4, B_READY = 8, B_DONE = 9, B_DFREE = 11, B_STEP = 13, CTRL_TMEM = 14 * 8,
+                   CTRL_STOP = 14 * 8 + 4;
 // TMEM columns
 constexpr uint32_t T_AHI = 0, T_ALO = 128, T_D0 = 256, T_D1 = 384, T_FHI = 384, T_FLO = 416;
 
@@ -66,55 +69,71 @@ __device__ __forceinline__ void stage_info(int i, uint32_t &off, uint32_t &bytes
 struct Issuer {
     uint8_t *smem;
     uint64_t *bars;
-    uint32_t tm;                 // TMEM base
-    long long prod, cons, total; // global stage counters over the whole launch (24 per player-step)
+    uint32_t tm;                   // TMEM base
+    // ring bookkeeping in small ints (no 64-bit division on the issue path): next stage to request / to consume
+    int p_stage, p_slot, p_round, p_player;      // stage within its player-step, ring slot, slot round parity, image select
+    int c_slot, c_round, inflight;
+    long long to_request;          // stages not yet requested over the whole launch
     uint32_t ready_par, dfree_par;
     const uint8_t *img_a, *img_b;  // weight images of the player-step sequence: even player-steps a, odd b
+    bool leader;                   // ALL lanes of the issuer warp run the program (uniform control flow keeps counters and
+                                   // descriptors in uniform registers); only the leader lane executes the TMA / MMA / commit
 
-    __device__ __forceinline__ const uint8_t *image(long long stage) const { return ((stage / PP_RNNTC_STAGES) & 1) ? img_b : img_a; }
-
-    __device__ __forceinline__ void fill() {            // keep up to RT_SLOTS stages in flight
-        while (prod < total && prod < cons + RT_SLOTS) {
-            const uint32_t slot = (uint32_t)(prod % RT_SLOTS), round = (uint32_t)((prod / RT_SLOTS) & 1);
-            { RT_T0(t_); tc::mbar_wait(bars + B_EMPTY + slot, round ^ 1u); RT_ADD(2, t_); }   // first round passes at once
+    // Keep up to RT_SLOTS stages in flight.  A slot is free once the MMAs that read it have COMPLETED; blocking on that
+    // here would drain the tensor pipe between stages, so slots that are still being read are skipped for now (the
+    // next acquire() tries again) — unless the stage about to be consumed has not even been requested yet.
+    __device__ __forceinline__ void fill() {
+        while (to_request > 0 && inflight < (int)RT_SLOTS) {
+            if (inflight > 0) {
+                if (!tc::mbar_test_wait(bars + B_EMPTY + p_slot, (uint32_t)(p_round ^ 1))) break;
+            } else { RT_T0(t_); tc::mbar_wait(bars + B_EMPTY + p_slot, (uint32_t)(p_round ^ 1)); if (leader) RT_ADD(2, t_); }   // first round passes at once
             uint32_t off, bytes;
-            stage_info((int)(prod % PP_RNNTC_STAGES), off, bytes);
-            tc::mbar_expect_tx(bars + B_FULL + slot, bytes);
-            tc::tma_bulk_g2s(smem + SM_RING + slot * RT_SLOT, image(prod) + off, bytes, bars + B_FULL + slot);
-            ++prod;
+            stage_info(p_stage, off, bytes);
+            if (leader) {
+                tc::mbar_expect_tx(bars + B_FULL + p_slot, bytes);
+                tc::tma_bulk_g2s(smem + SM_RING + p_slot * RT_SLOT, (p_player ? img_b : img_a) + off, bytes, bars + B_FULL + p_slot);
+            }
+            if (++p_stage == PP_RNNTC_STAGES) { p_stage = 0; p_player ^= 1; }
+            if (++p_slot == (int)RT_SLOTS) { p_slot = 0; p_round ^= 1; }
+            ++inflight; --to_request;
         }
     }
     __device__ __forceinline__ uint32_t acquire() {     // shared-memory address of the next stage, landed
         fill();
-        const uint32_t slot = (uint32_t)(cons % RT_SLOTS), round = (uint32_t)((cons / RT_SLOTS) & 1);
-        { RT_T0(t_); tc::mbar_wait(bars + B_FULL + slot, round); RT_ADD(3, t_); }
-        return tc::smem_u32(smem + SM_RING + slot * RT_SLOT);
+        { RT_T0(t_); tc::mbar_wait(bars + B_FULL + c_slot, (uint32_t)c_round); if (leader) RT_ADD(3, t_); }
+        return tc::smem_u32(smem + SM_RING + c_slot * RT_SLOT);
     }
     __device__ __forceinline__ void release() {         // the slot is free once the MMAs issued so far have read it
-        tc::umma_commit(bars + B_EMPTY + (uint32_t)(cons % RT_SLOTS));
-        ++cons;
+        if (leader) tc::umma_commit(bars + B_EMPTY + c_slot);
+        if (++c_slot == (int)RT_SLOTS) { c_slot = 0; c_round ^= 1; }
+        --inflight;
     }
     __device__ __forceinline__ void wait_ready() {
-        { RT_T0(t_); tc::mbar_wait(bars + B_READY, ready_par); RT_ADD(1, t_); }
+        { RT_T0(t_); tc::mbar_wait(bars + B_READY, ready_par); if (leader) RT_ADD(1, t_); }
         ready_par ^= 1u;
         tc::tc_fence_after();
     }
     __device__ __forceinline__ void wait_dfree(int b) {
-        { RT_T0(t_); tc::mbar_wait(bars + B_DFREE + b, (dfree_par >> b) & 1u); RT_ADD(4, t_); }
+        { RT_T0(t_); tc::mbar_wait(bars + B_DFREE + b, (dfree_par >> b) & 1u); if (leader) RT_ADD(4, t_); }
         dfree_par ^= 1u << b;
         tc::tc_fence_after();
     }
-    __device__ __forceinline__ void done(int b) { tc::umma_commit(bars + B_DONE + b); }
+    __device__ __forceinline__ void done(int b) { if (leader) tc::umma_commit(bars + B_DONE + b); }
 };
 
-template <int N> __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tm, uint32_t b_sm, bool acc) {
-    tc::umma_f16_ts(d, a_tm, tc::smem_desc(b_sm, N * 16, SBO), tc::idesc_f16(128, N), acc);
+#define RT_LEADER is.leader
+template <int N> __device__ __forceinline__ void mma_ts_(bool leader, uint32_t d, uint32_t a_tm, uint32_t b_sm, bool acc) {
+    const uint64_t bd = tc::smem_desc(b_sm, N * 16, SBO);
+    if (leader) tc::umma_f16_ts(d, a_tm, bd, tc::idesc_f16(128, N), acc);
 }
-template <int N> __device__ __forceinline__ void mma_ss(uint32_t d, uint32_t a_sm, uint32_t b_sm, bool acc) {
-    tc::umma_f16(d, tc::smem_desc(a_sm, A_LBO, SBO), tc::smem_desc(b_sm, N * 16, SBO), tc::idesc_f16(128, N), acc);
+template <int N> __device__ __forceinline__ void mma_ss_(bool leader, uint32_t d, uint32_t a_sm, uint32_t b_sm, bool acc) {
+    const uint64_t ad = tc::smem_desc(a_sm, A_LBO, SBO), bd = tc::smem_desc(b_sm, N * 16, SBO);
+    if (leader) tc::umma_f16(d, ad, bd, tc::idesc_f16(128, N), acc);
 }
+#define mma_ts mma_ts_
+#define mma_ss mma_ss_
 
-// one player-step of MMA work (called by the elected lane of the issuer warp)
+// one player-step of MMA work (called by ALL lanes of the issuer warp; see Issuer::leader)
 __device__ __forceinline__ void issue_player_step(Issuer &is) {
     const uint32_t tm = is.tm, x = tc::smem_u32(is.smem + SM_X);
     const uint32_t hh = tc::smem_u32(is.smem + SM_HNEW), hl = tc::smem_u32(is.smem + SM_HNEW_LO);
@@ -123,22 +142,22 @@ __device__ __forceinline__ void issue_player_step(Issuer &is) {
     // ---- L1: D0[0..63] = X * W1h' + X * W1l'
     is.wait_ready();
     a = is.acquire();
-    mma_ss<64>(tm + T_D0, x, a, false);
-    mma_ss<64>(tm + T_D0, x, a + 2048, true);
+    mma_ss<64>(RT_LEADER, tm + T_D0, x, a, false);
+    mma_ss<64>(RT_LEADER, tm + T_D0, x, a + 2048, true);
     is.release();
     is.done(0);
     // ---- features.2: D0[0..127] = F1h*Wh + F1l*Wh + X*B + F1h*Wl
     is.wait_ready();
     a = is.acquire();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) mma_ts<128>(tm + T_D0, tm + T_FHI + j * 8, a + j * KS128, j > 0);
+    for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, tm + T_D0, tm + T_FHI + j * 8, a + j * KS128, j > 0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) mma_ts<128>(tm + T_D0, tm + T_FLO + j * 8, a + j * KS128, true);
-    mma_ss<128>(tm + T_D0, x, a + PP_RNNTC_TILE, true);
+    for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, tm + T_D0, tm + T_FLO + j * 8, a + j * KS128, true);
+    mma_ss<128>(RT_LEADER, tm + T_D0, x, a + PP_RNNTC_TILE, true);
     is.release();
     a = is.acquire();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) mma_ts<128>(tm + T_D0, tm + T_FHI + j * 8, a + j * KS128, true);
+    for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, tm + T_D0, tm + T_FHI + j * 8, a + j * KS128, true);
     is.release();
     is.done(0);
     // ---- gates, four quarters of 32 units, K = 256 in four stages of 64
@@ -151,17 +170,17 @@ __device__ __forceinline__ void issue_player_step(Issuer &is) {
         for (int c = 0; c < 4; ++c) {
             a = is.acquire();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma_ts<128>(d, tm + T_AHI + (c * 4 + j) * 8, a + j * KS128, (c | j) != 0);
+            for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, d, tm + T_AHI + (c * 4 + j) * 8, a + j * KS128, (c | j) != 0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma_ts<128>(d, tm + T_ALO + (c * 4 + j) * 8, a + j * KS128, true);
-            if (c == 0) mma_ss<128>(d, x, a + PP_RNNTC_TILE, true);
+            for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, d, tm + T_ALO + (c * 4 + j) * 8, a + j * KS128, true);
+            if (c == 0) mma_ss<128>(RT_LEADER, d, x, a + PP_RNNTC_TILE, true);
             is.release();
         }
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {                   // A_hi * W_lo
             a = is.acquire();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma_ts<128>(d, tm + T_AHI + (c * 4 + j) * 8, a + j * KS128, true);
+            for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, d, tm + T_AHI + (c * 4 + j) * 8, a + j * KS128, true);
             is.release();
         }
         is.done(q & 1);
@@ -172,17 +191,17 @@ __device__ __forceinline__ void issue_player_step(Issuer &is) {
     for (int c = 0; c < 2; ++c) {
         a = is.acquire();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mma_ss<128>(tm + T_D0, hh + (c * 4 + j) * 2 * A_LBO, a + j * KS128, (c | j) != 0);
+        for (int j = 0; j < 4; ++j) mma_ss<128>(RT_LEADER, tm + T_D0, hh + (c * 4 + j) * 2 * A_LBO, a + j * KS128, (c | j) != 0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mma_ss<128>(tm + T_D0, hl + (c * 4 + j) * 2 * A_LBO, a + j * KS128, true);
-        if (c == 0) mma_ss<128>(tm + T_D0, x, a + PP_RNNTC_TILE, true);
+        for (int j = 0; j < 4; ++j) mma_ss<128>(RT_LEADER, tm + T_D0, hl + (c * 4 + j) * 2 * A_LBO, a + j * KS128, true);
+        if (c == 0) mma_ss<128>(RT_LEADER, tm + T_D0, x, a + PP_RNNTC_TILE, true);
         is.release();
     }
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         a = is.acquire();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mma_ss<128>(tm + T_D0, hh + (c * 4 + j) * 2 * A_LBO, a + j * KS128, true);
+        for (int j = 0; j < 4; ++j) mma_ss<128>(RT_LEADER, tm + T_D0, hh + (c * 4 + j) * 2 * A_LBO, a + j * KS128, true);
         is.release();
     }
     is.done(0);
@@ -190,16 +209,19 @@ __device__ __forceinline__ void issue_player_step(Issuer &is) {
     is.wait_ready();
     a = is.acquire();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mma_ts<16>(tm + T_D1, tm + T_AHI + j * 8, a + j * KS16, j > 0);
+    for (int j = 0; j < 8; ++j) mma_ts<16>(RT_LEADER, tm + T_D1, tm + T_AHI + j * 8, a + j * KS16, j > 0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mma_ts<16>(tm + T_D1, tm + T_ALO + j * 8, a + j * KS16, true);
+    for (int j = 0; j < 8; ++j) mma_ts<16>(RT_LEADER, tm + T_D1, tm + T_ALO + j * 8, a + j * KS16, true);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mma_ts<16>(tm + T_D1, tm + T_AHI + j * 8, a + 4096 + j * KS16, true);
-    mma_ss<16>(tm + T_D1, x, a + 8192, true);
+    for (int j = 0; j < 8; ++j) mma_ts<16>(RT_LEADER, tm + T_D1, tm + T_AHI + j * 8, a + 4096 + j * KS16, true);
+    mma_ss<16>(RT_LEADER, tm + T_D1, x, a + 8192, true);
     is.release();
     is.done(1);
     (void)KS64;
 }
+
+#undef mma_ts
+#undef mma_ss
 
 // ------------------------------------------------------------------------------------------ compute side
 struct Worker {
@@ -207,7 +229,7 @@ struct Worker {
     uint64_t *bars;
     uint32_t tm;             // TMEM base + this warp's lane offset
     uint32_t done_par;       // bit b = parity of done[b]
-    int row;
+    int row, half;           // env row (= TMEM lane) and which share of its columns this thread works on
 
     __device__ __forceinline__ void publish(bool smem_rows) {       // my operand rows are written
         if (smem_rows) tc::fence_proxy_async();
@@ -215,7 +237,7 @@ struct Worker {
         tc::mbar_arrive(bars + B_READY);
     }
     __device__ __forceinline__ void wait_done(int b) {
-        { RT_T0(t_); tc::mbar_wait(bars + B_DONE + b, (done_par >> b) & 1u); if (row == 0) RT_ADD(8, t_); }
+        { RT_T0(t_); tc::mbar_wait(bars + B_DONE + b, (done_par >> b) & 1u); if (row == 0 && half == 0) RT_ADD(8, t_); }
         done_par ^= 1u << b;
         tc::tc_fence_after();
     }
@@ -226,9 +248,9 @@ struct Worker {
 };
 
 // NCOLS accumulator columns at src -> ReLU -> hi/lo fp16 pairs -> TMEM at dst_hi / dst_lo (NCOLS / 2 columns each)
-template <int NCOLS> __device__ __forceinline__ void relu_split_to_tmem(uint32_t src, uint32_t dst_hi, uint32_t dst_lo) {
-#pragma unroll
-    for (int blk = 0; blk < NCOLS / 32; ++blk) {
+template <int NCOLS> __device__ __forceinline__ void relu_split_to_tmem(uint32_t src, uint32_t dst_hi, uint32_t dst_lo, int half) {
+#pragma unroll 1
+    for (int blk = half; blk < NCOLS / 32; blk += RT_HALVES) {
         uint32_t r0[16], r1[16], hi[16], lo[16];
         tc::tmem_ld16(src + blk * 32, r0);
         tc::tmem_ld16(src + blk * 32 + 16, r1);
@@ -248,8 +270,19 @@ template <int NCOLS> __device__ __forceinline__ void relu_split_to_tmem(uint32_t
     tc::tmem_st_wait();
 }
 
-__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float fast_tanh(float v) { return 2.0f * fast_sigmoid(2.0f * v) - 1.0f; }
+// LSTM cell of one unit from its four gate pre-activations (models/qnet_rnn.py:130, torch gate order i, f, g, o):
+// c' = s(f) c + s(i) tanh(g), h' = s(o) tanh(c').  The four logistic terms share ONE reciprocal (7 MUFU ops per unit
+// instead of 10): with a_x = 1 + e^-x,  s(x) = prod(other a) / prod(all a).  Arguments are clamped to +-20
+// (s(+-20) is 0 / 1 to 2e-9), which keeps the product of four terms far from overflow.
+__device__ __forceinline__ void lstm_cell(float gi, float gf, float gg, float go, float c_prev, float &c_new, float &h_new) {
+    auto e = [](float v) { return __expf(fminf(fmaxf(-v, -20.0f), 20.0f)); };
+    const float ai = 1.0f + e(gi), af = 1.0f + e(gf), ao = 1.0f + e(go), ag = 1.0f + e(2.0f * gg);
+    const float p1 = ai * af, p2 = ao * ag, r = __fdividef(1.0f, p1 * p2);
+    const float si = r * af * p2, sf = r * ai * p2, so = r * ag * p1, tg = 2.0f * (r * ao * p1) - 1.0f;
+    c_new = __fadd_rn(__fmul_rn(sf, c_prev), __fmul_rn(si, tg));
+    const float tc_ = 2.0f * __fdividef(1.0f, 1.0f + e(2.0f * c_new)) - 1.0f;
+    h_new = __fmul_rn(so, tc_);
+}
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -268,11 +301,24 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
     const float4 *h4 = reinterpret_cast<const float4 *>(gh + (size_t)env * 128);
     float4 *hs4 = reinterpret_cast<float4 *>(gh + (size_t)env * 128), *cs4 = reinterpret_cast<float4 *>(gc + (size_t)env * 128);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int half = w.half;
+    // ---- this thread's share of c_prev (sub-block `half` of every quarter: 32 values) is requested FIRST: the loads
+    // come from L2 / HBM and have the whole feature phase to land
+    constexpr int SUBS = 4 / RT_HALVES;
+    float4 cp[4][2 * SUBS];
+#pragma unroll
+    for (int qt = 0; qt < 4; ++qt)
+#pragma unroll
+        for (int sb = 0; sb < SUBS; ++sb) {
+            const int b = half * SUBS + sb;
+            cp[qt][2 * sb] = carry ? cs4[qt * 8 + 2 * b] : zero4;
+            cp[qt][2 * sb + 1] = carry ? cs4[qt * 8 + 2 * b + 1] : zero4;
+        }
     // ---- X row; h_prev -> A (columns 64..127 of the hi / lo halves)
-    write_x_row(w.smem + SM_X, row, obs);
+    if (half == 0) write_x_row(w.smem + SM_X, row, obs);
     RT_T0(th_);
 #pragma unroll 1
-    for (int blk = 0; blk < 4; ++blk) {                 // 32 units per block: 8 x 16-byte loads in flight, 16 packed pairs
+    for (int blk = half; blk < 4; blk += RT_HALVES) {   // 32 units per block: 8 x 16-byte loads in flight, 16 packed pairs
         float4 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = carry ? h4[blk * 8 + j] : zero4;
@@ -288,45 +334,40 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
         tc::tmem_st16(tm + T_ALO + 64 + blk * 16, lo);
     }
     tc::tmem_st_wait();
-    if (row == 0) RT_ADD(9, th_);
+    if (row == 0 && half == 0) RT_ADD(9, th_);
     w.publish(true);
     // ---- F1
     w.wait_done(0);
-    relu_split_to_tmem<64>(tm + T_D0, tm + T_FHI, tm + T_FLO);
+    relu_split_to_tmem<64>(tm + T_D0, tm + T_FHI, tm + T_FLO, half);
     w.publish(false);
     // ---- f2 -> A columns 0..63
     w.wait_done(0);
-    relu_split_to_tmem<128>(tm + T_D0, tm + T_AHI, tm + T_ALO);
+    relu_split_to_tmem<128>(tm + T_D0, tm + T_AHI, tm + T_ALO, half);
     w.publish(false);
-    // ---- LSTM cell, quarter by quarter (i, f, g, o at columns 0, 32, 64, 96 of the buffer; 8 units at a time).
-    // The quarter's 32 c_prev values are requested BEFORE waiting for its gates, so the loads ride under the MMAs.
+    // ---- LSTM cell, quarter by quarter (i, f, g, o at columns 0, 32, 64, 96 of the buffer; 8 units per sub-block, the
+    // sub-blocks of a quarter are shared out over the row's threads).
     uint8_t *hn = w.smem + SM_HNEW;
-#pragma unroll 1
-    for (int qt = 0; qt < 4; ++qt) {
-        float4 cp[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cp[j] = carry ? cs4[qt * 8 + j] : zero4;
+    for (int qt = 0; qt < 4; ++qt) {
         w.wait_done(qt & 1);
         const uint32_t d = tm + ((qt & 1) ? T_D1 : T_D0);
         RT_T0(tc_);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int sb = 0; sb < SUBS; ++sb) {
+            const int b = half * SUBS + sb;
             uint32_t gi[8], gf[8], gg[8], go[8];
             tmem_ld8(d + 8 * b, gi);
             tmem_ld8(d + 32 + 8 * b, gf);
             tmem_ld8(d + 64 + 8 * b, gg);
             tmem_ld8(d + 96 + 8 * b, go);
             tc::tmem_ld_wait();
-            const float cprev[8] = {cp[2 * b].x, cp[2 * b].y, cp[2 * b].z, cp[2 * b].w,
-                                    cp[2 * b + 1].x, cp[2 * b + 1].y, cp[2 * b + 1].z, cp[2 * b + 1].w};
+            const float cprev[8] = {cp[qt][2 * sb].x, cp[qt][2 * sb].y, cp[qt][2 * sb].z, cp[qt][2 * sb].w,
+                                    cp[qt][2 * sb + 1].x, cp[qt][2 * sb + 1].y, cp[qt][2 * sb + 1].z, cp[qt][2 * sb + 1].w};
             float hv[8], cv[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float ig = fast_sigmoid(__uint_as_float(gi[e])), fg = fast_sigmoid(__uint_as_float(gf[e]));
-                const float g2 = fast_tanh(__uint_as_float(gg[e])), og = fast_sigmoid(__uint_as_float(go[e]));
-                cv[e] = __fadd_rn(__fmul_rn(fg, cprev[e]), __fmul_rn(ig, g2));
-                hv[e] = __fmul_rn(og, fast_tanh(cv[e]));
-            }
+            for (int e = 0; e < 8; ++e)
+                lstm_cell(__uint_as_float(gi[e]), __uint_as_float(gf[e]), __uint_as_float(gg[e]), __uint_as_float(go[e]),
+                          cprev[e], cv[e], hv[e]);
             if (live) {
                 const int v4 = qt * 8 + 2 * b;
                 cs4[v4] = make_float4(cv[0], cv[1], cv[2], cv[3]); cs4[v4 + 1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
@@ -342,13 +383,13 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
             *reinterpret_cast<uint4 *>(hn + chunk * A_LBO + row * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
             *reinterpret_cast<uint4 *>(hn + 32768 + chunk * A_LBO + row * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
-        if (row == 0) RT_ADD(10, tc_);
+        if (row == 0 && half == 0) RT_ADD(10, tc_);
         if (qt < 2) w.drained(qt & 1);
     }
     w.publish(true);
     // ---- shared head -> s into A columns 0..63
     w.wait_done(0);
-    relu_split_to_tmem<128>(tm + T_D0, tm + T_AHI, tm + T_ALO);
+    relu_split_to_tmem<128>(tm + T_D0, tm + T_AHI, tm + T_ALO, half);
     w.publish(false);
     // ---- Q
     w.wait_done(1);
@@ -360,9 +401,10 @@ __device__ __forceinline__ uint32_t rnn_tc_prologue(uint8_t *smem, int warp_id) 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_CTRL + CTRL_TMEM);
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < RT_SLOTS; ++s) { tc::mbar_init(bars + B_FULL + s, 1); tc::mbar_init(bars + B_EMPTY + s, 1); }
-        tc::mbar_init(bars + B_READY, RT_ROWS);
+        tc::mbar_init(bars + B_READY, RT_WORKERS);
         tc::mbar_init(bars + B_DONE, 1); tc::mbar_init(bars + B_DONE + 1, 1);
-        tc::mbar_init(bars + B_DFREE, RT_ROWS); tc::mbar_init(bars + B_DFREE + 1, RT_ROWS);
+        tc::mbar_init(bars + B_DFREE, RT_WORKERS); tc::mbar_init(bars + B_DFREE + 1, RT_WORKERS);
+        tc::mbar_init(bars + B_STEP, RT_WORKERS);
         tc::fence_mbar_init();
     }
     if (warp_id == RT_ISSUER_WARP) tc::tmem_alloc<512>(tmem_slot);
@@ -387,20 +429,19 @@ qnetrnn_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy p
     int64_t my_tiles = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) ++my_tiles;
     if (warp_id == RT_ISSUER_WARP) {
-        if (tc::elect_one()) {
-            Issuer is{smem, bars, tm, 0, 0, my_tiles * PP_RNNTC_STAGES, 0u, 0u,
-                      reinterpret_cast<const uint8_t *>(pol.weights), reinterpret_cast<const uint8_t *>(pol.weights)};
-            for (int64_t t = 0; t < my_tiles; ++t) {
-                RT_T0(t_);
-                issue_player_step(is);
-                RT_ADD(5, t_);
-            }
+        Issuer is{smem, bars, tm, 0, 0, 0, 0, 0, 0, 0, my_tiles * PP_RNNTC_STAGES, 0u, 0u,
+                  reinterpret_cast<const uint8_t *>(pol.weights), reinterpret_cast<const uint8_t *>(pol.weights), tc::elect_one()};
+        for (int64_t t = 0; t < my_tiles; ++t) {
+            RT_T0(t_);
+            issue_player_step(is);
+            if (is.leader) RT_ADD(5, t_);
         }
         __syncwarp();
     } else {
-        Worker w{smem, bars, tm + ((uint32_t)(warp_id * 32) << 16), 0u, (int)threadIdx.x};
+        const int row = threadIdx.x & (RT_ROWS - 1), half = threadIdx.x / RT_ROWS;
+        Worker w{smem, bars, tm + ((uint32_t)((warp_id & 3) * 32) << 16), 0u, row, half};
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int64_t i = t * RT_ROWS + threadIdx.x;
+            const int64_t i = t * RT_ROWS + row;
             const bool live = i < n;
             const int64_t ic = live ? i : 0;
             float o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -413,13 +454,123 @@ qnetrnn_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy p
             RT_T0(t_);
             compute_player_step(w, o, fresh, live, pol.h, pol.c, ic, q);
             if (threadIdx.x == 0) RT_ADD(12, t_);
-            if (live) {
+            if (live && half == 0) {
                 int a = argmax3(q);
                 a = explore(a, pol.eps_threshold, seed, (uint32_t)(env_id_base + i), step_index, stream_id);
                 actions[i] = (uint8_t)a;
                 if (q_out) { q_out[i * 3 + 0] = q[0]; q_out[i * 3 + 1] = q[1]; q_out[i * 3 + 2] = q[2]; }
             }
         }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp_id == RT_ISSUER_WARP) tc::tmem_dealloc<512>(tm);
+}
+
+// ------------------------------------------------------------------------------------------ fused self-play rollout
+// k lock-step iterations of {obs, QNetRNN (or follower / random) A, B, env step, replay row, auto-reset} for tiles of
+// up to 128 envs per CTA (one CTA per SM): the recurrent-player form of tests/arena.py:294-304 and of the rollout loop
+// of scripts/train_rnn_iterative.py:732-780 on the tensor cores.  Env state lives in the registers of the row's first
+// thread; (h, c) are env-major in global memory and zeroed at every episode start.  The launch is cut into chunks of at
+// most 4 warps of envs, balanced to within one warp, a whole number of rounds over the SMs.
+template <typename R>
+__global__ void __launch_bounds__(RT_THREADS, 1)
+selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_steps, const PPPolicy pol_a,
+                       const PPPolicy pol_b, uint64_t seed, int64_t step_base, const PPServeSource src, int32_t quota,
+                       int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const uint32_t tm = rnn_tc_prologue(smem, warp_id);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_CTRL);
+    volatile uint32_t *stop_flag = reinterpret_cast<volatile uint32_t *>(smem + SM_CTRL + CTRL_STOP);
+    volatile uint8_t *row_fresh = smem + SM_FLAGS, *row_live = smem + SM_FLAGS + RT_ROWS;
+    const bool ra = pol_a.kind == PP_POLICY_QNETRNN, rb = pol_b.kind == PP_POLICY_QNETRNN;
+    const int64_t total_warps = (n + 31) / 32;
+
+    if (warp_id == RT_ISSUER_WARP) {
+        const uint8_t *ia = reinterpret_cast<const uint8_t *>(ra ? pol_a.weights : pol_b.weights);
+        const uint8_t *ib = reinterpret_cast<const uint8_t *>(rb ? pol_b.weights : pol_a.weights);
+        Issuer is{smem, bars, tm, 0, 0, 0, 0, 0, 0, 0, 0, 0u, 0u, ia, ib, tc::elect_one()};
+        uint32_t step_par = 0;
+#pragma unroll 1
+        for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+            if ((chunk + 1) * total_warps / n_chunks == chunk * total_warps / n_chunks) continue;     // empty chunk
+#pragma unroll 1
+            for (int64_t t = 0; t < k_steps; ++t) {
+                tc::mbar_wait(bars + B_STEP, step_par);
+                step_par ^= 1u;
+                if (*stop_flag) break;                                         // the tile is frozen by the quota
+                is.to_request += (long long)PP_RNNTC_STAGES * ((ra ? 1 : 0) + (rb ? 1 : 0));
+                if (ra) issue_player_step(is);
+                if (rb) issue_player_step(is);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int tid = threadIdx.x, row = tid & (RT_ROWS - 1), half = tid / RT_ROWS, lane = tid & 31, gw = row >> 5;
+        Worker w{smem, bars, tm + ((uint32_t)((warp_id & 3) * 32) << 16), 0u, row, half};
+        const EnvConsts<R> c(params);
+        const StatePtrs<R> s(st);
+        const int64_t ring_t0 = ring_first_step(ring, n, k_steps);
+        Tally total;
+#pragma unroll 1
+        for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+            const int64_t w_lo = chunk * total_warps / n_chunks, w_hi = (chunk + 1) * total_warps / n_chunks;
+            const int my_warps = (int)(w_hi - w_lo);                           // <= 4
+            if (my_warps == 0) continue;
+            const int64_t i = (w_lo + gw) * 32 + lane;
+            const bool valid = gw < my_warps && i < n;
+            const int64_t ic = valid ? i : 0;
+            Lane<R> L;
+            L.e = load_env<R>(s, ic);
+            L.ep_idx = s.ep_idx[ic]; L.ep_len = s.ep_len[ic];
+            const uint32_t gid = (uint32_t)(env_id_base + ic);
+            bool fresh = L.ep_len == 0;                                        // episode start: (h, c) = 0 before the first step
+#pragma unroll 1
+            for (int64_t t = 0; t < k_steps; ++t) {
+                const bool active = valid && !(quota > 0 && L.ep_idx >= quota);
+                const uint32_t step = (uint32_t)(step_base + t);
+                if (half == 0) { row_fresh[row] = fresh ? 1 : 0; row_live[row] = active ? 1 : 0; }
+                const bool any = tc::bar_red_or(1, RT_WORKERS, active && half == 0);   // also publishes the row flags
+                if (tid == 0) *stop_flag = any ? 0u : 1u;
+                tc::mbar_arrive(bars + B_STEP);                                // release: the issuer reads the flag after this
+                if (!any) break;
+                const bool r_fresh = row_fresh[row] != 0, r_live = row_live[row] != 0;
+                float oa[7], ob[7];
+                observe<R>(L.e, oa, ob);
+                int act_a = 1, act_b = 1;
+#pragma unroll 1
+                for (int p = 0; p < 2; ++p) {
+                    const PPPolicy &pol = p ? pol_b : pol_a;
+                    const uint32_t stream_id = p ? STREAM_ACT_B : STREAM_ACT_A;
+                    int a = 1;
+                    if (pol.kind == PP_POLICY_QNETRNN) {
+                        float q[3];
+                        compute_player_step(w, p ? ob : oa, r_fresh, r_live, pol.h, pol.c, ic, q);
+                        a = explore(argmax3(q), pol.eps_threshold, seed, gid, step, stream_id);   // (h, c) advance even when exploring
+                    } else if (pol.kind == PP_POLICY_RANDOM) {
+                        a = random_action(seed, gid, step, stream_id);
+                    } else {
+                        a = explore(follower_action(p ? ob : oa, pol.follower_tol), pol.eps_threshold, seed, gid, step, stream_id);
+                    }
+                    if (p) act_b = a; else act_a = a;
+                }
+                if (half == 0 && gw < my_warps) {                              // whole warps: the bookkeeping collectives are safe
+                    const int ep_before = L.ep_idx;
+                    step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
+                                     ring.head != nullptr && t >= ring_t0, src,
+                                     [&](int ep, R &vx, R &vy, R &sp) { next_serve<R>(params, src, n, i, env_id_base, ep, vx, vy, sp); });
+                    fresh = active ? (L.ep_idx != ep_before) : fresh;
+                }
+            }
+            if (valid && half == 0) {
+                store_env<R>(s, i, L.e);
+                s.ep_idx[i] = L.ep_idx;
+                s.ep_len[i] = L.ep_len;
+            }
+            if (half == 0) total.add(L.tally);
+        }
+        if (out.counters) total.flush(out.counters);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -454,6 +605,26 @@ int qnetrnn_act_tc_launch(int64_t n, const float *obs, const PPPolicy &pol, cons
     const unsigned blocks = (unsigned)(tiles < rt_sm_count() ? tiles : rt_sm_count());
     qnetrnn_act_tc_kernel<<<blocks, RT_THREADS, SM_TOTAL, stream>>>(n, obs, pol, reset_mask, seed, (uint32_t)step_index,
                                                                     env_id_base, (uint32_t)stream_id, actions, q_out);
+    return (int)cudaGetLastError();
+}
+
+int selfplay_rnn_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
+                           const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
+                           int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream) {
+    PPReplayRing r{};
+    if (ring) r = *ring;
+    const int64_t total_warps = (n + 31) / 32, slots = rt_sm_count();
+    int64_t n_chunks = (total_warps + 3) / 4;                                   // tiles of <= 4 warps ...
+    if (n_chunks > slots) n_chunks = ((total_warps + slots * 4 - 1) / (slots * 4)) * slots;   // ... a whole number of rounds
+    const unsigned blocks = (unsigned)(n_chunks < slots ? n_chunks : slots);
+    cudaError_t err;
+    if (mode == PP_MODE_F64) {
+        if ((err = cudaFuncSetAttribute(selfplay_rnn_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL)) != cudaSuccess) return (int)err;
+        selfplay_rnn_tc_kernel<double><<<blocks, RT_THREADS, SM_TOTAL, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota, env_id_base, out, r, n_chunks);
+    } else {
+        if ((err = cudaFuncSetAttribute(selfplay_rnn_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL)) != cudaSuccess) return (int)err;
+        selfplay_rnn_tc_kernel<float><<<blocks, RT_THREADS, SM_TOTAL, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota, env_id_base, out, r, n_chunks);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -36,6 +36,9 @@ int selfplay_rnn_launch(int mode, int64_t n, int64_t k, const PPParams &p, const
 int qnetrnn_act_tc_launch(int64_t n, const float *obs, const PPPolicy &pol, const uint8_t *reset_mask, uint64_t seed,
                           int64_t step_index, int64_t env_id_base, int32_t stream_id, uint8_t *actions, float *q_out,
                           cudaStream_t stream);
+int selfplay_rnn_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
+                           const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
+                           int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream);
 int replay_scatter_launch(int64_t n, const PPReplayRing &ring, const float *obs, const uint8_t *act, const float *rew,
                           const float *next_obs, const uint8_t *done, const uint8_t *valid, cudaStream_t stream);
 

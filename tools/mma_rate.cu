@@ -1,0 +1,61 @@
+// tools/mma_rate.cu — micro-benchmark: cycles per tcgen05.mma (M = 128, kind::f16, K = 16) when ONE thread issues a long
+// accumulate chain, for N in {16, 64, 128, 256}, A from shared memory (SS) or tensor memory (TS).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I pingpong_selfplay_ai_b200/csrc -o /tmp/mma_rate tools/mma_rate.cu
+#include <cstdio>
+#include "tc_ptx.cuh"
+using namespace pp;
+
+template <int N, bool TS, bool COMMIT_EACH>
+__global__ void rate_kernel(long long *out, int iters) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar, bar2;
+    __shared__ uint32_t slot;
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+    if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::mbar_init(&bar2, 1); tc::fence_mbar_init(); }
+    if (threadIdx.x < 32) tc::tmem_alloc<512>(&slot);
+    tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+    tc::fence_proxy_async();
+    const uint32_t tm = slot;
+    if (threadIdx.x == 0) {
+        const uint32_t a_sm = tc::smem_u32(smem), b_sm = tc::smem_u32(smem + 16384);
+        const uint64_t ad = tc::smem_desc(a_sm, 128 * 16, 128), bd = tc::smem_desc(b_sm, N * 16, 128);
+        const uint32_t idesc = tc::idesc_f16(128, N);
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (TS) tc::umma_f16_ts(tm + 256, tm + j * 8, bd, idesc, true);
+                else tc::umma_f16(tm + 256, ad, bd, idesc, true);
+            }
+            if (COMMIT_EACH) tc::umma_commit(&bar2);      // like releasing a ring slot after every 8 MMAs
+        }
+        long long t1 = clock64();
+        tc::umma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc::tc_fence_before(); __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc<512>(tm);
+}
+
+template <int N, bool TS, bool CE = false> void run(const char *name) {
+    long long *d, h[2];
+    cudaMalloc(&d, 16);
+    cudaFuncSetAttribute(rate_kernel<N, TS, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    const int iters = 200;
+    rate_kernel<N, TS, CE><<<1, 128, 64 * 1024>>>(d, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("%-10s issue %.1f cyc/MMA, complete %.1f cyc/MMA (%s)\n", name, (double)h[0] / (iters * 8), (double)h[1] / (iters * 8), cudaGetErrorString(e));
+    cudaFree(d);
+}
+
+int main() {
+    run<16, false>("N16 SS"); run<16, true>("N16 TS");
+    run<64, false>("N64 SS"); run<64, true>("N64 TS");
+    run<128, false>("N128 SS"); run<128, true>("N128 TS");
+    run<256, false>("N256 SS"); run<256, true>("N256 TS");
+    run<128, true, true>("N128 TS + commit/8"); run<64, true, true>("N64 TS + commit/8");
+    return 0;
+}
