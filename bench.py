@@ -38,6 +38,10 @@ METRIC = "self-play env-steps/sec (env + both players' QNet action)"
 UNIT = "env-steps/s"
 FLOP_PER_ENV_STEP = 19200            # 2 players x 2 x 4800 MAC
 BYTES_PER_STEP_F64 = 203             # K1 single step, all outputs materialised, fp64 mode
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/):
+NCU_TRAFFIC = {"selfplay_tc_kernel": 5.083904e6 + 27.136e3,      # r01_selfplay_r01b_metrics.txt, 65536 envs x 64 steps
+               "selfplay_kernel": 5.094144e6 + 15.36e3}           # r01_selfplay_r01_metrics.txt, same shape
+NCU_K1_TRAFFIC_PER_ENV = (293.624576e6 + 499.684352e6) / 4194304   # r01_k1_r01b_metrics.txt: 189.1 B per env-step at 4 M envs
 
 
 def load_peaks():
@@ -336,8 +340,13 @@ def main():
     }
     flop = 626432 if args.workload == "rnn" else FLOP_PER_ENV_STEP
     tf = value / world * flop / 1e12
+    kname = ("selfplay_rnn_tc_kernel" if args.precision == "f16" else "selfplay_rnn_kernel") if args.workload == "rnn" else \
+        ("selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel")
+    traffic = NCU_TRAFFIC.get(kname) if (args.envs, args.lockstep, args.mode) == (65536, 64, "f64") else None
     line["roofline"] = {"bound": "tensor", "kernel": ("selfplay_rnn_tc_kernel" if args.precision == "f16" else "selfplay_rnn_kernel") if args.workload == "rnn" else ("selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel"), "achieved": tf, "peak": peaks["bf16_sustained"],
-                        "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"], "traffic": None,
+                        "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"], "traffic": traffic,
+                        "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture of this shape (profiles/); "
+                                        "state lives in registers, so it is ~0.1 % of what a materialising step would move",
                         "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                         "note": f"algorithmic {flop} FLOP per env-step (both players' net) x env-steps per launch / "
                                 "CUDA-event launch time, per GPU"}
@@ -427,7 +436,9 @@ def measure_k1(pp, dev, peaks, mode, n):
     per = BYTES_PER_STEP_F64 if mode == "f64" else 147
     gbs = n * per / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "step_kernel", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
-            "frac": gbs / peaks["hbm"], "traffic": None, "envs": n, "ms_per_launch": ms,
+            "frac": gbs / peaks["hbm"], "traffic": NCU_K1_TRAFFIC_PER_ENV * n if mode == "f64" else None,
+            "traffic_note": "ncu dram bytes per env-step measured at 4 M envs (189.1 B vs 203 B algorithmic) x envs",
+            "envs": n, "ms_per_launch": ms,
             "env_steps_per_s": n / (ms * 1e-3), "peak_source": f"{peaks['src']} copy bandwidth",
             "note": f"{per} algorithmic B per env-step (SURVEY.md 8d), working set {n * per / 2**20:.0f} MiB >> L2"}
 
