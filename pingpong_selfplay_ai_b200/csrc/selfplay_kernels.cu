@@ -60,7 +60,7 @@ __device__ __forceinline__ int select_action(const PPPolicy &pol, const float *s
 }
 
 template <typename R>
-__global__ void __launch_bounds__(SP_THREADS)
+__global__ void __launch_bounds__(SP_THREADS, 4)
 selfplay_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_steps, const PPPolicy pol_a,
                 const PPPolicy pol_b, uint64_t seed, int64_t step_base, const PPServeSource src, int32_t quota,
                 int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring) {

@@ -37,6 +37,7 @@ class PrioritizedSampler:
         self.ring, self.alpha = ring, float(alpha)
         self.prios = torch.zeros(ring.capacity, dtype=torch.float32, device=ring.obs.device)
         self.seen = 0                                   # ring.head at the last note_new_rows()
+        self.size_t = torch.zeros((), dtype=torch.float32, device=ring.obs.device)     # len(self) on the device
 
     def __len__(self):
         return min(self.seen, self.ring.capacity)
@@ -65,20 +66,22 @@ class PrioritizedSampler:
                 self.prios[lo:] = max_p
                 self.prios[:hi] = max_p
         self.seen = head
+        self.size_t.fill_(float(len(self)))
         return new
 
-    def sample(self, batch_size: int, beta: float, generator=None):
-        """-> (idx int64[bs], importance weights f32[bs]) — :64-73."""
-        size = len(self)
-        if size == 0:
+    def sample(self, batch_size: int, beta, generator=None):
+        """-> (idx int64[bs], importance weights f32[bs]) — :64-73.  Shapes and control flow do not depend on how full
+        the ring is (unfilled slots have priority 0, hence probability 0; `beta` may be a 0-d device tensor), so the
+        whole update can be captured in a CUDA graph."""
+        if self.seen == 0:
             raise RuntimeError("sampling from an empty replay ring")
-        probs = self.prios[:size].pow(self.alpha)
+        probs = self.prios.pow(self.alpha)
         probs = probs / probs.sum()
         # np.random.choice(p=probs) is inverse-CDF sampling; the same here (torch.multinomial costs 1 ms at 2 M rows)
         cdf = probs.cumsum(0)
         u = torch.rand(batch_size, device=probs.device, generator=generator) * cdf[-1]
-        idx = torch.searchsorted(cdf, u, right=True).clamp_(max=size - 1)
-        w = (size * probs[idx]).pow(-beta)
+        idx = torch.searchsorted(cdf, u, right=True).clamp_(max=self.ring.capacity - 1)
+        w = (self.size_t * probs[idx]).pow(-beta)
         return idx, w / w.max()
 
     def update_priorities(self, idx, td_abs):
@@ -89,7 +92,8 @@ class DQNTrainer:
     """Double-DQN on the NoisyNet heads of player B (features frozen) — scripts/train_iterative.py:93-104,132-168."""
 
     def __init__(self, model_b: QNet, gamma: float = 0.99, lr: float = 2.5e-4, batch_size: int = 256,
-                 target_update_interval: int = 1000, beta_start: float = 0.4, beta_frames: int = 100000, device="cuda"):
+                 target_update_interval: int = 1000, beta_start: float = 0.4, beta_frames: int = 100000, device="cuda",
+                 use_graph: bool = True):
         self.device = torch.device(device)
         self.model = model_b.to(self.device)
         for p in self.model.features.parameters():                                   # :97
@@ -97,19 +101,17 @@ class DQNTrainer:
         self.target = copy.deepcopy(self.model)
         self.target.eval()                                                             # :100
         self.head_params = list(self.model.fc_V.parameters()) + list(self.model.fc_A.parameters())
-        self.opt = torch.optim.Adam(self.head_params, lr=lr)                         # :101-104
+        self.use_graph = use_graph
+        capturable = use_graph and self.device.type == "cuda"
+        self.opt = torch.optim.Adam(self.head_params, lr=lr, capturable=capturable)    # :101-104
+        self._graph, self._eager_runs = None, 0
         self.gamma, self.batch_size, self.target_update_interval = gamma, batch_size, target_update_interval
         self.beta_start, self.beta_frames = beta_start, beta_frames
         self.frame_idx = self.train_steps = 0
 
-    def update(self, sampler: PrioritizedSampler, generator=None):
-        """One train_step().  Returns the loss (a 0-d device tensor: no host sync), or None while the ring holds fewer
-        than batch_size rows (:134-135)."""
-        if len(sampler) < self.batch_size:
-            return None
+    def _body(self, sampler: PrioritizedSampler, beta, generator=None):
+        """train_step() on the device; `beta` is a float or a 0-d device tensor.  No host synchronisation."""
         ring = sampler.ring
-        self.frame_idx += 1
-        beta = min(1.0, self.beta_start + self.frame_idx * (1.0 - self.beta_start) / self.beta_frames)
         idx, iw = sampler.sample(self.batch_size, beta, generator)
         self.model.reset_noise()                                                       # :142-143
         self.target.reset_noise()
@@ -128,10 +130,43 @@ class DQNTrainer:
         ppd.allreduce_mean_grads(self.head_params)                                     # one NCCL all-reduce of 520 floats
         self.opt.step()
         sampler.update_priorities(idx, td)                                             # :163-164
+        return loss.detach()
+
+    def update(self, sampler: PrioritizedSampler, generator=None):
+        """One train_step().  Returns the loss (a 0-d device tensor: no host sync), or None while the ring holds fewer
+        than batch_size rows (:134-135).  On CUDA the update is captured into a CUDA graph after three eager calls
+        (~150 tiny kernels per update are otherwise bound by launch overhead, 2.7 ms of host time each)."""
+        if len(sampler) < self.batch_size:
+            return None
+        self.frame_idx += 1
+        beta = min(1.0, self.beta_start + self.frame_idx * (1.0 - self.beta_start) / self.beta_frames)
+        if self.use_graph and generator is None and self.device.type == "cuda":
+            loss = self._graphed(sampler, beta)
+        else:
+            loss = self._body(sampler, beta, generator)
         self.train_steps += 1
         if self.train_steps % self.target_update_interval == 0:                        # :166-168
             self.target.load_state_dict(self.model.state_dict())
-        return loss.detach()
+        return loss
+
+    def _graphed(self, sampler: PrioritizedSampler, beta: float):
+        if self._graph is None:
+            if self._eager_runs < 3:                      # the first updates run eagerly: they ARE the warm-up
+                self._eager_runs += 1
+                return self._body(sampler, beta)
+            self._beta_t = torch.zeros((), dtype=torch.float32, device=self.device)
+            self._beta_t.fill_(beta)
+            self._graph_sampler = sampler
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._loss_t = self._body(sampler, self._beta_t)
+            self._graph = graph                           # capture records without running: replay below IS this update
+        if sampler is not self._graph_sampler:
+            raise RuntimeError("the captured update is bound to the sampler (ring) it was built with")
+        self._beta_t.fill_(beta)
+        self._graph.replay()
+        return self._loss_t.clone()
 
 
 def train_generation(engine: SelfPlayEngine, trainer: DQNTrainer, ring: ReplayRing, sampler: PrioritizedSampler,
