@@ -39,8 +39,8 @@ __device__ unsigned long long g_rt_timing[16];
 namespace {
 
 // RT_HALVES threads share one env row (same TMEM lane, different columns): more warps per scheduler for the epilogues
-constexpr int RT_ROWS = 128, RT_HALVES = 2, RT_WORKERS = RT_ROWS * RT_HALVES, RT_THREADS = RT_WORKERS + 32,
-              RT_ISSUER_WARP = RT_WORKERS / 32;
+constexpr int RT_ROWS = 128, RT_HALVES = 2, RT_WORKERS = RT_ROWS * RT_HALVES, RT_THREADS = RT_WORKERS + 64,
+              RT_ISSUER_WARP = RT_WORKERS / 32, RT_PRODUCER_WARP = RT_ISSUER_WARP + 1;
 constexpr uint32_t RT_SLOTS = 4, RT_SLOT = PP_RNNTC_SLOT_BYTES;
 constexpr uint32_t SM_RING = 0, SM_HNEW = SM_RING + RT_SLOTS * RT_SLOT, SM_HNEW_LO = SM_HNEW + 32768,
                    SM_X = SM_HNEW + 65536, SM_CTRL = SM_X + 4096, SM_FLAGS = SM_CTRL + 128, SM_TOTAL = SM_FLAGS + 2 * RT_ROWS;
@@ -70,43 +70,18 @@ struct Issuer {
     uint8_t *smem;
     uint64_t *bars;
     uint32_t tm;                   // TMEM base
-    // ring bookkeeping in small ints (no 64-bit division on the issue path): next stage to request / to consume
-    int p_stage, p_slot, p_round, p_player;      // stage within its player-step, ring slot, slot round parity, image select
-    int c_slot, c_round, inflight;
-    long long to_request;          // stages not yet requested over the whole launch
+    int c_slot, c_round;           // ring slot to consume next and its round parity
     uint32_t ready_par, dfree_par;
-    const uint8_t *img_a, *img_b;  // weight images of the player-step sequence: even player-steps a, odd b
     bool leader;                   // ALL lanes of the issuer warp run the program (uniform control flow keeps counters and
                                    // descriptors in uniform registers); only the leader lane executes the TMA / MMA / commit
 
-    // Keep up to RT_SLOTS stages in flight.  A slot is free once the MMAs that read it have COMPLETED; blocking on that
-    // here would drain the tensor pipe between stages, so slots that are still being read are skipped for now (the
-    // next acquire() tries again) — unless the stage about to be consumed has not even been requested yet.
-    __device__ __forceinline__ void fill() {
-        while (to_request > 0 && inflight < (int)RT_SLOTS) {
-            if (inflight > 0) {
-                if (!tc::mbar_test_wait(bars + B_EMPTY + p_slot, (uint32_t)(p_round ^ 1))) break;
-            } else { RT_T0(t_); tc::mbar_wait(bars + B_EMPTY + p_slot, (uint32_t)(p_round ^ 1)); if (leader) RT_ADD(2, t_); }   // first round passes at once
-            uint32_t off, bytes;
-            stage_info(p_stage, off, bytes);
-            if (leader) {
-                tc::mbar_expect_tx(bars + B_FULL + p_slot, bytes);
-                tc::tma_bulk_g2s(smem + SM_RING + p_slot * RT_SLOT, (p_player ? img_b : img_a) + off, bytes, bars + B_FULL + p_slot);
-            }
-            if (++p_stage == PP_RNNTC_STAGES) { p_stage = 0; p_player ^= 1; }
-            if (++p_slot == (int)RT_SLOTS) { p_slot = 0; p_round ^= 1; }
-            ++inflight; --to_request;
-        }
-    }
-    __device__ __forceinline__ uint32_t acquire() {     // shared-memory address of the next stage, landed
-        fill();
+    __device__ __forceinline__ uint32_t acquire() {     // shared-memory address of the next stage, landed (Producer sent it)
         { RT_T0(t_); tc::mbar_wait(bars + B_FULL + c_slot, (uint32_t)c_round); if (leader) RT_ADD(3, t_); }
         return tc::smem_u32(smem + SM_RING + c_slot * RT_SLOT);
     }
     __device__ __forceinline__ void release() {         // the slot is free once the MMAs issued so far have read it
         if (leader) tc::umma_commit(bars + B_EMPTY + c_slot);
         if (++c_slot == (int)RT_SLOTS) { c_slot = 0; c_round ^= 1; }
-        --inflight;
     }
     __device__ __forceinline__ void wait_ready() {
         { RT_T0(t_); tc::mbar_wait(bars + B_READY, ready_par); if (leader) RT_ADD(1, t_); }
@@ -121,46 +96,77 @@ struct Issuer {
     __device__ __forceinline__ void done(int b) { if (leader) tc::umma_commit(bars + B_DONE + b); }
 };
 
-#define RT_LEADER is.leader
-template <int N> __device__ __forceinline__ void mma_ts_(bool leader, uint32_t d, uint32_t a_tm, uint32_t b_sm, bool acc) {
-    const uint64_t bd = tc::smem_desc(b_sm, N * 16, SBO);
-    if (leader) tc::umma_f16_ts(d, a_tm, bd, tc::idesc_f16(128, N), acc);
+// The producer warp: streams the weight image of every player-step, stage by stage, into the ring (TMA bulk copies).
+// It only ever blocks on a slot's `empty` barrier, i.e. on the MMAs that still read that slot.
+struct Producer {
+    uint8_t *smem;
+    uint64_t *bars;
+    int slot, round;
+    bool leader;
+    __device__ __forceinline__ void player_step(const uint8_t *img) {
+#pragma unroll 1
+        for (int st = 0; st < PP_RNNTC_STAGES; ++st) {
+            tc::mbar_wait(bars + B_EMPTY + slot, (uint32_t)(round ^ 1));       // first round passes at once
+            uint32_t off, bytes;
+            stage_info(st, off, bytes);
+            if (leader) {
+                tc::mbar_expect_tx(bars + B_FULL + slot, bytes);
+                tc::tma_bulk_g2s(smem + SM_RING + slot * RT_SLOT, img + off, bytes, bars + B_FULL + slot);
+            }
+            if (++slot == (int)RT_SLOTS) { slot = 0; round ^= 1; }
+        }
+    }
+};
+
+// MMA issue helpers.  Descriptors are built once per operand and ADVANCED by constants (one uniform add per MMA): the
+// issue loop must run well ahead of the 64-cycle-per-MMA tensor pipe.
+template <int N> __device__ __forceinline__ uint64_t bdesc(uint32_t b_sm) { return tc::smem_desc(b_sm, N * 16, SBO); }
+__device__ __forceinline__ uint64_t adesc(uint32_t a_sm) { return tc::smem_desc(a_sm, A_LBO, SBO); }
+constexpr uint64_t A_KSTEP = (2 * A_LBO) >> 4;                    // descriptor increment per K = 16 step of a 128-row A tile
+
+// COUNT K-steps: D (+)= A[tmem at a_tm + 8 j] * B[bd + j * kstep].  ONE branch on the leader predicate around the whole
+// run (a branch per MMA costs more than the MMA's issue slot); the operands are warp-uniform values computed by all lanes.
+template <int N, int COUNT> __device__ __forceinline__ void mma_ts_run(bool leader, uint32_t d, uint32_t a_tm, uint64_t bd, bool acc_first) {
+    if (leader) {
+#pragma unroll
+        for (int j = 0; j < COUNT; ++j)
+            tc::umma_f16_ts(d, a_tm + 8 * j, bd + (uint64_t)j * ((2 * N * 16) >> 4), tc::idesc_f16(128, N), acc_first || j > 0);
+    }
 }
-template <int N> __device__ __forceinline__ void mma_ss_(bool leader, uint32_t d, uint32_t a_sm, uint32_t b_sm, bool acc) {
-    const uint64_t ad = tc::smem_desc(a_sm, A_LBO, SBO), bd = tc::smem_desc(b_sm, N * 16, SBO);
-    if (leader) tc::umma_f16(d, ad, bd, tc::idesc_f16(128, N), acc);
+template <int N, int COUNT> __device__ __forceinline__ void mma_ss_run(bool leader, uint32_t d, uint64_t ad, uint64_t bd, bool acc_first) {
+    if (leader) {
+#pragma unroll
+        for (int j = 0; j < COUNT; ++j)
+            tc::umma_f16(d, ad + (uint64_t)j * A_KSTEP, bd + (uint64_t)j * ((2 * N * 16) >> 4), tc::idesc_f16(128, N), acc_first || j > 0);
+    }
 }
-#define mma_ts mma_ts_
-#define mma_ss mma_ss_
 
 // one player-step of MMA work (called by ALL lanes of the issuer warp; see Issuer::leader)
 __device__ __forceinline__ void issue_player_step(Issuer &is) {
-    const uint32_t tm = is.tm, x = tc::smem_u32(is.smem + SM_X);
-    const uint32_t hh = tc::smem_u32(is.smem + SM_HNEW), hl = tc::smem_u32(is.smem + SM_HNEW_LO);
-    constexpr uint32_t KS128 = 2 * 128 * 16, KS64 = 2 * 64 * 16, KS16 = 2 * 16 * 16;      // B bytes per K = 16 step
+    const bool ld = is.leader;
+    const uint32_t tm = is.tm;
+    const uint64_t x = adesc(tc::smem_u32(is.smem + SM_X));
+    const uint64_t hh = adesc(tc::smem_u32(is.smem + SM_HNEW)), hl = adesc(tc::smem_u32(is.smem + SM_HNEW_LO));
     uint32_t a;
     // ---- L1: D0[0..63] = X * W1h' + X * W1l'
     is.wait_ready();
     a = is.acquire();
-    mma_ss<64>(RT_LEADER, tm + T_D0, x, a, false);
-    mma_ss<64>(RT_LEADER, tm + T_D0, x, a + 2048, true);
+    mma_ss_run<64, 1>(ld, tm + T_D0, x, bdesc<64>(a), false);
+    mma_ss_run<64, 1>(ld, tm + T_D0, x, bdesc<64>(a + 2048), true);
     is.release();
     is.done(0);
     // ---- features.2: D0[0..127] = F1h*Wh + F1l*Wh + X*B + F1h*Wl
     is.wait_ready();
     a = is.acquire();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, tm + T_D0, tm + T_FHI + j * 8, a + j * KS128, j > 0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, tm + T_D0, tm + T_FLO + j * 8, a + j * KS128, true);
-    mma_ss<128>(RT_LEADER, tm + T_D0, x, a + PP_RNNTC_TILE, true);
+    mma_ts_run<128, 4>(ld, tm + T_D0, tm + T_FHI, bdesc<128>(a), false);
+    mma_ts_run<128, 4>(ld, tm + T_D0, tm + T_FLO, bdesc<128>(a), true);
+    mma_ss_run<128, 1>(ld, tm + T_D0, x, bdesc<128>(a + PP_RNNTC_TILE), true);
     is.release();
     a = is.acquire();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, tm + T_D0, tm + T_FHI + j * 8, a + j * KS128, true);
+    mma_ts_run<128, 4>(ld, tm + T_D0, tm + T_FHI, bdesc<128>(a), true);
     is.release();
     is.done(0);
-    // ---- gates, four quarters of 32 units, K = 256 in four stages of 64
+    // ---- gates, four quarters of 32 units, K = 256 in four stages of 64 (hi weights), then four more (lo weights)
     is.wait_ready();
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
@@ -169,18 +175,16 @@ __device__ __forceinline__ void issue_player_step(Issuer &is) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             a = is.acquire();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, d, tm + T_AHI + (c * 4 + j) * 8, a + j * KS128, (c | j) != 0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, d, tm + T_ALO + (c * 4 + j) * 8, a + j * KS128, true);
-            if (c == 0) mma_ss<128>(RT_LEADER, d, x, a + PP_RNNTC_TILE, true);
+            const uint64_t bd = bdesc<128>(a);
+            mma_ts_run<128, 4>(ld, d, tm + T_AHI + c * 32, bd, c != 0);
+            mma_ts_run<128, 4>(ld, d, tm + T_ALO + c * 32, bd, true);
+            if (c == 0) mma_ss_run<128, 1>(ld, d, x, bdesc<128>(a + PP_RNNTC_TILE), true);
             is.release();
         }
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {                   // A_hi * W_lo
             a = is.acquire();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mma_ts<128>(RT_LEADER, d, tm + T_AHI + (c * 4 + j) * 8, a + j * KS128, true);
+            mma_ts_run<128, 4>(ld, d, tm + T_AHI + c * 32, bdesc<128>(a), true);
             is.release();
         }
         is.done(q & 1);
@@ -190,38 +194,29 @@ __device__ __forceinline__ void issue_player_step(Issuer &is) {
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         a = is.acquire();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_ss<128>(RT_LEADER, tm + T_D0, hh + (c * 4 + j) * 2 * A_LBO, a + j * KS128, (c | j) != 0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_ss<128>(RT_LEADER, tm + T_D0, hl + (c * 4 + j) * 2 * A_LBO, a + j * KS128, true);
-        if (c == 0) mma_ss<128>(RT_LEADER, tm + T_D0, x, a + PP_RNNTC_TILE, true);
+        const uint64_t bd = bdesc<128>(a);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hh + c * 4 * A_KSTEP, bd, c != 0);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hl + c * 4 * A_KSTEP, bd, true);
+        if (c == 0) mma_ss_run<128, 1>(ld, tm + T_D0, x, bdesc<128>(a + PP_RNNTC_TILE), true);
         is.release();
     }
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         a = is.acquire();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_ss<128>(RT_LEADER, tm + T_D0, hh + (c * 4 + j) * 2 * A_LBO, a + j * KS128, true);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hh + c * 4 * A_KSTEP, bdesc<128>(a), true);
         is.release();
     }
     is.done(0);
     // ---- dueling heads: D1[0..15] = Sh*Whh + Sl*Whh + Sh*Whl + X*B     (K = 128, N = 16)
     is.wait_ready();
     a = is.acquire();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mma_ts<16>(RT_LEADER, tm + T_D1, tm + T_AHI + j * 8, a + j * KS16, j > 0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mma_ts<16>(RT_LEADER, tm + T_D1, tm + T_ALO + j * 8, a + j * KS16, true);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mma_ts<16>(RT_LEADER, tm + T_D1, tm + T_AHI + j * 8, a + 4096 + j * KS16, true);
-    mma_ss<16>(RT_LEADER, tm + T_D1, x, a + 8192, true);
+    mma_ts_run<16, 8>(ld, tm + T_D1, tm + T_AHI, bdesc<16>(a), false);
+    mma_ts_run<16, 8>(ld, tm + T_D1, tm + T_ALO, bdesc<16>(a), true);
+    mma_ts_run<16, 8>(ld, tm + T_D1, tm + T_AHI, bdesc<16>(a + 4096), true);
+    mma_ss_run<16, 1>(ld, tm + T_D1, x, bdesc<16>(a + 8192), true);
     is.release();
     is.done(1);
-    (void)KS64;
 }
-
-#undef mma_ts
-#undef mma_ss
 
 // ------------------------------------------------------------------------------------------ compute side
 struct Worker {
@@ -302,26 +297,19 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
     float4 *hs4 = reinterpret_cast<float4 *>(gh + (size_t)env * 128), *cs4 = reinterpret_cast<float4 *>(gc + (size_t)env * 128);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int half = w.half;
-    // ---- this thread's share of c_prev (sub-block `half` of every quarter: 32 values) is requested FIRST: the loads
-    // come from L2 / HBM and have the whole feature phase to land
     constexpr int SUBS = 4 / RT_HALVES;
-    float4 cp[4][2 * SUBS];
-#pragma unroll
-    for (int qt = 0; qt < 4; ++qt)
-#pragma unroll
-        for (int sb = 0; sb < SUBS; ++sb) {
-            const int b = half * SUBS + sb;
-            cp[qt][2 * sb] = carry ? cs4[qt * 8 + 2 * b] : zero4;
-            cp[qt][2 * sb + 1] = carry ? cs4[qt * 8 + 2 * b + 1] : zero4;
-        }
     // ---- X row; h_prev -> A (columns 64..127 of the hi / lo halves)
     if (half == 0) write_x_row(w.smem + SM_X, row, obs);
     RT_T0(th_);
-#pragma unroll 1
-    for (int blk = half; blk < 4; blk += RT_HALVES) {   // 32 units per block: 8 x 16-byte loads in flight, 16 packed pairs
-        float4 v[8];
+    float4 hv_[4 / RT_HALVES][8];                        // ALL of this thread's h_prev loads are in flight before the first use
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = carry ? h4[blk * 8 + j] : zero4;
+    for (int bi = 0; bi < 4 / RT_HALVES; ++bi)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hv_[bi][j] = carry ? h4[(half + bi * RT_HALVES) * 8 + j] : zero4;
+#pragma unroll
+    for (int bi = 0; bi < 4 / RT_HALVES; ++bi) {        // 32 units per block -> 16 packed pairs
+        const int blk = half + bi * RT_HALVES;
+        const float4 (&v)[8] = hv_[bi];
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -346,9 +334,18 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
     w.publish(false);
     // ---- LSTM cell, quarter by quarter (i, f, g, o at columns 0, 32, 64, 96 of the buffer; 8 units per sub-block, the
     // sub-blocks of a quarter are shared out over the row's threads).
+    // The quarter's c_prev values are requested BEFORE waiting for its gates, so the loads ride under the MMAs; the
+    // quarter loop is not unrolled (the cell code is large and the kernel was instruction-cache bound when it was).
     uint8_t *hn = w.smem + SM_HNEW;
-#pragma unroll
+#pragma unroll 1
     for (int qt = 0; qt < 4; ++qt) {
+        float4 cp[2 * SUBS];
+#pragma unroll
+        for (int sb = 0; sb < SUBS; ++sb) {
+            const int b = half * SUBS + sb;
+            cp[2 * sb] = carry ? cs4[qt * 8 + 2 * b] : zero4;
+            cp[2 * sb + 1] = carry ? cs4[qt * 8 + 2 * b + 1] : zero4;
+        }
         w.wait_done(qt & 1);
         const uint32_t d = tm + ((qt & 1) ? T_D1 : T_D0);
         RT_T0(tc_);
@@ -361,8 +358,8 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
             tmem_ld8(d + 64 + 8 * b, gg);
             tmem_ld8(d + 96 + 8 * b, go);
             tc::tmem_ld_wait();
-            const float cprev[8] = {cp[qt][2 * sb].x, cp[qt][2 * sb].y, cp[qt][2 * sb].z, cp[qt][2 * sb].w,
-                                    cp[qt][2 * sb + 1].x, cp[qt][2 * sb + 1].y, cp[qt][2 * sb + 1].z, cp[qt][2 * sb + 1].w};
+            const float cprev[8] = {cp[2 * sb].x, cp[2 * sb].y, cp[2 * sb].z, cp[2 * sb].w,
+                                    cp[2 * sb + 1].x, cp[2 * sb + 1].y, cp[2 * sb + 1].z, cp[2 * sb + 1].w};
             float hv[8], cv[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
@@ -429,13 +426,16 @@ qnetrnn_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy p
     int64_t my_tiles = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) ++my_tiles;
     if (warp_id == RT_ISSUER_WARP) {
-        Issuer is{smem, bars, tm, 0, 0, 0, 0, 0, 0, 0, my_tiles * PP_RNNTC_STAGES, 0u, 0u,
-                  reinterpret_cast<const uint8_t *>(pol.weights), reinterpret_cast<const uint8_t *>(pol.weights), tc::elect_one()};
+        Issuer is{smem, bars, tm, 0, 0, 0u, 0u, tc::elect_one()};
         for (int64_t t = 0; t < my_tiles; ++t) {
             RT_T0(t_);
             issue_player_step(is);
             if (is.leader) RT_ADD(5, t_);
         }
+        __syncwarp();
+    } else if (warp_id == RT_PRODUCER_WARP) {
+        Producer pr{smem, bars, 0, 0, tc::elect_one()};
+        for (int64_t t = 0; t < my_tiles; ++t) pr.player_step(reinterpret_cast<const uint8_t *>(pol.weights));
         __syncwarp();
     } else {
         const int row = threadIdx.x & (RT_ROWS - 1), half = threadIdx.x / RT_ROWS;
@@ -487,10 +487,10 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
     const bool ra = pol_a.kind == PP_POLICY_QNETRNN, rb = pol_b.kind == PP_POLICY_QNETRNN;
     const int64_t total_warps = (n + 31) / 32;
 
-    if (warp_id == RT_ISSUER_WARP) {
-        const uint8_t *ia = reinterpret_cast<const uint8_t *>(ra ? pol_a.weights : pol_b.weights);
-        const uint8_t *ib = reinterpret_cast<const uint8_t *>(rb ? pol_b.weights : pol_a.weights);
-        Issuer is{smem, bars, tm, 0, 0, 0, 0, 0, 0, 0, 0, 0u, 0u, ia, ib, tc::elect_one()};
+    if (warp_id == RT_ISSUER_WARP || warp_id == RT_PRODUCER_WARP) {
+        const bool producer = warp_id == RT_PRODUCER_WARP;                      // both follow the same step protocol
+        Issuer is{smem, bars, tm, 0, 0, 0u, 0u, tc::elect_one()};
+        Producer pr{smem, bars, 0, 0, is.leader};
         uint32_t step_par = 0;
 #pragma unroll 1
         for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
@@ -500,9 +500,13 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
                 tc::mbar_wait(bars + B_STEP, step_par);
                 step_par ^= 1u;
                 if (*stop_flag) break;                                         // the tile is frozen by the quota
-                is.to_request += (long long)PP_RNNTC_STAGES * ((ra ? 1 : 0) + (rb ? 1 : 0));
-                if (ra) issue_player_step(is);
-                if (rb) issue_player_step(is);
+                if (producer) {
+                    if (ra) pr.player_step(reinterpret_cast<const uint8_t *>(pol_a.weights));
+                    if (rb) pr.player_step(reinterpret_cast<const uint8_t *>(pol_b.weights));
+                } else {
+                    if (ra) issue_player_step(is);
+                    if (rb) issue_player_step(is);
+                }
             }
         }
         __syncwarp();

@@ -5,8 +5,9 @@
 #include "tc_ptx.cuh"
 using namespace pp;
 
-template <int N, bool TS, bool COMMIT_EACH>
+template <int N, bool TS, bool COMMIT_EACH, int NOISE = 0>      // NOISE: 1 = the other warps hammer TMEM loads, 2 = MUFU
 __global__ void rate_kernel(long long *out, int iters) {
+    __shared__ volatile int stop;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar, bar2;
     __shared__ uint32_t slot;
@@ -16,6 +17,24 @@ __global__ void rate_kernel(long long *out, int iters) {
     tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
     tc::fence_proxy_async();
     const uint32_t tm = slot;
+    if (threadIdx.x == 0) stop = 0;
+    __syncthreads();
+    if (NOISE && threadIdx.x >= 32) {
+        const uint32_t lane_addr = (uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16;
+        float acc = 0.f;
+        while (!stop) {
+            if (NOISE == 1) {
+                uint32_t r[16];
+                tc::tmem_ld16(tm + lane_addr + 384, r);
+                tc::tmem_ld_wait();
+                acc += __uint_as_float(r[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc = __expf(acc) + 1.0f;
+            }
+        }
+        if (acc == 123.456f) out[1] = 0;
+    }
     if (threadIdx.x == 0) {
         const uint32_t a_sm = tc::smem_u32(smem), b_sm = tc::smem_u32(smem + 16384);
         const uint64_t ad = tc::smem_desc(a_sm, 128 * 16, 128), bd = tc::smem_desc(b_sm, N * 16, 128);
@@ -34,17 +53,18 @@ __global__ void rate_kernel(long long *out, int iters) {
         tc::mbar_wait(&bar, 0);
         long long t2 = clock64();
         out[0] = t1 - t0; out[1] = t2 - t0;
+        stop = 1;
     }
     tc::tc_fence_before(); __syncthreads();
     if (threadIdx.x < 32) tc::tmem_dealloc<512>(tm);
 }
 
-template <int N, bool TS, bool CE = false> void run(const char *name) {
+template <int N, bool TS, bool CE = false, int NOISE = 0, int THREADS = 128> void run(const char *name) {
     long long *d, h[2];
     cudaMalloc(&d, 16);
-    cudaFuncSetAttribute(rate_kernel<N, TS, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(rate_kernel<N, TS, CE, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const int iters = 200;
-    rate_kernel<N, TS, CE><<<1, 128, 64 * 1024>>>(d, iters);
+    rate_kernel<N, TS, CE, NOISE><<<1, THREADS, 64 * 1024>>>(d, iters);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
     printf("%-10s issue %.1f cyc/MMA, complete %.1f cyc/MMA (%s)\n", name, (double)h[0] / (iters * 8), (double)h[1] / (iters * 8), cudaGetErrorString(e));
@@ -57,5 +77,7 @@ int main() {
     run<128, false>("N128 SS"); run<128, true>("N128 TS");
     run<256, false>("N256 SS"); run<256, true>("N256 TS");
     run<128, true, true>("N128 TS + commit/8"); run<64, true, true>("N64 TS + commit/8");
+    run<128, true, false, 1, 288>("N128 TS + 8 warps tcgen05.ld"); run<128, true, false, 2, 288>("N128 TS + 8 warps MUFU");
+    run<64, true, false, 1, 512>("N64 TS + 15 warps tcgen05.ld"); run<64, true, false, 2, 512>("N64 TS + 15 warps MUFU");
     return 0;
 }
