@@ -330,7 +330,8 @@ def main():
     value = env_steps / (dev_ms * 1e-3)
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if args.workload == "qnet" else METRIC.replace("QNet", "QNetRNN"),
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": f"{args.mode} env state + {args.precision} QNet", "data": "synthetic",
         "config": workload_config(args, world), "clocks": clocks, "gpu_launches": args.steps,
