@@ -131,8 +131,25 @@ def _sd_np(sd, prefix):
     return {f"{prefix}/{k}": v.detach().cpu().numpy() for k, v in sd.items()}
 
 
+def gen_extra_cfgs():
+    """tests/golden/env_extra_cfgs.npz: 3 000-step reference trajectories for pong_port.EXTRA_ENV_CONFIGS."""
+    from .pong_port import EXTRA_ENV_CONFIGS
+    PongEnv2P, _, _, _ = ref_shim.load_reference()
+    out = {}
+    for ci, kw in enumerate(EXTRA_ENV_CONFIGS):
+        summary, arr = run_trajectory(PongEnv2P, kw, 3000, seed=500 + ci, action_seed=900 + ci)
+        for k, v in arr.items():
+            out[f"c{ci}/{k}"] = v
+        print(ci, {k: summary[k] for k in ("episodes", "wins_a", "wins_b", "paddle_hits")})
+    np.savez_compressed(os.path.join(OUT, "env_extra_cfgs.npz"), **out)
+
+
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        gen_extra_cfgs()
+        return
     PongEnv2P, collide, QNet, QNetRNN = ref_shim.load_reference()
     cfg = ref_shim.load_reference_config("config.yaml")["env"]
     cfg_rnn = ref_shim.load_reference_config("config_rnn.yaml")["env"]

@@ -49,6 +49,17 @@ CONFIG_YAML_ENV = dict(
 )
 CONFIG_RNN_YAML_ENV = dict(CONFIG_YAML_ENV, restitution=1.0, speed_scale_every=5, speed_increment=0.2)
 
+# Constructor keyword sets beyond the two YAML blocks (the reference accepts all of them, my_pong_env_2p.py:19-39):
+# parity is also pinned on these through tests/golden/env_extra_cfgs.npz (oracle/gen_golden.py, from the reference).
+EXTRA_ENV_CONFIGS = [
+    dict(),                                                                    # the constructor defaults
+    dict(enable_spin=False, restitution=0.9, friction=0.2, max_score=1),
+    dict(paddle_width=0.35, paddle_speed=0.07, max_score=5, speed_scale_every=2, speed_increment=0.35,
+         ball_speed_range=(0.02, 0.12), spin_range=(-25, 25), magnus_factor=0.06, world_ball_radius=0.05, ball_mass=2.5),
+    dict(restitution=1, friction=0.0, speed_scale_every=1, speed_increment=0.0, ball_angle_intervals=[[-80, -10], [10, 80]]),
+    dict(restitution=0.5, friction=1.5, paddle_width=0.05, ball_speed_range=(0.2, 0.6), max_score=2),   # very fast balls
+]
+
 
 def collide(vn, vt, u, omega, e, mu, m, R):
     """envs/physics.py:3-23 — returns (vn', vt', omega')."""

@@ -230,3 +230,47 @@ def test_full_size_properties_1m_envs(H):
         assert torch.equal(e._real[:, :q].view(torch.int64), env._real[:, r * q:(r + 1) * q].view(torch.int64))
         tot += e.counters
     assert torch.equal(tot, env.counters)
+
+
+from oracle.pong_port import EXTRA_ENV_CONFIGS as _FUZZ_CFGS
+
+
+@pytest.mark.parametrize("ci", range(len(_FUZZ_CFGS)))
+@pytest.mark.parametrize("mode", ["f64", "f32"])
+def test_other_env_parameters_bit_exact_vs_oracle(ci, mode):
+    """The env kernels take every constructor keyword of the reference, not just the two YAML blocks: defaults, spin off,
+    ints from YAML, wide paddles, fast balls (multiple events per few steps), friction 0 / > 1, max_score 1..5."""
+    cfg = pp.resolve_env_config(_FUZZ_CFGS[ci])
+    n, K, depth = 1536, 160, 5
+    pool = gu.make_pool(100 + ci, n, depth, cfg, mode)
+    acts = gu.random_actions(ci, K, n, with_invalid=True)
+    env = pp.VecPongEnv2P(n, mode=mode, serve=pool, **_FUZZ_CFGS[ci])
+    env.reset()
+    b = gu.oracle_batch_like(env, mode)
+    got = env.rollout(torch.from_numpy(acts).cuda(), trace=True)
+    want = po.rollout(po.make_params(cfg), b, acts, pool, trace=True)
+    assert np.array_equal(gu.bits(gu.np_of(got["trace_real"])), gu.bits(want["trace_real"]))
+    assert np.array_equal(gu.np_of(got["trace_int"]), want["trace_int"])
+    assert np.array_equal(gu.np_of(env.counters), want["counters"])
+    gu.assert_state_equal(env, b)
+    # and the single-step kernel with all outputs on the same state
+    a1 = gu.random_actions(77 + ci, 1, n)[0]
+    (oa, ob), (ra, rb), done, _ = env.step(torch.from_numpy(a1[:, 0].copy()), torch.from_numpy(a1[:, 1].copy()))
+    woa, wob, wra, wrb, wdone = po.step(po.make_params(cfg), b, a1[:, 0], a1[:, 1])
+    assert np.array_equal(gu.bits(gu.np_of(oa)), gu.bits(woa)) and np.array_equal(gu.bits(gu.np_of(ob)), gu.bits(wob))
+    assert np.array_equal(gu.np_of(ra), wra) and np.array_equal(gu.np_of(done), wdone)
+
+
+@pytest.mark.parametrize("ci", range(5))
+def test_rollout_kernel_replays_reference_trajectories_of_other_configs(ci):
+    """The reference's own 3 000-step trajectories for the extra constructor keyword sets, replayed on the device."""
+    g = {k.split("/", 1)[1]: v for k, v in np.load(os.path.join(gu.GOLDEN, "env_extra_cfgs.npz")).items() if k.startswith(f"c{ci}/")}
+    serves = g["serves"]
+    pool = tuple(serves[:, i].reshape(-1, 1).copy() for i in range(3))
+    env = pp.VecPongEnv2P(1, mode="f64", serve=pool, **_FUZZ_CFGS[ci])
+    env.reset()
+    K = g["actions"].shape[0]
+    out = env.rollout(torch.from_numpy(g["actions"].reshape(K, 1, 2).copy()).cuda(), trace=True)
+    assert np.array_equal(gu.bits(gu.np_of(out["trace_real"])[:, :, 0]), gu.bits(g["state"]))
+    ti = gu.np_of(out["trace_int"])
+    assert np.array_equal(ti[:, :3, 0], g["ints"]) and np.array_equal(ti[:, 3, 0] & 1, g["done"])

@@ -168,3 +168,23 @@ def test_f32_mode_tracks_f64_teacher_forced(golden_dir, hashes):
     scale = np.maximum(np.maximum(np.abs(s64[:, same_event]), np.abs(pre32.T.astype(np.float64)[:, same_event])), 1e-2)
     assert (err / scale).max() < 1e-5
     del exact, post
+
+
+@pytest.mark.parametrize("ci", range(5))
+def test_c_oracle_and_port_replay_reference_trajectories_of_other_configs(golden_dir, ci):
+    """Constructor keyword sets beyond the YAML blocks (defaults, spin off, fast balls, friction 0 / > 1, max_score 1..5):
+    3 000-step trajectories generated from the unmodified reference, replayed bit for bit by the C oracle."""
+    from oracle.pong_port import ENV_DEFAULTS, EXTRA_ENV_CONFIGS
+    g = {k.split("/", 1)[1]: v for k, v in np.load(os.path.join(golden_dir, "env_extra_cfgs.npz")).items() if k.startswith(f"c{ci}/")}
+    cfg = dict(ENV_DEFAULTS, **EXTRA_ENV_CONFIGS[ci])
+    if not cfg["ball_angle_intervals"]:
+        cfg["ball_angle_intervals"] = [[-60, -30], [30, 60]]
+    serves = g["serves"]
+    b = po.EnvBatch(1, "f64")
+    b.serve(*serves[0])
+    K = g["actions"].shape[0]
+    out = po.rollout(po.make_params(cfg), b, g["actions"].reshape(K, 1, 2), tuple(serves[:, i].reshape(-1, 1) for i in range(3)), trace=True)
+    assert np.array_equal(_bits(out["trace_real"][:, :, 0]), _bits(g["state"]))
+    assert np.array_equal(out["trace_int"][:, :3, 0], g["ints"])
+    assert np.array_equal(out["trace_int"][:, 3, 0] & 1, g["done"])
+    assert g["done"].sum() >= 5
