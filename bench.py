@@ -200,8 +200,12 @@ def run_reference(args, rank: int):
     procs = max(1, min(cores, int(os.environ.get("PP_REF_PROCS", cores))))
     per_proc = args.ref_steps
     pool = PortPool(procs)
-    for _ in range(args.warmup):
-        pool.run(max(per_proc // 8, 50))
+    rate = None
+    for _ in range(max(args.warmup, 1)):
+        v, _ = pool.run(max(per_proc // 8, 50))
+        rate = v / procs                                   # env-steps/s of one process
+    # keep the whole timed run within ~2.5 minutes whatever --steps is: a step is a BOUNDED sample of the workload
+    per_proc = int(min(per_proc, max(50, 150.0 * rate / max(args.steps, 1))))
     t0 = time.perf_counter()
     for _ in range(args.steps):
         pool.run(per_proc)

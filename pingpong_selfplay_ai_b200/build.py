@@ -60,6 +60,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = _nvcc()
     os.makedirs(BUILD, exist_ok=True)
+    # one builder at a time (torchrun starts several ranks at once); the others wait and then find a fresh library
+    import fcntl
+    lock = open(os.path.join(BUILD, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not is_stale():
+            return LIB
+        return _build_locked(nvcc, force, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, force: bool, verbose: bool) -> str:
     dep_t = max(os.path.getmtime(p) for p in _deps())
 
     def compile_one(src):
