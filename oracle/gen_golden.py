@@ -144,9 +144,93 @@ def gen_extra_cfgs():
     np.savez_compressed(os.path.join(OUT, "env_extra_cfgs.npz"), **out)
 
 
+def gen_checkpoint_golden():
+    """tests/golden/ckpt_golden.npz: what the reference's own loader (tests/test_round_robin.py:116-185) makes of the
+    three on-disk formats — Q-values of the loaded nets on seeded observations.  The legacy (`fc.*`) case is a synthetic
+    state_dict stored in the fixture itself, so the test needs no reference file; the three real files are addressed by
+    their path under the reference root and checked only where that tree exists (this container)."""
+    import tempfile
+
+    import torch
+    rr = ref_shim.load_reference_round_robin()
+    rs = np.random.RandomState(2468)
+    obs = np.concatenate([rs.uniform(-1, 1, size=(48, 7)), rs.uniform(-0.1, 1.1, size=(48, 7))]).astype(np.float32)
+    out = {"obs": obs}
+    g = torch.Generator().manual_seed(97)
+    legacy = {"fc.0.weight": torch.randn(64, 7, generator=g) * 0.6, "fc.0.bias": torch.randn(64, generator=g) * 0.2,
+              "fc.2.weight": torch.randn(64, 64, generator=g) * 0.25, "fc.2.bias": torch.randn(64, generator=g) * 0.2,
+              "fc.4.weight": torch.randn(3, 64, generator=g) * 0.3, "fc.4.bias": torch.randn(3, generator=g) * 0.2}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "legacy.pth")
+        torch.save({"model": legacy, "epsilon": 0.1, "episode": 7}, path)
+        net = rr.load_model_universal({"name": "legacy", "path": path, "type": "QNet"}, {}, torch.device("cpu"))
+    with torch.no_grad():
+        out["legacy/q"] = net(torch.from_numpy(obs)).numpy()
+    for k, v in legacy.items():
+        out["legacy/sd/" + k] = v.numpy()
+    real = {"legacy_file": ("QNet", "checkpoints/model4-12.pth"), "dueling_file": ("QNet", "checkpoints/model5-3_fault.pth"),
+            "rnn_file": ("QNetRNN", "checkpoints_rnn/rnn_pong_soul_2.pth")}
+    for tag, (typ, rel) in real.items():
+        net = rr.load_model_universal({"name": tag, "path": os.path.join(ref_shim.REFERENCE_ROOT, rel), "type": typ}, {},
+                                      torch.device("cpu"))
+        with torch.no_grad():
+            if typ == "QNet":
+                q = net(torch.from_numpy(obs))
+            else:                                           # two steps, so (h, c) of the first one matter
+                h = net.init_hidden(obs.shape[0], torch.device("cpu"))
+                _, h = net(torch.from_numpy(obs[::-1].copy()).unsqueeze(1), h)
+                q, _ = net(torch.from_numpy(obs).unsqueeze(1), h)
+        out[tag + "/q"] = q.numpy()
+        out[tag + "/path"] = np.array(rel)
+        out[tag + "/type"] = np.array(typ)
+    np.savez_compressed(os.path.join(OUT, "ckpt_golden.npz"), **out)
+    print({k: (v.shape if v.ndim else str(v)) for k, v in out.items() if not k.startswith("legacy/sd")})
+
+
+def synthetic_arena_database():
+    """A small arena_database.json-shaped history: 5 models, uneven pair counts, swapped sides, a draw."""
+    import random
+    rng = random.Random(4242)
+    models = [{"id": f"m{k}", "type": "QNet", "path": f"checkpoints/m{k}.pth", "description": f"model {k}"} for k in range(4)]
+    models.append({"id": "BallFollowerBot", "type": "HardcodedBallFollower", "path": "N/A"})
+    ids = [m["id"] for m in models]
+    hist = []
+    for a in range(len(ids)):
+        for b in range(a + 1, len(ids)):
+            for _ in range(rng.randint(0, 7)):
+                p1, p2 = (ids[a], ids[b]) if rng.random() < 0.6 else (ids[b], ids[a])
+                sa, sb = (3, rng.randint(0, 2)) if rng.random() < 0.55 else (rng.randint(0, 2), 3)
+                hist.append({"p1": p1, "p2": p2, "winner": p1 if sa > sb else p2, "p1_score": sa, "p2_score": sb,
+                             "timestamp": "2025-01-01T00:00:00Z"})
+    hist.append({"p1": "m0", "p2": "m1", "winner": "draw", "p1_score": 2, "p2_score": 2, "timestamp": "2025-01-01T00:00:00Z"})
+    return {"models": models, "match_history": hist}
+
+
+def gen_arena_golden():
+    """tests/golden/arena_golden.json: the reference's own create_match_plan / generate_summary_report / register_models
+    (tests/arena.py:147-155,222-245,323-352) on the synthetic database above."""
+    import copy
+    arena = ref_shim.load_reference_round_robin("arena.py")
+    db = synthetic_arena_database()
+    plan = arena.create_match_plan(copy.deepcopy(db), 5)
+    summary = arena.generate_summary_report(copy.deepcopy(db)).reset_index().to_dict(orient="records")
+    db2 = copy.deepcopy(db)
+    added = arena.register_models(db2, [{"id": "m1", "type": "QNet", "path": "x"}, {"id": "new", "type": "QNetRNN", "path": "y"}])
+    with open(os.path.join(OUT, "arena_golden.json"), "w") as f:
+        json.dump({"database": db, "plan_5": plan, "summary": summary, "register_added": bool(added),
+                   "register_ids": [m["id"] for m in db2["models"]]}, f, indent=1)
+    print(len(db["match_history"]), "records;", len(plan), "pairings to play;", summary[0])
+
+
 def main():
     import sys
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "arena":
+        gen_arena_golden()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "ckpt":
+        gen_checkpoint_golden()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "extra":
         gen_extra_cfgs()
         return

@@ -79,3 +79,23 @@ def load_reference_config(name: str = "config.yaml") -> dict:
     import yaml
     with open(os.path.join(REFERENCE_ROOT, name), "r") as f:
         return yaml.safe_load(f)
+
+
+def load_reference_round_robin(filename: str = "test_round_robin.py"):
+    """tests/test_round_robin.py (or tests/arena.py) of the reference as a module, for its load_model_universal /
+    select_action_universal / database helpers.  Both import matplotlib and seaborn at module top for their plots;
+    neither is installed, neither touches the functions used here."""
+    import importlib.util
+    load_reference()                                   # gym / pygame stubs + the reference's envs / models in sys.modules
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    spec = importlib.util.spec_from_file_location("_ref_" + filename[:-3], os.path.join(REFERENCE_ROOT, "tests", filename))
+    mod = importlib.util.module_from_spec(spec)
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    return mod

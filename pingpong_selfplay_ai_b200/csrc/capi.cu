@@ -153,16 +153,15 @@ int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, 
     if (!state_ok(state, true) || !serve_ok(serve) || !out_ok(out)) return fail(PP_E_NULL, "pp_selfplay_rollout");
     if (!policy_ok(policy_a, true) || !policy_ok(policy_b, true)) return fail(PP_E_MODE, "pp_selfplay_rollout");
     const bool rnn = policy_a->kind == PP_POLICY_QNETRNN || policy_b->kind == PP_POLICY_QNETRNN;
-    // a recurrent player meets another recurrent player, the ball follower or the random player (tests/arena.py pairings
-    // QNetRNN x QNet would need both weight sets resident: not built)
-    if (rnn && (policy_a->kind == PP_POLICY_QNET || policy_b->kind == PP_POLICY_QNET)) return fail(PP_E_MODE, "pp_selfplay_rollout");
+    // a recurrent player meets any other player (tests/arena.py pairings); a QNet that meets a recurrent player runs in
+    // fp32 on the CUDA cores of the recurrent kernel whatever its `precision` says (exact fp32 meets both tolerances)
     if (!prec_ok(policy_a) || !prec_ok(policy_b)) return fail(PP_E_MODE, "pp_selfplay_rollout");
     const bool rnn_tc = rnn && ((policy_a->kind == PP_POLICY_QNETRNN && policy_a->precision == PP_PREC_F16) ||
                                 (policy_b->kind == PP_POLICY_QNETRNN && policy_b->precision == PP_PREC_F16));
     if (rnn_tc && ((policy_a->kind == PP_POLICY_QNETRNN && policy_a->precision != PP_PREC_F16) ||
                    (policy_b->kind == PP_POLICY_QNETRNN && policy_b->precision != PP_PREC_F16)))
         return fail(PP_E_MODE, "pp_selfplay_rollout");                 // both recurrent players on the same path
-    const bool tc = uses_tc(policy_a) || uses_tc(policy_b);
+    const bool tc = !rnn && (uses_tc(policy_a) || uses_tc(policy_b));
     if (tc && ((policy_a->kind == PP_POLICY_QNET && !uses_tc(policy_a)) || (policy_b->kind == PP_POLICY_QNET && !uses_tc(policy_b))))
         return fail(PP_E_MODE, "pp_selfplay_rollout");                 // both QNet players on the same path
     if (ring && !ring_ok(ring)) return fail(PP_E_NULL, "pp_selfplay_rollout");

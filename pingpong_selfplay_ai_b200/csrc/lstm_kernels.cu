@@ -282,6 +282,7 @@ selfplay_rnn_kernel(const PPParams params, const PPEnvState st, int64_t n, int64
                 __syncthreads();                                // obs_s / A are reused by the other player
             } else if (env_thread) {
                 if (pol.kind == PP_POLICY_RANDOM) a = random_action(seed, gid, step, stream_id);
+                else if (pol.kind == PP_POLICY_QNET) a = explore(qnet_greedy_global(pol.weights, p ? ob : oa), pol.eps_threshold, seed, gid, step, stream_id);
                 else a = explore(follower_action(p ? ob : oa, pol.follower_tol), pol.eps_threshold, seed, gid, step, stream_id);
             }
             if (p) act_b = a; else act_a = a;

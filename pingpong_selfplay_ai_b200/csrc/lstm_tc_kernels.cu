@@ -554,6 +554,9 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
                         a = explore(argmax3(q), pol.eps_threshold, seed, gid, step, stream_id);   // (h, c) advance even when exploring
                     } else if (pol.kind == PP_POLICY_RANDOM) {
                         a = random_action(seed, gid, step, stream_id);
+                    } else if (pol.kind == PP_POLICY_QNET) {                   // fp32 on the CUDA cores of the env's own thread
+                        if (half == 0 && gw < my_warps)
+                            a = explore(qnet_greedy_global(pol.weights, p ? ob : oa), pol.eps_threshold, seed, gid, step, stream_id);
                     } else {
                         a = explore(follower_action(p ? ob : oa, pol.follower_tol), pol.eps_threshold, seed, gid, step, stream_id);
                     }

@@ -73,6 +73,15 @@ __device__ __forceinline__ int argmax3(const float (&q)[3]) {     // first maxim
     return best;
 }
 
+// Greedy QNet action with the blob read straight from GLOBAL memory (all lanes read the same words: broadcast
+// loads that hit L1).  Used where a QNet meets a recurrent player (tests/arena.py pairings QNet x QNetRNN): the
+// recurrent player's tiles own the shared memory there.  Same fmaf chain as above, so the same bits.
+static __device__ __noinline__ int qnet_greedy_global(const float *__restrict__ blob, const float (&obs)[7]) {
+    float q[3];
+    qnet_forward(blob, obs, q);
+    return argmax3(q);
+}
+
 // HardcodedBallFollower                                                      tests/arena.py:211-217
 __device__ __forceinline__ int follower_action(const float (&obs)[7], float tol) {
     const float lo = __fsub_rn(obs[4], tol), hi = __fadd_rn(obs[4], tol);

@@ -289,7 +289,10 @@ def _rnn_teacher_forced_check(cfg, n, K, pol_kinds, mode="f64", quota=0, prec="f
     env = pp.VecPongEnv2P(n, mode=mode, serve=pool, **cfg)
     env.reset()
     b = gu.oracle_batch_like(env, mode)
-    mk = {"rnn_a": lambda: pp.Policy.qnetrnn(net_a, num_envs=n, precision=prec),
+    torch.manual_seed(13); net_q = pp.QNet()
+    wq = po.qnet_weights_from_state_dict(net_q.state_dict())
+    mk = {"qnet": lambda: pp.Policy.qnet(net_q, precision=prec),
+          "rnn_a": lambda: pp.Policy.qnetrnn(net_a, num_envs=n, precision=prec),
           "rnn_b": lambda: pp.Policy.qnetrnn(net_b, num_envs=n, precision=prec),
           "follower": lambda: pp.Policy.follower(), "random": lambda: pp.Policy.random()}
     pa, pb = mk[pol_kinds[0]](), mk[pol_kinds[1]]()
@@ -308,6 +311,9 @@ def _rnn_teacher_forced_check(cfg, n, K, pol_kinds, mode="f64", quota=0, prec="f
         oa, ob = po.observe(b)
         live = ~((quota > 0) & (b.ep_idx >= quota)) if quota else np.ones(n, bool)
         for side, (kind, obs) in enumerate(zip(pol_kinds, (oa, ob))):
+            if kind == "qnet":                                   # fp32 fmaf chain on the CUDA cores: the oracle's bits
+                _, a = po.qnet_forward(wq, obs)
+                assert np.array_equal(acts[t, live, side], a[live]), (t, side)
             if kind not in wts:
                 continue
             h, c = hc[kind]
@@ -334,6 +340,14 @@ def _rnn_teacher_forced_check(cfg, n, K, pol_kinds, mode="f64", quota=0, prec="f
 @pytest.mark.parametrize("kinds", [("rnn_a", "rnn_b"), ("follower", "rnn_b"), ("rnn_a", "random")])
 def test_selfplay_qnetrnn_rollout_teacher_forced(H, kinds):
     _rnn_teacher_forced_check(H["env_config_rnn_yaml"], 200, 70, kinds)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f16"])
+@pytest.mark.parametrize("kinds", [("qnet", "rnn_b"), ("rnn_a", "qnet")])
+def test_selfplay_qnet_meets_qnetrnn(H, kinds, prec):
+    """tests/arena.py pairs QNet and QNetRNN agents: the QNet side runs in fp32 inside the recurrent kernel (both the
+    CUDA-core and the tensor-core one) and picks exactly the oracle's actions."""
+    _rnn_teacher_forced_check(H["env_config_yaml"], 230, 50, kinds, prec=prec)
 
 
 def test_selfplay_qnetrnn_quota_and_f32_mode(H):
