@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 3
+#define PP_ABI_VERSION 4
 
 enum { PP_MODE_F64 = 0, PP_MODE_F32 = 1 };
 
@@ -174,7 +174,13 @@ typedef struct PPRolloutOut {
  * 62 bytes per row over five arrays; *head is a monotonically increasing write cursor (slot = cursor %
  * capacity).  A call that pushes more rows than `capacity` writes only the rows that sequential pushes
  * would leave in the ring (the last `capacity` rows of pp_replay_scatter, the last capacity / n lock-step
- * steps of pp_selfplay_rollout, which needs capacity >= n); *head counts written rows. */
+ * steps of pp_selfplay_rollout, which needs capacity >= n); *head counts written rows.
+ *
+ * Lock-step layout (lockstep_envs = n > 0, capacity % n == 0; pp_selfplay_rollout only): the row of env i at
+ * lock-step step t of the launch goes to slot ((lockstep_step0 + t) % (capacity / n)) * n + i, i.e. the ring is a
+ * [capacity / n][n] array in time order per env — what episode-SEQUENCE replay needs (SequenceReplayBuffer,
+ * scripts/train_rnn_iterative.py:100-171).  The caller keeps lockstep_step0 (steps written so far); *head is not
+ * touched by the kernel in this layout.  Envs frozen by a quota write nothing. */
 typedef struct PPReplayRing {
     float *obs;                 /* [capacity][7] */
     uint8_t *act;               /* [capacity]    */
@@ -183,6 +189,8 @@ typedef struct PPReplayRing {
     uint8_t *done;              /* [capacity]    */
     int64_t capacity;
     unsigned long long *head;
+    int64_t lockstep_envs;      /* 0 = append layout (compacted rows, cursor *head)           */
+    int64_t lockstep_step0;     /* lock-step layout: steps written before this launch          */
 } PPReplayRing;
 
 int pp_version(void);

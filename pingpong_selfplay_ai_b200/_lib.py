@@ -13,7 +13,7 @@ from . import build as _build
 
 c_i32, c_i64, c_u64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_void_p
 
-PP_ABI_VERSION = 3
+PP_ABI_VERSION = 4
 MODE_F64, MODE_F32 = 0, 1
 SERVE_POOL, SERVE_PHILOX, SERVE_QUEUE = 0, 1, 2
 POLICY_QNET, POLICY_QNETRNN, POLICY_FOLLOWER, POLICY_RANDOM = 0, 1, 2, 3
@@ -59,7 +59,7 @@ class PPRolloutOut(C.Structure):
 
 class PPReplayRing(C.Structure):
     _fields_ = [("obs", c_vp), ("act", c_vp), ("rew", c_vp), ("next_obs", c_vp), ("done", c_vp),
-                ("capacity", c_i64), ("head", c_vp)]
+                ("capacity", c_i64), ("head", c_vp), ("lockstep_envs", c_i64), ("lockstep_step0", c_i64)]
 
 
 P = C.POINTER

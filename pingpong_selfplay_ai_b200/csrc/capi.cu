@@ -166,6 +166,9 @@ int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, 
         return fail(PP_E_MODE, "pp_selfplay_rollout");                 // both QNet players on the same path
     if (ring && !ring_ok(ring)) return fail(PP_E_NULL, "pp_selfplay_rollout");
     if (ring && ring->capacity < n) return fail(PP_E_SIZE, "pp_selfplay_rollout");     // one lock-step step must fit
+    if (ring && ring->lockstep_envs != 0 &&
+        (ring->lockstep_envs != n || ring->capacity % n != 0 || ring->lockstep_step0 < 0))
+        return fail(PP_E_SIZE, "pp_selfplay_rollout");                 // [capacity / n][n] layout of exactly this slab
     if (serve->kind == PP_SERVE_QUEUE && (int64_t)quota != serve->queue_total) return fail(PP_E_SIZE, "pp_selfplay_rollout");
     if (n == 0 || k == 0) return 0;
     if (rnn_tc)
@@ -185,6 +188,7 @@ int pp_replay_scatter(int64_t n, const PPReplayRing *ring, const float *obs, con
                       const float *next_obs, const uint8_t *done, const uint8_t *valid, void *stream) {
     if (n < 0) return fail(PP_E_SIZE, "pp_replay_scatter");
     if (!ring_ok(ring) || !obs || !act || !rew || !next_obs || !done) return fail(PP_E_NULL, "pp_replay_scatter");
+    if (ring->lockstep_envs != 0) return fail(PP_E_MODE, "pp_replay_scatter");       // appends have no (step, env) address
     if (n == 0) return 0;
     return ok_or(pp::replay_scatter_launch(n, *ring, obs, act, rew, next_obs, done, valid, (cudaStream_t)stream),
                  "pp_replay_scatter");

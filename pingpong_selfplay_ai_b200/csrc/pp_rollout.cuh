@@ -34,7 +34,19 @@ __device__ __forceinline__ void step_and_book(const EnvConsts<R> &c, Lane<R> &L,
         if (out.actions_out)
             reinterpret_cast<uchar2 *>(out.actions_out)[t * n + i] = make_uchar2((unsigned char)act_a, (unsigned char)act_b);
     }
-    if (ring_on) {       // memory.push((oB, aB, rB, nB, done)) scripts/train_iterative.py:243, rows compacted per warp
+    if (ring_on && ring.lockstep_envs) {   // memory.push_step scripts/train_rnn_iterative.py:764: [time][env] layout
+        if (active) {
+            const int64_t steps = ring.capacity / ring.lockstep_envs;
+            const int64_t slot = ((ring.lockstep_step0 + t) % steps) * ring.lockstep_envs + i;
+            float na[7], nb[7];
+            observe<R>(L.e, na, nb);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { ring.obs[slot * 7 + k] = ob[k]; ring.next_obs[slot * 7 + k] = nb[k]; }
+            ring.act[slot] = (uint8_t)act_b;
+            ring.rew[slot] = (flags & F_POINT_B) ? 1.0f : ((flags & F_POINT_A) ? -1.0f : 0.0f);
+            ring.done[slot] = (uint8_t)(flags & F_DONE);
+        }
+    } else if (ring_on) {   // memory.push((oB, aB, rB, nB, done)) scripts/train_iterative.py:243, rows compacted per warp
         const unsigned m = __ballot_sync(0xffffffffu, active);
         if (m) {
             unsigned long long base = 0;

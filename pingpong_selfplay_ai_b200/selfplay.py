@@ -25,9 +25,15 @@ class ReplayRing:
     """Device replay ring of player B's transitions (oB, aB, rB, nB, done): 62 bytes per row over five arrays
     (scripts/train_iterative.py:49-63,243).  `head` counts every row ever written; slot = head % capacity."""
 
-    def __init__(self, capacity: int, device="cuda"):
+    def __init__(self, capacity: int, device="cuda", lockstep_envs: int = 0):
+        """lockstep_envs = n: the [capacity / n][n] time-major layout that sequence replay needs (row of env i at
+        lock-step step t -> slot (t % (capacity / n)) * n + i); 0: compacted appends."""
         dev = torch.device(device)
         self.capacity = int(capacity)
+        self.lockstep_envs = int(lockstep_envs)
+        self.steps_written = 0                          # lock-step layout: the host keeps the time cursor
+        if self.lockstep_envs and self.capacity % self.lockstep_envs:
+            raise ValueError("lock-step layout: capacity must be a multiple of the number of envs")
         self.obs = torch.zeros(capacity, 7, dtype=torch.float32, device=dev)
         self.act = torch.zeros(capacity, dtype=torch.uint8, device=dev)
         self.rew = torch.zeros(capacity, dtype=torch.float32, device=dev)
@@ -37,7 +43,12 @@ class ReplayRing:
 
     def struct(self) -> _lib.PPReplayRing:
         return _lib.PPReplayRing(_ptr(self.obs), _ptr(self.act), _ptr(self.rew), _ptr(self.next_obs), _ptr(self.done),
-                                 self.capacity, _ptr(self.head))
+                                 self.capacity, _ptr(self.head), self.lockstep_envs, self.steps_written)
+
+    def note_lockstep_launch(self, n: int, k: int):
+        """Lock-step layout: the kernel leaves the cursors to the host — advance them by the k steps just launched."""
+        self.steps_written += int(k)
+        self.head += int(n) * min(int(k), self.capacity // int(n))      # rows written (stream-ordered after the launch)
 
     def __len__(self):
         return min(int(self.head.item()), self.capacity)
@@ -108,6 +119,8 @@ class SelfPlayEngine:
                 C.byref(rs) if rs is not None else None, _stream_ptr(env.device)), "pp_selfplay_rollout")
         self.step_base += int(k)
         env._served_once = True
+        if ring is not None and ring.lockstep_envs:
+            ring.note_lockstep_launch(env.n, k)
         return bufs
 
     def _deterministic_players(self) -> bool:

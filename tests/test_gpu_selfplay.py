@@ -191,6 +191,79 @@ def test_selfplay_ring_smaller_than_launch_keeps_last_steps(H, nets):
         pp.SelfPlayEngine(env, ga, gb).run(2, ring=pp.ReplayRing(n - 1))
 
 
+def test_selfplay_lockstep_ring_is_time_major_per_env_and_wraps(H, nets):
+    """ReplayRing(lockstep_envs=n): the row of env i at lock-step step t sits at slot (t % T) * n + i — the oracle's
+    step-major replay order — over several launches and across the wrap; the host keeps the cursors."""
+    cfg = H["env_config_yaml"]
+    n, T = 300, 64
+    pool = gu.make_pool(4, n, 8, cfg, "f64")
+    env = pp.VecPongEnv2P(n, mode="f64", serve=pool, **cfg)
+    env.reset()
+    b = gu.oracle_batch_like(env, "f64")
+    ga, oa = _mk(("qnet", "seed1", 0.0), nets, 0)
+    gb, ob = _mk(("qnet", "seed0", 0.2), nets, 1)
+    ring = pp.ReplayRing(n * T, lockstep_envs=n)
+    eng = pp.SelfPlayEngine(env, ga, gb, seed=5)
+    for k in (40, 25, 35):
+        eng.run(k, ring=ring)
+    K = 100
+    assert ring.steps_written == K and int(ring.head.item()) == n * K
+    w = po.selfplay(po.make_params(cfg), b, oa, ob, K, pool, seed=5, replay_cap=n * K)["replay"]
+    for t in range(K - T, K):
+        lo, slot = t * n, (t % T) * n
+        assert np.array_equal(gu.np_of(ring.obs[slot:slot + n]), w["obs"][lo:lo + n]), t
+        assert np.array_equal(gu.np_of(ring.next_obs[slot:slot + n]), w["next"][lo:lo + n])
+        assert np.array_equal(gu.np_of(ring.act[slot:slot + n]), w["act"][lo:lo + n])
+        assert np.array_equal(gu.np_of(ring.rew[slot:slot + n]), w["rew"][lo:lo + n])
+        assert np.array_equal(gu.np_of(ring.done[slot:slot + n]), w["done"][lo:lo + n])
+    with pytest.raises(pp.PongB200Error):                                       # the layout belongs to one slab size
+        eng.run(2, ring=pp.ReplayRing(n * 2 * T, lockstep_envs=2 * n))
+    with pytest.raises(pp.PongB200Error):                                       # appends have no (step, env) address
+        ring.scatter(torch.zeros(4, 7), torch.zeros(4), torch.zeros(4), torch.zeros(4, 7), torch.zeros(4))
+
+
+@pytest.mark.parametrize("prec,opp", [("f32", "rnn"), ("f16", "rnn"), ("f16", "qnet")])
+def test_train_rnn_generation_sequence_replay_and_drqn_updates(H, prec, opp):
+    """DRQN training mode on one slab (scripts/train_rnn_iterative.py:728-800): the recurrent kernel writes the lock-step
+    ring, windows of 8 steps are drawn on the device, all 175 k parameters train, epsilon decays."""
+    from pingpong_selfplay_ai_b200.train_rnn import DRQNTrainer, SequenceSampler, train_rnn_generation
+    cfg = H["env_config_rnn_yaml"]
+    n, steps, T = 1024, 96, 128
+    torch.manual_seed(21); net_b = pp.QNetRNN()
+    if opp == "rnn":
+        torch.manual_seed(20)
+        pa = pp.Policy.qnetrnn(pp.QNetRNN(), num_envs=n, precision=prec)
+    else:
+        torch.manual_seed(20)
+        pa = pp.Policy.qnet(pp.QNet(), precision=prec)
+    before = {k: v.clone() for k, v in net_b.state_dict().items()}
+    env = pp.VecPongEnv2P(n, mode="f64", serve="philox", seed=6, **cfg)
+    env.reset()
+    trainer = DRQNTrainer(net_b, batch_size=64, target_update_interval=6, lr=1e-3)
+    eng = pp.SelfPlayEngine(env, pa, pp.Policy.qnetrnn(trainer.model, num_envs=n, noisy=True, eps=1.0, precision=prec), seed=3)
+    ring = pp.ReplayRing(n * T, lockstep_envs=n)
+    sampler = SequenceSampler(ring, trace_length=8)
+    out = train_rnn_generation(eng, trainer, ring, sampler, steps, chunk=16, updates_per_chunk=2, epsilon=1.0,
+                               epsilon_decay=0.9, min_epsilon=0.05, precision=prec)
+    assert out["env_steps"] == n * steps and ring.steps_written == steps and int(ring.head.item()) == n * steps
+    assert out["stored_episodes"] > n // 2 and out["updates"] >= 8 and trainer.train_steps == out["updates"]
+    assert out["mean_loss"] > 0 and np.isfinite(out["mean_loss"]) and 0.05 <= out["epsilon"] < 1.0
+    after = trainer.model.state_dict()
+    moved = [k for k in before if not k.endswith("epsilon") and not torch.equal(before[k].to(after[k].device), after[k])]
+    assert {"features_extractor.0.weight", "lstm.weight_hh_l0", "fc_A.weight_mu", "fc_V.bias_sigma"} <= set(moved)
+    # the ring is one time-ordered column per env: B's next observation is its observation one step later, except
+    # across an episode end (terminal obs vs the new serve)
+    obs = gu.np_of(ring.obs).reshape(T, n, 7)[:steps]
+    nxt = gu.np_of(ring.next_obs).reshape(T, n, 7)[:steps]
+    done = gu.np_of(ring.done).reshape(T, n)[:steps] != 0
+    same = np.all(nxt[:-1] == obs[1:], axis=2)
+    assert np.all(same[~done[:-1]]) and done.sum() == out["episodes"]
+    assert not np.any(same[done[:-1]])
+    rows = gu.np_of(sampler.sample_rows(512))
+    t, i = rows // n, rows % n
+    assert np.all(np.diff(t, axis=1) == 1) and np.all(i == i[:, :1]) and not done[t[:, :-1], i[:, :-1]].any()
+
+
 # ------------------------------------------------------------------------------------------ tensor-core path
 @pytest.mark.parametrize("mode", ["f64", "f32"])
 @pytest.mark.parametrize("n", [1000, 5000])
