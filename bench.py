@@ -254,9 +254,10 @@ def main():
     ap.add_argument("--precision", default="f16", choices=["f32", "f16"],
                     help="QNet path: f16 = tcgen05 tensor cores (fp16 hi/lo operands, fp32 accumulate, ~1e-6 of fp32); "
                          "f32 = CUDA-core fmaf chain, bit-identical to the oracle")
-    ap.add_argument("--workload", default="qnet", choices=["qnet", "rnn", "train"],
+    ap.add_argument("--workload", default="qnet", choices=["qnet", "rnn", "train", "train_rnn"],
                     help="qnet = configs[2] (the headline); rnn = configs[3] shape: QNetRNN A vs B with per-env (h, c); "
-                         "train = configs[4] shape: epsilon-greedy rollout + replay scatter + PER Double-DQN updates + grad all-reduce")
+                         "train = configs[4] shape: epsilon-greedy rollout + replay scatter + PER Double-DQN updates + grad all-reduce; "
+                         "train_rnn = DRQN training mode: recurrent rollout + lock-step ring + sequence updates")
     ap.add_argument("--ref-steps", type=int, default=1500, help="reference arm: env-steps per process per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -305,6 +306,9 @@ def main():
 
     if args.workload == "train":
         run_train_workload(pp, ppd, args, env, net_a, net_b, dev, rank, world)
+        return
+    if args.workload == "train_rnn":
+        run_train_rnn_workload(pp, ppd, args, env, dev, rank, world)
         return
     for _ in range(args.warmup):
         eng.run(k)
@@ -396,6 +400,43 @@ def run_train_workload(pp, ppd, args, env, net_a, net_b, dev, rank, world):
                           "config": {"workload": "configs[4] shape: train generation chunk loop", "envs_per_gpu": n,
                                      "lockstep_steps_per_chunk": k, "updates_per_chunk": 4, "batch_per_rank": 256,
                                      "replay_capacity": ring.capacity, "qnet_precision": args.precision}}), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def run_train_rnn_workload(pp, ppd, args, env, dev, rank, world):
+    """DRQN training mode per GPU (scripts/train_rnn_iterative.py:728-800 shape): recurrent B learns against recurrent A;
+    one bench step = one chunk of `--lockstep` steps written to the lock-step ring + 4 sequence updates of batch 64 per
+    rank (trace length 8, all 175 k parameters, gradient all-reduce).  Prints its own JSON line (not the headline)."""
+    from pingpong_selfplay_ai_b200.train_rnn import DRQNTrainer, SequenceSampler, train_rnn_generation
+    n, k = args.envs, args.lockstep
+    torch.manual_seed(0); net_a = pp.QNetRNN()
+    torch.manual_seed(1); net_b = pp.QNetRNN()
+    trainer = DRQNTrainer(net_b, batch_size=64, device=dev)
+    eng = pp.SelfPlayEngine(env, pp.Policy.qnetrnn(net_a, num_envs=n, precision=args.precision, device=dev),
+                            pp.Policy.qnetrnn(trainer.model, num_envs=n, noisy=True, eps=0.5, precision=args.precision, device=dev), seed=7)
+    steps_in_ring = max(64, k)
+    ring = pp.ReplayRing(n * steps_in_ring, device=dev, lockstep_envs=n)
+    sampler = SequenceSampler(ring, trace_length=8)
+    kw = dict(chunk=k, updates_per_chunk=4, epsilon=0.5, precision=args.precision)
+    train_rnn_generation(eng, trainer, ring, sampler, k * args.warmup, **kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    out = train_rnn_generation(eng, trainer, ring, sampler, k * args.steps, **kw)
+    torch.cuda.synchronize()
+    wall = ppd.max_over_ranks(time.perf_counter() - t0, dev)
+    if rank == 0:
+        print(json.dumps({"metric": "DRQN training-mode env-steps/sec (recurrent rollout + sequence replay + updates)",
+                          "value": out["env_steps"] / wall, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * wall / args.steps, "updates_per_s": out["updates"] / wall,
+                          "mean_loss": out["mean_loss"], "epsilon": out["epsilon"], "stored_episodes": out["stored_episodes"],
+                          "config": {"workload": "DRQN train generation chunk loop (config_rnn.yaml training block shape)",
+                                     "envs_per_gpu": n, "lockstep_steps_per_chunk": k, "updates_per_chunk": 4,
+                                     "batch_per_rank": 64, "trace_length": 8, "ring_steps": steps_in_ring,
+                                     "qnet_precision": args.precision}}), flush=True)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -21,6 +21,7 @@ How the reference's sequential schedule maps to n lock-step envs (SURVEY.md sect
 from __future__ import annotations
 
 import copy
+import os
 
 import torch
 
@@ -109,8 +110,9 @@ class DQNTrainer:
         self.beta_start, self.beta_frames = beta_start, beta_frames
         self.frame_idx = self.train_steps = 0
 
-    def _body(self, sampler: PrioritizedSampler, beta, generator=None):
-        """train_step() on the device; `beta` is a float or a 0-d device tensor.  No host synchronisation."""
+    def _pre(self, sampler: PrioritizedSampler, beta, generator=None):
+        """train_step() up to loss.backward(): local gradients are in p.grad afterwards.  `beta` is a float or a 0-d
+        device tensor.  No host synchronisation."""
         ring = sampler.ring
         idx, iw = sampler.sample(self.batch_size, beta, generator)
         self.model.reset_noise()                                                       # :142-143
@@ -127,14 +129,23 @@ class DQNTrainer:
         loss = (iw * td.pow(2)).mean()                                                 # :158
         self.opt.zero_grad(set_to_none=False)
         loss.backward()
-        ppd.allreduce_mean_grads(self.head_params)                                     # one NCCL all-reduce of 520 floats
-        self.opt.step()
-        sampler.update_priorities(idx, td)                                             # :163-164
+        self._idx, self._td = idx, td.detach()
         return loss.detach()
+
+    def _post(self, sampler: PrioritizedSampler):
+        """The rest of train_step(): optimiser step on the (rank-averaged) gradients, new priorities."""
+        self.opt.step()
+        sampler.update_priorities(self._idx, self._td)                                 # :163-164
+
+    def _body(self, sampler, beta, generator=None):
+        loss = self._pre(sampler, beta, generator)
+        ppd.allreduce_mean_grads(self.head_params)                                     # one NCCL all-reduce of 520 floats
+        self._post(sampler)
+        return loss
 
     def update(self, sampler: PrioritizedSampler, generator=None):
         """One train_step().  Returns the loss (a 0-d device tensor: no host sync), or None while the ring holds fewer
-        than batch_size rows (:134-135).  On CUDA the update is captured into a CUDA graph after three eager calls
+        than batch_size rows (:134-135).  On CUDA the update is captured into CUDA graphs after three eager calls
         (~150 tiny kernels per update are otherwise bound by launch overhead, 2.7 ms of host time each)."""
         if len(sampler) < self.batch_size:
             return None
@@ -149,7 +160,10 @@ class DQNTrainer:
             self.target.load_state_dict(self.model.state_dict())
         return loss
 
-    def _graphed(self, sampler: PrioritizedSampler, beta: float):
+    def _graphed(self, sampler, beta: float):
+        """Replay of the captured update.  One graph on a single GPU.  With several ranks the gradient all-reduce stays
+        OUT of the graphs (NCCL's watchdog thread and stream capture do not mix): graph 1 = sample + forward + backward,
+        eager NCCL all-reduce of the static gradient tensors, graph 2 = optimiser step + priorities."""
         if self._graph is None:
             if self._eager_runs < 3:                      # the first updates run eagerly: they ARE the warm-up
                 self._eager_runs += 1
@@ -157,15 +171,24 @@ class DQNTrainer:
             self._beta_t = torch.zeros((), dtype=torch.float32, device=self.device)
             self._beta_t.fill_(beta)
             self._graph_sampler = sampler
+            self._split = ppd.is_parallel() or os.environ.get("PP_SPLIT_UPDATE_GRAPH") == "1"      # the env var: tests
             torch.cuda.synchronize(self.device)
+            pool = torch.cuda.graph_pool_handle()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._loss_t = self._body(sampler, self._beta_t)
+            with torch.cuda.graph(graph, pool=pool):
+                self._loss_t = self._pre(sampler, self._beta_t) if self._split else self._body(sampler, self._beta_t)
+            if self._split:
+                self._graph_post = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph_post, pool=pool):
+                    self._post(sampler)
             self._graph = graph                           # capture records without running: replay below IS this update
         if sampler is not self._graph_sampler:
             raise RuntimeError("the captured update is bound to the sampler (ring) it was built with")
         self._beta_t.fill_(beta)
         self._graph.replay()
+        if self._split:
+            ppd.allreduce_mean_grads(self.head_params)
+            self._graph_post.replay()
         return self._loss_t.clone()
 
 

@@ -151,14 +151,21 @@ class DRQNTrainer(DQNTrainer):
             targets = rew[:, -1] + self.gamma * nq * (~done[:, -1])                      # :505
         return F.smooth_l1_loss(q, targets)                                              # :509
 
-    def _body(self, sampler: SequenceSampler, beta=None, generator=None):
+    def _pre(self, sampler: SequenceSampler, beta=None, generator=None):
         loss = self.loss_on(*sampler.sample(self.batch_size, generator))
         self.opt.zero_grad(set_to_none=False)
         loss.backward()
-        ppd.allreduce_mean_grads(self.params)                                            # one NCCL all-reduce of 175 k floats
+        return loss.detach()
+
+    def _post(self, sampler: SequenceSampler):
         torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip_norm)        # :516
         self.opt.step()
-        return loss.detach()
+
+    def _body(self, sampler, beta=None, generator=None):
+        loss = self._pre(sampler, beta, generator)
+        ppd.allreduce_mean_grads(self.params)                                            # one NCCL all-reduce of 175 k floats
+        self._post(sampler)
+        return loss
 
     def update(self, sampler: SequenceSampler, generator=None):
         """One train_step_rnn().  None while fewer than batch_size episodes are stored (:404-407)."""
