@@ -254,10 +254,11 @@ def main():
     ap.add_argument("--precision", default="f16", choices=["f32", "f16"],
                     help="QNet path: f16 = tcgen05 tensor cores (fp16 hi/lo operands, fp32 accumulate, ~1e-6 of fp32); "
                          "f32 = CUDA-core fmaf chain, bit-identical to the oracle")
-    ap.add_argument("--workload", default="qnet", choices=["qnet", "rnn", "train", "train_rnn"],
+    ap.add_argument("--workload", default="qnet", choices=["qnet", "rnn", "train", "train_rnn", "arena"],
                     help="qnet = configs[2] (the headline); rnn = configs[3] shape: QNetRNN A vs B with per-env (h, c); "
                          "train = configs[4] shape: epsilon-greedy rollout + replay scatter + PER Double-DQN updates + grad all-reduce; "
-                         "train_rnn = DRQN training mode: recurrent rollout + lock-step ring + sequence updates")
+                         "train_rnn = DRQN training mode: recurrent rollout + lock-step ring + sequence updates; "
+                         "arena = a tests/arena.py-shaped round robin (10 agents, 100 games per pairing) on the batched engine")
     ap.add_argument("--ref-steps", type=int, default=1500, help="reference arm: env-steps per process per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -272,6 +273,9 @@ def main():
         run_reference(args, rank)
         return
 
+    if args.workload == "arena":
+        run_arena_workload(args)
+        return
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # before CUDA is touched: the workers are forked
         cpu_baseline = measure_cpu_baseline()
@@ -403,6 +407,77 @@ def run_train_workload(pp, ppd, args, env, net_a, net_b, dev, rank, world):
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+def _port_arena_games(games: int) -> tuple[int, float]:
+    """The match loop of tests/arena.py:294-308 for one QNetRNN x QNetRNN pairing on the CPU port (pure-Python env +
+    torch batch-1 recurrent forwards) — what the reference spends per game.  -> (env-steps, seconds)."""
+    import random
+
+    from oracle import pong_port
+    from oracle.policy_torch import QNetRNNPort
+    torch.set_num_threads(1)
+    random.seed(1)
+    torch.manual_seed(0); net_a = QNetRNNPort().eval()
+    torch.manual_seed(1); net_b = QNetRNNPort().eval()
+    env = pong_port.PongPort(**ENV_CFG)
+    steps, t0 = 0, time.perf_counter()
+    with torch.no_grad():
+        for _ in range(games):
+            oa, ob = env.reset()
+            ha, hb, done = net_a.init_hidden(1, "cpu"), net_b.init_hidden(1, "cpu"), False
+            while not done:
+                qa, ha = net_a(torch.tensor(oa, dtype=torch.float32).unsqueeze(0).unsqueeze(0), ha)
+                qb, hb = net_b(torch.tensor(ob, dtype=torch.float32).unsqueeze(0).unsqueeze(0), hb)
+                (oa, ob), _, done, _ = env.step(int(qa.argmax(1).item()), int(qb.argmax(1).item()))
+                steps += 1
+    return steps, time.perf_counter() - t0
+
+
+def run_arena_workload(args):
+    """A tests/arena.py-shaped tournament (ARENA_CONFIG: 2 QNet + 7 QNetRNN + the ball follower, 100 games per pairing,
+    45 pairings) on the batched engine, one launch per pairing, pairings overlapped on CUDA streams.  One bench step = one
+    whole tournament incl. the host logic (database records, result read-back).  Prints its own JSON line."""
+    cpu = None
+    if not args.no_cpu_baseline:
+        st, sec = _port_arena_games(300)
+        cpu = {"games_per_s": 300 / sec, "env_steps_per_s": st / sec, "cores": 1, "kind": "port",
+               "sample": "300 QNetRNN x QNetRNN games, reference-shaped match loop (tests/arena.py:294-308), one process"}
+    import pingpong_selfplay_ai_b200 as pp
+    from pingpong_selfplay_ai_b200 import arena, checkpoint as ck
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    models, agents = [], {}
+    for k in range(10):
+        torch.manual_seed(k)
+        typ = "QNet" if k < 2 else ("QNetRNN" if k < 9 else "HardcodedBallFollower")
+        net = pp.QNet() if typ == "QNet" else (pp.QNetRNN() if typ == "QNetRNN" else None)
+        info = {"id": f"agent{k}", "type": typ, "path": "random-init"}
+        models.append(info)
+        agents[info["id"]] = ck.Agent(info, net.eval() if net is not None else None)
+    games = 100
+
+    def tournament(seed):
+        db = {"models": list(models), "match_history": []}
+        plan = arena.create_match_plan(db, games)
+        res = arena.run_tournament(ENV_CFG, db, None, plan, agents=agents, seed=seed, precision=args.precision, concurrent=8)
+        return len(db["match_history"]), int(sum(int(r[2].sum()) for r in res.values()))
+    for w in range(max(args.warmup, 1)):
+        tournament(1000 * w)
+    torch.cuda.synchronize()
+    reps = max(1, min(args.steps, 20))
+    t0, n_games, n_steps = time.perf_counter(), 0, 0
+    for r in range(reps):
+        g, st = tournament(77 + 1000 * r)
+        n_games += g; n_steps += st
+    wall = time.perf_counter() - t0
+    print(json.dumps({"metric": "arena round robin games/sec (45 pairings x 100 games, host logic included)",
+                      "value": n_games / wall, "unit": "games/s", "env_steps_per_s": n_steps / wall, "n_gpus": 1,
+                      "steps": reps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * wall / reps, "higher_is_better": True,
+                      "config": {"workload": "tests/arena.py ARENA_CONFIG shape: 2 QNet + 7 QNetRNN + ball follower, random init",
+                                 "pairings": 45, "games_per_pairing": games, "qnet_precision": args.precision,
+                                 "concurrent_pairings": 8},
+                      "cpu_baseline": cpu}), flush=True)
 
 
 def run_train_rnn_workload(pp, ppd, args, env, dev, rank, world):
