@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 4
+#define PP_ABI_VERSION 5
 
 enum { PP_MODE_F64 = 0, PP_MODE_F32 = 1 };
 
@@ -193,6 +193,16 @@ typedef struct PPReplayRing {
     int64_t lockstep_step0;     /* lock-step layout: steps written before this launch          */
 } PPReplayRing;
 
+/* One NoisyLinear layer (models/qnet.py:6-50): device tensors in torch's layout.  The grad_* pointers are written by
+ * pp_dqn_head_grads (each may be NULL) and ignored elsewhere. */
+typedef struct PPNoisyLayer {
+    int32_t in_features, out_features;
+    float *weight_mu, *weight_sigma, *weight_epsilon;       /* [out][in] */
+    float *bias_mu, *bias_sigma, *bias_epsilon;             /* [out]     */
+    float *grad_weight_mu, *grad_weight_sigma;              /* [out][in] */
+    float *grad_bias_mu, *grad_bias_sigma;                  /* [out]     */
+} PPNoisyLayer;
+
 int pp_version(void);
 const char *pp_last_error(void);
 
@@ -258,6 +268,36 @@ int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *pa
                           const float *host_weights_a, const float *host_weights_b, int32_t precision,
                           int64_t chunk, int64_t max_steps,
                           unsigned long long *host_counters, int32_t *host_ep_log, int64_t ep_log_cap);
+
+/* ---- training mode (scripts/train_iterative.py): three small launches per update instead of ~130 framework kernels */
+
+/* NoisyLinear.reset_noise (models/qnet.py:33-41) for `count` <= 8 layers in one launch: e = sign(g) sqrt|g| with
+ * g ~ N(0, 1) (Philox keyed by seed, *counter, layer, index; Box-Muller), weight_epsilon = outer(e_out, e_in),
+ * bias_epsilon = e_out.  *counter (device memory) is read and incremented by the kernel, so a CUDA graph that
+ * contains the launch draws fresh noise at every replay.  in_features + out_features <= 1024 per layer. */
+int pp_noisy_reset(const PPNoisyLayer *layers, int32_t count, uint64_t seed, unsigned long long *counter, void *stream);
+
+/* The reference QNet (features.0 [64][7], features.2 [64][64], NoisyLinear fc_V [1][64] and fc_A [3][64]) in torch's
+ * layout -> the k-major PP_QNET_* blob the act / rollout kernels take.  noisy != 0: the train-mode forward
+ * mu + sigma * epsilon (models/qnet.py:44-46), else mu. */
+int pp_pack_qnet(const float *features0_weight, const float *features0_bias, const float *features2_weight,
+                 const float *features2_bias, const PPNoisyLayer *fc_v, const PPNoisyLayer *fc_a, int32_t noisy,
+                 float *blob, void *stream);
+
+/* train_step() of scripts/train_iterative.py:139-164 up to the gradients, for a sampled batch of replay rows:
+ *   q = Q(s)[a];  a* = argmax Q(s');  target = r + gamma * Q_target(s')[a*] * (1 - done);  td = q - target;
+ *   loss = mean(iw * td^2)
+ * and d loss / d {weight_mu, weight_sigma, bias_mu, bias_sigma} of the online heads fc_V / fc_A written (not
+ * accumulated) to the grad_* pointers of online_v / online_a; the feature layers (features.0 [64][7], features.2
+ * [64][64], torch layout) are frozen (:97) and shared by the online and the target net.  idx[batch] are ring slots,
+ * iw[batch] the importance weights.  td_out[batch], loss_out[1] and prios (the PER priority array indexed by ring
+ * slot, receives |td| + 1e-6, :74-76,163-164) may be NULL.  noisy_online / noisy_target select the train- or
+ * eval-mode forward of each net (the reference: online train mode, target eval mode :100). */
+int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float *iw, int32_t batch,
+                      const float *features0_weight, const float *features0_bias, const float *features2_weight,
+                      const float *features2_bias, const PPNoisyLayer *online_v, const PPNoisyLayer *online_a,
+                      const PPNoisyLayer *target_v, const PPNoisyLayer *target_a, int32_t noisy_online,
+                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios, void *stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ from . import build as _build
 
 c_i32, c_i64, c_u64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_void_p
 
-PP_ABI_VERSION = 4
+PP_ABI_VERSION = 5
 MODE_F64, MODE_F32 = 0, 1
 SERVE_POOL, SERVE_PHILOX, SERVE_QUEUE = 0, 1, 2
 POLICY_QNET, POLICY_QNETRNN, POLICY_FOLLOWER, POLICY_RANDOM = 0, 1, 2, 3
@@ -62,6 +62,13 @@ class PPReplayRing(C.Structure):
                 ("capacity", c_i64), ("head", c_vp), ("lockstep_envs", c_i64), ("lockstep_step0", c_i64)]
 
 
+class PPNoisyLayer(C.Structure):
+    _fields_ = [("in_features", c_i32), ("out_features", c_i32),
+                ("weight_mu", c_vp), ("weight_sigma", c_vp), ("weight_epsilon", c_vp),
+                ("bias_mu", c_vp), ("bias_sigma", c_vp), ("bias_epsilon", c_vp),
+                ("grad_weight_mu", c_vp), ("grad_weight_sigma", c_vp), ("grad_bias_mu", c_vp), ("grad_bias_sigma", c_vp)]
+
+
 P = C.POINTER
 _PROTOTYPES = {
     "pp_version": (C.c_int, []),
@@ -78,6 +85,10 @@ _PROTOTYPES = {
                                       c_u64, c_i64, P(PPServeSource), c_i32, c_i64, P(PPRolloutOut), P(PPReplayRing),
                                       c_vp]),
     "pp_replay_scatter": (C.c_int, [c_i64, P(PPReplayRing), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pp_noisy_reset": (C.c_int, [P(PPNoisyLayer), c_i32, c_u64, c_vp, c_vp]),
+    "pp_pack_qnet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_vp, c_vp]),
+    "pp_dqn_head_grads": (C.c_int, [P(PPReplayRing), c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, P(PPNoisyLayer), P(PPNoisyLayer),
+                                    P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "pp_host_selfplay_eval": (C.c_int, [C.c_int, c_i64, c_i32, P(PPParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                         c_i64, c_i64, c_vp, c_vp, c_i64]),
 }

@@ -195,6 +195,50 @@ int pp_replay_scatter(int64_t n, const PPReplayRing *ring, const float *obs, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Training mode.
+namespace {
+bool noisy_ok(const PPNoisyLayer *l, int in, int out) {
+    return l && l->in_features == in && l->out_features == out && l->weight_mu && l->weight_sigma && l->weight_epsilon &&
+           l->bias_mu && l->bias_sigma && l->bias_epsilon;
+}
+}  // namespace
+
+int pp_noisy_reset(const PPNoisyLayer *layers, int32_t count, uint64_t seed, unsigned long long *counter, void *stream) {
+    if (count < 0 || count > 8) return fail(PP_E_SIZE, "pp_noisy_reset");
+    if (!counter || (count > 0 && !layers)) return fail(PP_E_NULL, "pp_noisy_reset");
+    for (int i = 0; i < count; ++i) {
+        const PPNoisyLayer &l = layers[i];
+        if (l.in_features <= 0 || l.out_features <= 0 || l.in_features + l.out_features > 1024) return fail(PP_E_SIZE, "pp_noisy_reset");
+        if (!l.weight_epsilon || !l.bias_epsilon) return fail(PP_E_NULL, "pp_noisy_reset");
+    }
+    if (count == 0) return 0;
+    return ok_or(pp::noisy_reset_launch(layers, count, seed, counter, (cudaStream_t)stream), "pp_noisy_reset");
+}
+
+int pp_pack_qnet(const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer *fc_v,
+                 const PPNoisyLayer *fc_a, int32_t noisy, float *blob, void *stream) {
+    if (!w1 || !b1 || !w2 || !b2 || !blob) return fail(PP_E_NULL, "pp_pack_qnet");
+    if (!noisy_ok(fc_v, 64, 1) || !noisy_ok(fc_a, 64, 3)) return fail(PP_E_PARAM, "pp_pack_qnet");
+    return ok_or(pp::pack_qnet_launch(w1, b1, w2, b2, *fc_v, *fc_a, noisy, blob, (cudaStream_t)stream), "pp_pack_qnet");
+}
+
+int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float *iw, int32_t batch,
+                      const float *features0_weight, const float *features0_bias, const float *features2_weight,
+                      const float *features2_bias, const PPNoisyLayer *online_v, const PPNoisyLayer *online_a,
+                      const PPNoisyLayer *target_v, const PPNoisyLayer *target_a, int32_t noisy_online,
+                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios, void *stream) {
+    const char *fn = "pp_dqn_head_grads";
+    if (batch <= 0 || batch > (1 << 20)) return fail(PP_E_SIZE, fn);
+    if (!ring_ok(ring) || !idx || !iw || !features0_weight || !features0_bias || !features2_weight || !features2_bias)
+        return fail(PP_E_NULL, fn);
+    if (!noisy_ok(online_v, 64, 1) || !noisy_ok(online_a, 64, 3) || !noisy_ok(target_v, 64, 1) || !noisy_ok(target_a, 64, 3))
+        return fail(PP_E_PARAM, fn);
+    return ok_or(pp::dqn_head_grads_launch(*ring, idx, iw, batch, features0_weight, features0_bias, features2_weight,
+                                           features2_bias, *online_v, *online_a, *target_v, *target_a,
+                                           noisy_online, noisy_target, gamma, td_out, loss_out, prios, (cudaStream_t)stream), fn);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host-buffer evaluation.  Owns a small cache of device staging buffers (grown on demand, freed at
 // process exit) so repeated calls do not pay cudaMalloc; everything runs on one private stream.
 namespace {

@@ -42,4 +42,12 @@ int selfplay_rnn_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, co
 int replay_scatter_launch(int64_t n, const PPReplayRing &ring, const float *obs, const uint8_t *act, const float *rew,
                           const float *next_obs, const uint8_t *done, const uint8_t *valid, cudaStream_t stream);
 
+int dqn_head_grads_launch(const PPReplayRing &ring, const int64_t *idx, const float *iw, int32_t batch,
+                          const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &on_v, const PPNoisyLayer &on_a,
+                          const PPNoisyLayer &tg_v, const PPNoisyLayer &tg_a, int noisy_online, int noisy_target, float gamma,
+                          float *td_out, float *loss_out, float *prios, cudaStream_t stream);
+int noisy_reset_launch(const PPNoisyLayer *layers, int32_t count, uint64_t seed, unsigned long long *counter, cudaStream_t stream);
+int pack_qnet_launch(const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &v,
+                     const PPNoisyLayer &a, int noisy, float *blob, cudaStream_t stream);
+
 }  // namespace pp

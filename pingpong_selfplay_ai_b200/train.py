@@ -25,9 +25,12 @@ import os
 
 import torch
 
+import ctypes as C
+
+from . import _lib
 from . import dist as ppd
-from .policy import Policy, QNet, pack_qnet
-from .selfplay import ReplayRing, SelfPlayEngine
+from .policy import NoisyLinear, Policy, QNet, pack_qnet
+from .selfplay import ReplayRing, SelfPlayEngine, _ptr, _stream_ptr
 
 
 class PrioritizedSampler:
@@ -76,13 +79,13 @@ class PrioritizedSampler:
         whole update can be captured in a CUDA graph."""
         if self.seen == 0:
             raise RuntimeError("sampling from an empty replay ring")
-        probs = self.prios.pow(self.alpha)
-        probs = probs / probs.sum()
+        pa = self.prios.pow(self.alpha)                  # probs = pa / pa.sum() (:66-67), never materialised: two passes
         # np.random.choice(p=probs) is inverse-CDF sampling; the same here (torch.multinomial costs 1 ms at 2 M rows)
-        cdf = probs.cumsum(0)
-        u = torch.rand(batch_size, device=probs.device, generator=generator) * cdf[-1]
+        cdf = pa.cumsum(0)                               # over the ring instead of four
+        total = cdf[-1]
+        u = torch.rand(batch_size, device=pa.device, generator=generator) * total
         idx = torch.searchsorted(cdf, u, right=True).clamp_(max=self.ring.capacity - 1)
-        w = (self.size_t * probs[idx]).pow(-beta)
+        w = (self.size_t * (pa[idx] / total)).pow(-beta)
         return idx, w / w.max()
 
     def update_priorities(self, idx, td_abs):
@@ -94,7 +97,10 @@ class DQNTrainer:
 
     def __init__(self, model_b: QNet, gamma: float = 0.99, lr: float = 2.5e-4, batch_size: int = 256,
                  target_update_interval: int = 1000, beta_start: float = 0.4, beta_frames: int = 100000, device="cuda",
-                 use_graph: bool = True):
+                 use_graph: bool = True, fused: bool | None = None, seed: int = 0):
+        """fused (default: on CUDA): forward, TD error, loss and head gradients run in ONE hand-written kernel
+        (pp_dqn_head_grads), NoisyNet noise in another (pp_noisy_reset); the PyTorch formulation below is what they
+        are tested against and what runs on the CPU."""
         self.device = torch.device(device)
         self.model = model_b.to(self.device)
         for p in self.model.features.parameters():                                   # :97
@@ -109,10 +115,65 @@ class DQNTrainer:
         self.gamma, self.batch_size, self.target_update_interval = gamma, batch_size, target_update_interval
         self.beta_start, self.beta_frames = beta_start, beta_frames
         self.frame_idx = self.train_steps = 0
+        self.fused = (self.device.type == "cuda") if fused is None else bool(fused)
+        if self.fused:
+            self._init_fused(seed)
+
+    # ---- the hand-written update path (csrc/dqn_kernels.cu)
+    @staticmethod
+    def _layer(mod: NoisyLinear, grads: bool) -> _lib.PPNoisyLayer:
+        g = (lambda p: _ptr(p.grad)) if grads else (lambda p: None)
+        return _lib.PPNoisyLayer(mod.in_features, mod.out_features, _ptr(mod.weight_mu), _ptr(mod.weight_sigma),
+                                 _ptr(mod.weight_epsilon), _ptr(mod.bias_mu), _ptr(mod.bias_sigma), _ptr(mod.bias_epsilon),
+                                 g(mod.weight_mu), g(mod.weight_sigma), g(mod.bias_mu), g(mod.bias_sigma))
+
+    def _init_fused(self, seed: int):
+        self._lib = _lib.load()
+        for p in self.head_params:                       # the kernel writes the gradients Adam reads: fixed tensors
+            p.grad = torch.zeros_like(p)
+        m, t = self.model, self.target
+        self._on_v, self._on_a = self._layer(m.fc_V, True), self._layer(m.fc_A, True)
+        self._tg_v, self._tg_a = self._layer(t.fc_V, False), self._layer(t.fc_A, False)
+        self._noise_all = (_lib.PPNoisyLayer * 4)(self._on_v, self._on_a, self._tg_v, self._tg_a)
+        self._noise_model = (_lib.PPNoisyLayer * 2)(self._on_v, self._on_a)
+        self._noise_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._noise_seed = int(seed) & (2 ** 64 - 1)
+        self._td_buf = torch.zeros(self.batch_size, dtype=torch.float32, device=self.device)
+        self._loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def _feature_ptrs(self):
+        f = self.model.features                          # frozen (:97) and identical in the target net
+        return _ptr(f[0].weight), _ptr(f[0].bias), _ptr(f[2].weight), _ptr(f[2].bias)
+
+    def reset_noise_and_pack(self, blob: torch.Tensor):
+        """model.reset_noise() + pack_qnet(model, noisy=True) into `blob` (a player's weights): two launches."""
+        st = _stream_ptr(self.device)
+        m = self.model
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pp_noisy_reset(self._noise_model, 2, self._noise_seed, _ptr(self._noise_counter), st), "pp_noisy_reset")
+            _lib.check(self._lib.pp_pack_qnet(*self._feature_ptrs(), C.byref(self._on_v), C.byref(self._on_a), 1,
+                                              _ptr(blob), st), "pp_pack_qnet")
+
+    def _pre_fused(self, sampler: "PrioritizedSampler", beta, generator=None):
+        idx, iw = sampler.sample(self.batch_size, beta, generator)
+        idx, iw = idx.contiguous(), iw.to(torch.float32).contiguous()
+        ring = sampler.ring.struct()
+        st = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pp_noisy_reset(self._noise_all, 4, self._noise_seed, _ptr(self._noise_counter), st), "pp_noisy_reset")  # :142-143
+            _lib.check(self._lib.pp_dqn_head_grads(C.byref(ring), _ptr(idx), _ptr(iw), self.batch_size, *self._feature_ptrs(),
+                                                   C.byref(self._on_v), C.byref(self._on_a), C.byref(self._tg_v), C.byref(self._tg_a),
+                                                   int(self.model.training), int(self.target.training), float(self.gamma),
+                                                   _ptr(self._td_buf), _ptr(self._loss_buf), _ptr(sampler.prios), st),
+                       "pp_dqn_head_grads")
+        self._idx, self._td = idx, self._td_buf
+        return self._loss_buf[0]
 
     def _pre(self, sampler: PrioritizedSampler, beta, generator=None):
         """train_step() up to loss.backward(): local gradients are in p.grad afterwards.  `beta` is a float or a 0-d
         device tensor.  No host synchronisation."""
+        if self.fused:
+            return self._pre_fused(sampler, beta, generator)
         ring = sampler.ring
         idx, iw = sampler.sample(self.batch_size, beta, generator)
         self.model.reset_noise()                                                       # :142-143
@@ -135,7 +196,8 @@ class DQNTrainer:
     def _post(self, sampler: PrioritizedSampler):
         """The rest of train_step(): optimiser step on the (rank-averaged) gradients, new priorities."""
         self.opt.step()
-        sampler.update_priorities(self._idx, self._td)                                 # :163-164
+        if not self.fused:                                                             # the fused kernel wrote them
+            sampler.update_priorities(self._idx, self._td)                             # :163-164
 
     def _body(self, sampler, beta, generator=None):
         loss = self._pre(sampler, beta, generator)
@@ -206,8 +268,11 @@ def train_generation(engine: SelfPlayEngine, trainer: DQNTrainer, ring: ReplayRi
         engine.pb = Policy.qnet(trainer.model, noisy=True, eps=epsilon, precision=precision, device=dev)
     while done_steps < lockstep_steps:
         k = min(chunk, lockstep_steps - done_steps)
-        trainer.model.reset_noise()                                                    # B's noise: one draw per chunk
-        engine.pb.set_weights(pack_qnet(trainer.model, noisy=True))
+        if trainer.fused:                                                              # B's noise: one draw per chunk
+            trainer.reset_noise_and_pack(engine.pb.weights)
+        else:
+            trainer.model.reset_noise()
+            engine.pb.set_weights(pack_qnet(trainer.model, noisy=True))
         engine.pb.eps = epsilon
         engine.run(k, ring=ring)
         done_steps += k

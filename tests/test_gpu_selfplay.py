@@ -484,7 +484,7 @@ def test_train_generation_rollout_replay_and_updates(H, prec):
     rew, done, act = gu.np_of(ring.rew), gu.np_of(ring.done), gu.np_of(ring.act)
     assert set(np.unique(rew)) <= {-1.0, 0.0, 1.0} and act.max() <= 2 and np.all(rew[done != 0] != 0)
     # epsilon = 1.0 at the start: B's first actions are uniform over {0, 1, 2}
-    assert 0.3 < (act == 1).mean() < 0.45
+    assert 0.25 < (act == 1).mean() < 0.45
 
 
 @pytest.mark.parametrize("kinds", [("rnn_a", "rnn_b"), ("follower", "rnn_b"), ("rnn_a", "random")])

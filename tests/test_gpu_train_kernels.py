@@ -1,0 +1,173 @@
+"""GPU parity of the hand-written training-mode kernels (csrc/dqn_kernels.cu) against the PyTorch formulation of
+scripts/train_iterative.py:132-168 (fp32; tolerance 1e-5 relative, the north-star bound for fp32 work)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import pp_testutil as gu
+
+pytestmark = pytest.mark.gpu
+
+pp = gu.pp
+from pingpong_selfplay_ai_b200 import _lib  # noqa: E402
+from pingpong_selfplay_ai_b200.selfplay import _ptr, _stream_ptr  # noqa: E402
+
+
+def _ring(cap, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ring = pp.ReplayRing(cap)
+    ring.obs.copy_(torch.rand(cap, 7, generator=g, device="cuda") * 2 - 1)
+    ring.next_obs.copy_(torch.rand(cap, 7, generator=g, device="cuda") * 2 - 1)
+    ring.act.copy_(torch.randint(0, 3, (cap,), generator=g, device="cuda").to(torch.uint8))
+    ring.rew.copy_(torch.randint(-1, 2, (cap,), generator=g, device="cuda").float())
+    ring.done.copy_((torch.rand(cap, generator=g, device="cuda") < 0.2).to(torch.uint8))
+    ring.head.fill_(cap)
+    return ring
+
+
+def _torch_update(tr, ring, idx, iw):
+    """The PyTorch formulation (DQNTrainer._pre without the fused kernel) on a given batch -> (td, loss, grads)."""
+    s, ns = ring.obs[idx], ring.next_obs[idx]
+    a = ring.act[idx].to(torch.int64)
+    r, d = ring.rew[idx], ring.done[idx] != 0
+    q = tr.model(s).gather(1, a.unsqueeze(1)).squeeze(1)
+    with torch.no_grad():
+        na = tr.model(ns).argmax(1, keepdim=True)
+        nq = tr.target(ns).gather(1, na).squeeze(1)
+    td = q - (r + tr.gamma * nq * (~d))
+    loss = (iw * td.pow(2)).mean()
+    grads = torch.autograd.grad(loss, tr.head_params, allow_unused=True)
+    return td.detach(), loss.detach(), [torch.zeros_like(p) if g is None else g for p, g in zip(tr.head_params, grads)]
+
+
+@pytest.mark.parametrize("batch", [256, 100, 700])
+@pytest.mark.parametrize("online_train_mode", [True, False])
+def test_dqn_head_grads_kernel_matches_autograd(batch, online_train_mode):
+    torch.manual_seed(5)
+    net = pp.QNet()
+    with torch.no_grad():
+        for m in (net.fc_V, net.fc_A):                       # sizeable sigma so that the noise matters
+            m.weight_sigma.mul_(8.0); m.bias_sigma.mul_(8.0)
+    tr = pp.DQNTrainer(net, batch_size=batch, fused=True, use_graph=False)
+    with torch.no_grad():                                   # online and target differ, target has its own noise buffers
+        for m in (tr.target.fc_V, tr.target.fc_A):          # (the frozen features are shared by construction, :97)
+            for p in m.parameters():
+                p.add_(0.03 * torch.randn_like(p))
+    tr.model.train(online_train_mode)
+    tr.model.reset_noise(); tr.target.reset_noise()
+    ring = _ring(4096, seed=batch)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    idx = torch.randint(0, ring.capacity, (batch,), generator=g, device="cuda")
+    iw = torch.rand(batch, generator=g, device="cuda") + 0.1
+    td_w, loss_w, grads_w = _torch_update(tr, ring, idx, iw)
+    prios = torch.zeros(ring.capacity, device="cuda")
+    td = torch.zeros(batch, device="cuda"); loss = torch.zeros(1, device="cuda")
+    rs = ring.struct()
+    lib = _lib.load()
+    _lib.check(lib.pp_dqn_head_grads(C.byref(rs), _ptr(idx), _ptr(iw), batch, *tr._feature_ptrs(), C.byref(tr._on_v),
+                                     C.byref(tr._on_a), C.byref(tr._tg_v), C.byref(tr._tg_a), int(tr.model.training),
+                                     int(tr.target.training), tr.gamma, _ptr(td), _ptr(loss), _ptr(prios),
+                                     _stream_ptr(torch.device("cuda"))), "pp_dqn_head_grads")
+    torch.cuda.synchronize()
+    assert torch.allclose(td, td_w, rtol=1e-5, atol=2e-6)
+    assert abs(loss.item() - loss_w.item()) <= 1e-5 * abs(loss_w.item()) + 1e-7
+    for p, gw in zip(tr.head_params, grads_w):
+        scale = max(gw.abs().max().item(), 1e-6)
+        assert (p.grad - gw).abs().max().item() <= 2e-5 * scale + 1e-8, (p.shape, (p.grad - gw).abs().max().item(), scale)
+    if not online_train_mode:                               # eval-mode forward: sigma does not enter
+        assert all(torch.count_nonzero(p.grad) == 0 for p in (tr.model.fc_V.weight_sigma, tr.model.fc_A.bias_sigma))
+    # priorities: |td| + 1e-6 at the sampled slots, untouched elsewhere (:74-76)
+    touched = torch.zeros(ring.capacity, dtype=torch.bool, device="cuda"); touched[idx] = True
+    assert torch.count_nonzero(prios[~touched]) == 0
+    last = {}
+    for r_, s_ in enumerate(idx.tolist()):                  # `for idx, err in zip(idxs, errors)`: the last occurrence wins
+        last[s_] = r_
+    pc, tdc = prios.cpu(), td.cpu()
+    assert len(last) < batch or batch < 200                 # the batch does contain repeated slots
+    assert all(float(pc[s_]) == float(tdc[r_].abs() + 1e-6) for s_, r_ in last.items())
+
+
+def test_noisy_reset_kernel_is_factorised_gaussian_noise_and_advances_its_counter():
+    lin = pp.NoisyLinear(128, 96).cuda()
+    small = pp.NoisyLinear(64, 3).cuda()
+    mk = lambda m: _lib.PPNoisyLayer(m.in_features, m.out_features, _ptr(m.weight_mu), _ptr(m.weight_sigma), _ptr(m.weight_epsilon),
+                                     _ptr(m.bias_mu), _ptr(m.bias_sigma), _ptr(m.bias_epsilon), None, None, None, None)
+    layers = (_lib.PPNoisyLayer * 2)(mk(lin), mk(small))
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lib, st = _lib.load(), _stream_ptr(torch.device("cuda"))
+    samples, seen = [], set()
+    for it in range(300):
+        _lib.check(lib.pp_noisy_reset(layers, 2, 1234, _ptr(counter), st), "pp_noisy_reset")
+        w, b = lin.weight_epsilon.clone(), lin.bias_epsilon.clone()
+        if it < 3:                                           # weight_epsilon = outer(e_out, e_in), bias_epsilon = e_out  (:36-41)
+            e_in = w[0] / b[0]
+            assert torch.allclose(w, torch.outer(b, e_in), rtol=1e-5, atol=1e-7)
+            ws, bs = small.weight_epsilon, small.bias_epsilon
+            assert torch.allclose(ws, torch.outer(bs, ws[0] / bs[0]), rtol=1e-5, atol=1e-7)
+        samples.append(torch.cat([b, w[0] / b[0]]))
+        seen.add(float(b[0]))
+    assert int(counter.item()) == 300 and len(seen) == 300   # fresh noise at every launch
+    e = torch.cat(samples).double()
+    g = e.sign() * e * e                                      # invert f(g) = sign(g) sqrt|g|
+    assert abs(g.mean().item()) < 0.02 and abs(g.std().item() - 1.0) < 0.02
+    assert abs((g.abs() < 0.6745).double().mean().item() - 0.5) < 0.01       # quartiles of N(0, 1)
+    assert abs((e * e).mean().item() - np.sqrt(2 / np.pi)) < 0.02
+    c2 = torch.zeros(1, dtype=torch.int64, device="cuda")     # same (seed, counter) -> same noise
+    _lib.check(lib.pp_noisy_reset(layers, 2, 1234, _ptr(c2), st), "pp_noisy_reset")
+    first = lin.bias_epsilon.clone()
+    c2.zero_()
+    _lib.check(lib.pp_noisy_reset(layers, 2, 1234, _ptr(c2), st), "pp_noisy_reset")
+    assert torch.equal(first, lin.bias_epsilon)
+
+
+@pytest.mark.parametrize("noisy", [True, False])
+def test_pack_qnet_kernel_equals_the_host_packing(noisy):
+    torch.manual_seed(8)
+    net = pp.QNet().cuda()
+    with torch.no_grad():
+        net.fc_V.weight_sigma.mul_(20); net.fc_A.bias_sigma.mul_(20)
+    tr = pp.DQNTrainer(net, fused=True, use_graph=False)
+    blob = torch.zeros(_lib.QNET_BLOB_FLOATS, device="cuda")
+    m = tr.model
+    _lib.check(_lib.load().pp_pack_qnet(_ptr(m.features[0].weight), _ptr(m.features[0].bias), _ptr(m.features[2].weight),
+                                        _ptr(m.features[2].bias), C.byref(tr._on_v), C.byref(tr._on_a), int(noisy), _ptr(blob),
+                                        _stream_ptr(torch.device("cuda"))), "pp_pack_qnet")
+    assert torch.equal(blob, pp.pack_qnet(m, noisy=noisy))
+    if noisy:                                                # reset_noise_and_pack = new noise, then exactly this packing
+        before = m.fc_A.weight_epsilon.clone()
+        tr.reset_noise_and_pack(blob)
+        assert not torch.equal(before, m.fc_A.weight_epsilon)
+        assert torch.equal(blob, pp.pack_qnet(m, noisy=True))
+
+
+def test_fused_and_framework_updates_train_alike():
+    """Same batch, same noise: one update through the fused kernels moves the heads and the priorities like the
+    PyTorch formulation does."""
+    torch.manual_seed(2)
+    net = pp.QNet()
+    ring = _ring(8192, seed=3)
+
+    def run(fused, noise_from=None):
+        tr = pp.DQNTrainer(pp.QNet(), batch_size=256, fused=fused, use_graph=False, lr=1e-3)
+        tr.model.load_state_dict(net.state_dict()); tr.target.load_state_dict(net.state_dict())
+        sampler = pp.PrioritizedSampler(ring); sampler.note_new_rows()
+        torch.manual_seed(9)
+        idx, iw = sampler.sample(256, 0.4)
+        sampler.sample = lambda *a, **k: (idx, iw)          # the same batch for both
+        if noise_from is not None:                           # replay the noise the fused update drew
+            for dst, src in ((tr.model, noise_from.model), (tr.target, noise_from.target)):
+                for name in ("fc_V", "fc_A"):
+                    getattr(dst, name).weight_epsilon.copy_(getattr(src, name).weight_epsilon)
+                    getattr(dst, name).bias_epsilon.copy_(getattr(src, name).bias_epsilon)
+                dst.reset_noise = lambda: None
+        tr.update(sampler)
+        return tr, torch.cat([p.detach().flatten() for p in tr.head_params]).clone(), sampler.prios.clone()
+
+    tr_f, heads_f, prios_f = run(True)
+    _, heads_t, prios_t = run(False, noise_from=tr_f)
+    assert not torch.equal(heads_f, torch.cat([p.detach().flatten().cuda() for p in
+                                                (list(net.fc_V.parameters()) + list(net.fc_A.parameters()))]))
+    assert torch.allclose(heads_f, heads_t, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(prios_f, prios_t, rtol=1e-4, atol=2e-6)

@@ -80,12 +80,14 @@ def test_dqn_update_equals_reference_train_step_restated():
         ref_prios[idxs] = (q_vals - targets).detach().abs() + 1e-6
         if step % 2 == 0:
             ref_target.load_state_dict(ref_model.state_dict())
-        assert float(loss) == pytest.approx(float(ref_loss.detach()), rel=1e-6)
+        # same batch, same noise; the sampler never materialises the normalised probabilities (pa[idx] / total instead of
+        # (pa / total)[idx]), so importance weights agree to rounding, not bit for bit
+        assert float(loss) == pytest.approx(float(ref_loss.detach()), rel=1e-5)
         for p, q in zip(tr.model.state_dict().values(), ref_model.state_dict().values()):
-            assert torch.equal(p, q)
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-8)
         for p, q in zip(tr.target.state_dict().values(), ref_target.state_dict().values()):
-            assert torch.equal(p, q)
-        assert torch.equal(s1.prios, ref_prios)
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-8)
+        assert torch.allclose(s1.prios, ref_prios, rtol=1e-5, atol=1e-9)
     assert tr.train_steps == 3 and torch.equal(tr.model.features[0].weight, net.features[0].weight)
     assert not torch.equal(tr.model.fc_A.weight_mu, net.fc_A.weight_mu)
 
