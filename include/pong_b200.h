@@ -203,6 +203,13 @@ typedef struct PPNoisyLayer {
     float *grad_bias_mu, *grad_bias_sigma;                  /* [out]     */
 } PPNoisyLayer;
 
+/* One parameter tensor of torch.optim.Adam with its optimiser state (optimizer.state[p]): all device pointers.
+ * `step` is the 0-d float32 step counter of a capturable optimiser. */
+typedef struct PPAdamParam {
+    float *param, *grad, *exp_avg, *exp_avg_sq, *step;
+    int64_t numel;
+} PPAdamParam;
+
 int pp_version(void);
 const char *pp_last_error(void);
 
@@ -292,12 +299,22 @@ int pp_pack_qnet(const float *features0_weight, const float *features0_bias, con
  * [64][64], torch layout) are frozen (:97) and shared by the online and the target net.  idx[batch] are ring slots,
  * iw[batch] the importance weights.  td_out[batch], loss_out[1] and prios (the PER priority array indexed by ring
  * slot, receives |td| + 1e-6, :74-76,163-164) may be NULL.  noisy_online / noisy_target select the train- or
- * eval-mode forward of each net (the reference: online train mode, target eval mode :100). */
+ * eval-mode forward of each net (the reference: online train mode, target eval mode :100).  batch <= 4096.
+ * `workspace`: pp_dqn_workspace_floats(batch) floats of device memory, ZERO before the first launch that uses it (the
+ * kernel leaves it ready for the next one): per-tile partial sums + the ticket of the CTA that finishes last. */
 int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float *iw, int32_t batch,
                       const float *features0_weight, const float *features0_bias, const float *features2_weight,
                       const float *features2_bias, const PPNoisyLayer *online_v, const PPNoisyLayer *online_a,
                       const PPNoisyLayer *target_v, const PPNoisyLayer *target_a, int32_t noisy_online,
-                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios, void *stream);
+                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios,
+                      float *workspace, void *stream);
+int64_t pp_dqn_workspace_floats(int32_t batch);
+
+/* optimizerB.step() of scripts/train_iterative.py:162 — torch.optim.Adam (betas, eps as given; no amsgrad, no weight
+ * decay) for `count` <= 16 small tensors in one launch, IN PLACE on the parameter and on the optimiser's own state:
+ *   step += 1;  m = lerp(m, g, 1 - beta1);  v = beta2 v + (1 - beta2) g^2;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps) */
+int pp_adam_step(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, void *stream);
 
 #ifdef __cplusplus
 }

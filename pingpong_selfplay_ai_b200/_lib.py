@@ -69,6 +69,10 @@ class PPNoisyLayer(C.Structure):
                 ("grad_weight_mu", c_vp), ("grad_weight_sigma", c_vp), ("grad_bias_mu", c_vp), ("grad_bias_sigma", c_vp)]
 
 
+class PPAdamParam(C.Structure):
+    _fields_ = [("param", c_vp), ("grad", c_vp), ("exp_avg", c_vp), ("exp_avg_sq", c_vp), ("step", c_vp), ("numel", c_i64)]
+
+
 P = C.POINTER
 _PROTOTYPES = {
     "pp_version": (C.c_int, []),
@@ -88,7 +92,9 @@ _PROTOTYPES = {
     "pp_noisy_reset": (C.c_int, [P(PPNoisyLayer), c_i32, c_u64, c_vp, c_vp]),
     "pp_pack_qnet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_vp, c_vp]),
     "pp_dqn_head_grads": (C.c_int, [P(PPReplayRing), c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, P(PPNoisyLayer), P(PPNoisyLayer),
-                                    P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),
+                                    P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pp_dqn_workspace_floats": (c_i64, [c_i32]),
+    "pp_adam_step": (C.c_int, [P(PPAdamParam), c_i32, c_f64, c_f64, c_f64, c_f64, c_vp]),
     "pp_host_selfplay_eval": (C.c_int, [C.c_int, c_i64, c_i32, P(PPParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                         c_i64, c_i64, c_vp, c_vp, c_i64]),
 }

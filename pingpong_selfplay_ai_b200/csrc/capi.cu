@@ -226,16 +226,33 @@ int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float 
                       const float *features0_weight, const float *features0_bias, const float *features2_weight,
                       const float *features2_bias, const PPNoisyLayer *online_v, const PPNoisyLayer *online_a,
                       const PPNoisyLayer *target_v, const PPNoisyLayer *target_a, int32_t noisy_online,
-                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios, void *stream) {
+                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios, float *workspace,
+                      void *stream) {
     const char *fn = "pp_dqn_head_grads";
-    if (batch <= 0 || batch > (1 << 20)) return fail(PP_E_SIZE, fn);
+    if (batch <= 0 || batch > 4096) return fail(PP_E_SIZE, fn);
+    if (!workspace) return fail(PP_E_NULL, fn);
     if (!ring_ok(ring) || !idx || !iw || !features0_weight || !features0_bias || !features2_weight || !features2_bias)
         return fail(PP_E_NULL, fn);
     if (!noisy_ok(online_v, 64, 1) || !noisy_ok(online_a, 64, 3) || !noisy_ok(target_v, 64, 1) || !noisy_ok(target_a, 64, 3))
         return fail(PP_E_PARAM, fn);
     return ok_or(pp::dqn_head_grads_launch(*ring, idx, iw, batch, features0_weight, features0_bias, features2_weight,
                                            features2_bias, *online_v, *online_a, *target_v, *target_a,
-                                           noisy_online, noisy_target, gamma, td_out, loss_out, prios, (cudaStream_t)stream), fn);
+                                           noisy_online, noisy_target, gamma, td_out, loss_out, prios, workspace, (cudaStream_t)stream), fn);
+}
+
+int64_t pp_dqn_workspace_floats(int32_t batch) { return batch > 0 ? pp::dqn_workspace_floats(batch) : 0; }
+
+int pp_adam_step(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, void *stream) {
+    if (count < 0 || count > 16) return fail(PP_E_SIZE, "pp_adam_step");
+    if (count > 0 && !params) return fail(PP_E_NULL, "pp_adam_step");
+    for (int i = 0; i < count; ++i) {
+        const PPAdamParam &a = params[i];
+        if (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq || !a.step) return fail(PP_E_NULL, "pp_adam_step");
+        if (a.numel < 0) return fail(PP_E_SIZE, "pp_adam_step");
+    }
+    if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0)) return fail(PP_E_PARAM, "pp_adam_step");
+    if (count == 0) return 0;
+    return ok_or(pp::adam_step_launch(params, count, lr, beta1, beta2, eps, (cudaStream_t)stream), "pp_adam_step");
 }
 
 // ---------------------------------------------------------------------------------------------

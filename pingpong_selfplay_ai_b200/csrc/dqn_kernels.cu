@@ -3,10 +3,13 @@
 // the rollout kernels — three small launches instead of ~130 framework kernels per update.
 //
 // Only the NoisyNet heads train (features are frozen, scripts/train_iterative.py:97): 520 parameters.  A batch row
-// needs two feature forwards (s and s') of 4 544 MACs each and three head evaluations; one CTA of 256 threads does a
-// batch of 256 rows in ~6 us: one row per thread through the same broadcast-LDS fmaf chain as the CUDA-core rollout,
-// the 64 hidden activations of s parked in shared memory, then a column-per-thread reduction over the rows for the
-// 4 x 64 weight gradients.  fp32 throughout (tolerance vs torch autograd: 1e-5).
+// needs two feature forwards (s and s') of 4 544 MACs each and three head evaluations.  The batch is small, so the
+// kernel is latency-bound: it is cut into tiles of 16 rows, one CTA each; SIXTEEN lanes share a row (each owns 4 of the
+// 64 units of either layer), partial head sums meet through four shuffles, the activations of s are parked in shared
+// memory and a column-per-thread pass over the tile's rows gives the CTA's share of the 4 x 64 weight gradients.
+// Partials go to a workspace; the CTA that takes the last ticket adds them in tile order (deterministic), writes the
+// eight gradient tensors, the loss and the new priorities (last occurrence of a slot in the batch wins, like the
+// reference's Python loop).  fp32 throughout (tolerance vs torch autograd: 1e-5).
 #include "pp_host.h"
 #include "pp_policy.cuh"
 
@@ -15,49 +18,38 @@ namespace pp {
 namespace {
 
 constexpr int D_THREADS = 256;
+constexpr int D_ROWS = 16;                              // batch rows per CTA: sixteen lanes per row, 4 units each
+constexpr int D_MAX_BATCH = 4096;                       // the last CTA stages all slots of the batch in shared memory
 constexpr int D_H2_STRIDE = 65;                         // row stride of the h2 tile: conflict-free column walks
 constexpr int D_FEAT_FLOATS = PP_QNET_WHT;              // W1T, B1, W2T, B2 of the packed blob (4 672 floats)
+constexpr int D_PART = 264;                             // per-CTA partials: 256 weight grads, 4 bias grads, loss, pad
 
-// features(x) of QNet: h2 = relu(W2 relu(W1 x + b1) + b2); consume(k, h2[k]) is called for k = 0..63 ascending.
-template <typename F>
-__device__ __forceinline__ void qnet_features(const float *__restrict__ sw, const float (&obs)[7], F &&consume) {
-    float h1[64];
-    {
-        const float4 *w1 = reinterpret_cast<const float4 *>(sw + PP_QNET_W1T);
-        const float4 *b1 = reinterpret_cast<const float4 *>(sw + PP_QNET_B1);
+// h2 = relu(W2 relu(W1 x + b1) + b2) for one row shared by SIXTEEN lanes (half a warp): lane part `pt` computes units
+// pt*4..+3 of both layers; the row's h1 goes through shared memory (h1row, 64 floats, private to the row).  Rolled
+// loops, short dependent chains: the batch is small, so the kernel is latency- not throughput-bound.
+__device__ __forceinline__ float4 qnet_features4(const float *__restrict__ sw, const float (&obs)[7], int pt,
+                                                 float *__restrict__ h1row) {
+    const float4 *w1 = reinterpret_cast<const float4 *>(sw + PP_QNET_W1T) + pt;
+    float4 acc = reinterpret_cast<const float4 *>(sw + PP_QNET_B1)[pt];
 #pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4) {
-            float4 acc = b1[j4];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const float4 w = w1[k * 16 + j4];
-                acc.x = fmaf(w.x, obs[k], acc.x); acc.y = fmaf(w.y, obs[k], acc.y);
-                acc.z = fmaf(w.z, obs[k], acc.z); acc.w = fmaf(w.w, obs[k], acc.w);
-            }
-            h1[j4 * 4 + 0] = relu(acc.x); h1[j4 * 4 + 1] = relu(acc.y);
-            h1[j4 * 4 + 2] = relu(acc.z); h1[j4 * 4 + 3] = relu(acc.w);
-        }
+    for (int k = 0; k < 7; ++k) {
+        const float4 w = w1[k * 16];
+        acc.x = fmaf(w.x, obs[k], acc.x); acc.y = fmaf(w.y, obs[k], acc.y);
+        acc.z = fmaf(w.z, obs[k], acc.z); acc.w = fmaf(w.w, obs[k], acc.w);
     }
-    const float4 *w2 = reinterpret_cast<const float4 *>(sw + PP_QNET_W2T);
-    const float4 *b2 = reinterpret_cast<const float4 *>(sw + PP_QNET_B2);
-#pragma unroll 1
-    for (int jb = 0; jb < 4; ++jb) {
-        float4 a0 = b2[jb * 4 + 0], a1 = b2[jb * 4 + 1], a2 = b2[jb * 4 + 2], a3 = b2[jb * 4 + 3];
-#pragma unroll
-        for (int k = 0; k < 64; ++k) {
-            const float x = h1[k];
-            const float4 u0 = w2[k * 16 + jb * 4 + 0], u1 = w2[k * 16 + jb * 4 + 1];
-            const float4 u2 = w2[k * 16 + jb * 4 + 2], u3 = w2[k * 16 + jb * 4 + 3];
-            a0.x = fmaf(u0.x, x, a0.x); a0.y = fmaf(u0.y, x, a0.y); a0.z = fmaf(u0.z, x, a0.z); a0.w = fmaf(u0.w, x, a0.w);
-            a1.x = fmaf(u1.x, x, a1.x); a1.y = fmaf(u1.y, x, a1.y); a1.z = fmaf(u1.z, x, a1.z); a1.w = fmaf(u1.w, x, a1.w);
-            a2.x = fmaf(u2.x, x, a2.x); a2.y = fmaf(u2.y, x, a2.y); a2.z = fmaf(u2.z, x, a2.z); a2.w = fmaf(u2.w, x, a2.w);
-            a3.x = fmaf(u3.x, x, a3.x); a3.y = fmaf(u3.y, x, a3.y); a3.z = fmaf(u3.z, x, a3.z); a3.w = fmaf(u3.w, x, a3.w);
-        }
-        const float h2[16] = {relu(a0.x), relu(a0.y), relu(a0.z), relu(a0.w), relu(a1.x), relu(a1.y), relu(a1.z), relu(a1.w),
-                              relu(a2.x), relu(a2.y), relu(a2.z), relu(a2.w), relu(a3.x), relu(a3.y), relu(a3.z), relu(a3.w)};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) consume(jb * 16 + i, h2[i]);
+    __syncwarp();                                                              // the row's previous h1 has been consumed
+    reinterpret_cast<float *>(h1row)[pt * 4 + 0] = relu(acc.x); h1row[pt * 4 + 1] = relu(acc.y);
+    h1row[pt * 4 + 2] = relu(acc.z); h1row[pt * 4 + 3] = relu(acc.w);
+    __syncwarp();                                                              // the sixteen lanes of a row sit in one warp
+    const float4 *w2 = reinterpret_cast<const float4 *>(sw + PP_QNET_W2T) + pt;
+    float4 a = reinterpret_cast<const float4 *>(sw + PP_QNET_B2)[pt];
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) {
+        const float x = h1row[k];
+        const float4 u = w2[k * 16];
+        a.x = fmaf(u.x, x, a.x); a.y = fmaf(u.y, x, a.y); a.z = fmaf(u.z, x, a.z); a.w = fmaf(u.w, x, a.w);
     }
+    return make_float4(relu(a.x), relu(a.y), relu(a.z), relu(a.w));
 }
 
 __device__ __forceinline__ float eff(const float *mu, const float *sigma, const float *eps, int i, bool noisy) {
@@ -98,100 +90,155 @@ __device__ __forceinline__ float block_sum(float v, float *scratch) {         //
     return s;
 }
 
+__device__ __forceinline__ float4 row_sum(float4 v) {                          // over the sixteen lanes of a row
+#pragma unroll
+    for (int o = 1; o <= 8; o <<= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+    }
+    return v;
+}
+
+__device__ __forceinline__ float4 f4_add(const float4 &a, const float4 &b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
 // Double-DQN on the heads: forward, TD error, loss and the gradients of the eight head tensors.
+// ws: [tiles][D_PART] partials, then [batch] TD errors, then the ticket counter (zero between launches).
 __global__ void __launch_bounds__(D_THREADS, 1)
 dqn_head_grads_kernel(const PPReplayRing ring, const int64_t *__restrict__ idx, const float *__restrict__ iw, int batch,
                       const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
                       const float *__restrict__ b2, const PPNoisyLayer on_v, const PPNoisyLayer on_a,
                       const PPNoisyLayer tg_v, const PPNoisyLayer tg_a, int noisy_online, int noisy_target, float gamma,
-                      float *__restrict__ td_out, float *__restrict__ loss_out, float *__restrict__ prios) {
+                      float *__restrict__ td_out, float *__restrict__ loss_out, float *__restrict__ prios, float *ws) {
     extern __shared__ __align__(16) float smem[];
     float *sw = smem;                                                          // feature weights
     float4 *head_on = reinterpret_cast<float4 *>(smem + D_FEAT_FLOATS);        // [65]
     float4 *head_tg = head_on + 65;                                            // [65]
-    float *h2s = reinterpret_cast<float *>(head_tg + 65);                      // [256][65]
-    float *g_s = h2s + D_THREADS * D_H2_STRIDE;                                // [256] dL/dQ(s, a)
-    int *a_s = reinterpret_cast<int *>(g_s + D_THREADS);                       // [256] action taken
-    float *scratch = reinterpret_cast<float *>(a_s + D_THREADS);               // [8]
-    long long *slot_s = reinterpret_cast<long long *>(scratch + 8);            // [256] ring slot of each row of the tile
-    const int tid = threadIdx.x;
+    float *h2s = reinterpret_cast<float *>(head_tg + 65);                      // [64][65]
+    float *g_s = h2s + D_ROWS * D_H2_STRIDE;                                   // [64] dL/dQ(s, a)
+    int *a_s = reinterpret_cast<int *>(g_s + D_ROWS);                          // [64] action taken
+    float *scratch = reinterpret_cast<float *>(a_s + D_ROWS);                  // [8]
+    float *h1s = scratch + 8;                                                  // [64][65] first-layer activations per row
+    __shared__ int is_last;
+    const int tid = threadIdx.x, tiles = gridDim.x;
+    float *ws_td = ws + (size_t)tiles * D_PART;
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(ws_td + batch);
     // feature layers straight from the module's tensors ([out][in]) into the k-major tables of the fmaf chain
-    for (int i = tid; i < 64 * 7; i += D_THREADS) sw[PP_QNET_W1T + (i % 7) * 64 + i / 7] = w1[i];
-    for (int i = tid; i < 64 * 64; i += D_THREADS) sw[PP_QNET_W2T + (i & 63) * 64 + (i >> 6)] = w2[i];
+    // (consecutive lanes write consecutive words; the strided global reads of a warp share their sectors in L1)
+    for (int o = tid; o < 64 * 7; o += D_THREADS) sw[PP_QNET_W1T + o] = w1[(o & 63) * 7 + (o >> 6)];
+    for (int o = tid; o < 64 * 64; o += D_THREADS) sw[PP_QNET_W2T + o] = w2[(o & 63) * 64 + (o >> 6)];
     if (tid < 64) { sw[PP_QNET_B1 + tid] = b1[tid]; sw[PP_QNET_B2 + tid] = b2[tid]; }
     stage_head(head_on, on_v, on_a, noisy_online != 0);
     stage_head(head_tg, tg_v, tg_a, noisy_target != 0);
     __syncthreads();
 
-    const int hj = tid >> 6, hk = tid & 63;                                    // this thread's gradient column: head row, unit
-    float grad_w = 0.f, grad_b = 0.f, loss_part = 0.f;
+    const int row = tid >> 4, pt = tid & 15;                                   // sixteen consecutive lanes share a row
+    const int r = blockIdx.x * D_ROWS + row;
     const float inv_b = 1.0f / (float)batch;
-    for (int base = 0; base < batch; base += D_THREADS) {
-        const int r = base + tid;
-        float g = 0.f, prio = 0.f;
-        int act = 0;
-        int64_t slot = -1;
-        if (r < batch) {
-            slot = idx[r];
-            float s[7], ns[7];
+    float loss_part = 0.f;
+    {
+        const bool live = r < batch;
+        const int64_t slot = live ? idx[r] : 0;
+        float s[7], ns[7];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) { s[k] = ring.obs[slot * 7 + k]; ns[k] = ring.next_obs[slot * 7 + k]; }
-            act = ring.act[slot];
-            act = act > 2 ? 2 : act;
-            float4 hs = head_on[64];
-            float *row = h2s + tid * D_H2_STRIDE;
-            qnet_features(sw, s, [&](int k, float v) { row[k] = v; head_acc(hs, head_on[k], v); });
-            float4 hn_on = head_on[64], hn_tg = head_tg[64];
-            qnet_features(sw, ns, [&](int k, float v) { head_acc(hn_on, head_on[k], v); head_acc(hn_tg, head_tg[k], v); });
-            float q[3], qn_on[3], qn_tg[3];
-            dueling(hs, q); dueling(hn_on, qn_on); dueling(hn_tg, qn_tg);
-            const int best = argmax3(qn_on);                                   // :154
-            const float alive = ring.done[slot] ? 0.0f : 1.0f;
-            const float target = ring.rew[slot] + gamma * qn_tg[best] * alive; // :155-156
-            const float td = q[act] - target;
-            const float w = iw[r];
-            loss_part += w * td * td;                                          // :158
-            g = 2.0f * w * td * inv_b;
-            if (td_out) td_out[r] = td;
-            prio = fabsf(td) + 1e-6f;                                          // :163-164, :74-76
-        } else {
-            float *row = h2s + tid * D_H2_STRIDE;
-#pragma unroll 1
-            for (int k = 0; k < 64; ++k) row[k] = 0.f;
+        for (int k = 0; k < 7; ++k) { s[k] = ring.obs[slot * 7 + k]; ns[k] = ring.next_obs[slot * 7 + k]; }
+        float *h1row = h1s + row * D_H2_STRIDE;
+        const float4 h2 = qnet_features4(sw, s, pt, h1row);
+        const float h2v[4] = {h2.x, h2.y, h2.z, h2.w};
+        float4 hs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            h2s[row * D_H2_STRIDE + pt * 4 + i] = live ? h2v[i] : 0.f;
+            head_acc(hs, head_on[pt * 4 + i], h2v[i]);
         }
-        g_s[tid] = g; a_s[tid] = act; slot_s[tid] = slot;
-        __syncthreads();
-        if (prios && slot >= 0) {              // `for idx, err in zip(...)`: the LAST occurrence of a slot in the batch wins
-            bool last = true;
-            for (int rr = tid + 1; rr < D_THREADS; ++rr) last = last && slot_s[rr] != slot;
-            if (last) prios[slot] = prio;      // (a later tile overwrites an earlier one: tiles run in batch order)
+        const float4 n2 = qnet_features4(sw, ns, pt, h1row);
+        const float n2v[4] = {n2.x, n2.y, n2.z, n2.w};
+        float4 hn_on = make_float4(0.f, 0.f, 0.f, 0.f), hn_tg = hn_on;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { head_acc(hn_on, head_on[pt * 4 + i], n2v[i]); head_acc(hn_tg, head_tg[pt * 4 + i], n2v[i]); }
+        hs = f4_add(row_sum(hs), head_on[64]);
+        hn_on = f4_add(row_sum(hn_on), head_on[64]);
+        hn_tg = f4_add(row_sum(hn_tg), head_tg[64]);
+        if (pt == 0) {
+            float g = 0.f;
+            int act = 0;
+            if (live) {
+                float q[3], qn_on[3], qn_tg[3];
+                dueling(hs, q); dueling(hn_on, qn_on); dueling(hn_tg, qn_tg);
+                act = ring.act[slot];
+                act = act > 2 ? 2 : act;
+                const int best = argmax3(qn_on);                               // :154
+                const float nq = best == 0 ? qn_tg[0] : (best == 1 ? qn_tg[1] : qn_tg[2]);
+                const float qa = act == 0 ? q[0] : (act == 1 ? q[1] : q[2]);
+                const float alive = ring.done[slot] ? 0.0f : 1.0f;
+                const float td = qa - (ring.rew[slot] + gamma * nq * alive);   // :152-156
+                const float w = iw[r];
+                loss_part = w * td * td;                                       // :158
+                g = 2.0f * w * td * inv_b;
+                ws_td[r] = td;
+                if (td_out) td_out[r] = td;
+            }
+            g_s[row] = g; a_s[row] = act;
         }
-        // d/dV = g ; d/dA_j = g * ([j == a] - 1/3)        (Q_a = V + A_a - mean A)
-#pragma unroll 4
-        for (int rr = 0; rr < D_THREADS; ++rr) {
-            const float gr = g_s[rr];
-            const float coef = hj == 0 ? gr : gr * ((a_s[rr] == hj - 1 ? 1.0f : 0.0f) - (1.0f / 3.0f));
-            grad_w = fmaf(coef, h2s[rr * D_H2_STRIDE + hk], grad_w);
-            if (hk == 0) grad_b += coef;
-        }
-        __syncthreads();
     }
-    const float loss = block_sum(loss_part, scratch) * inv_b;
-    if (tid == 0 && loss_out) *loss_out = loss;
-    // gradients of mu and sigma (weight = mu + sigma * eps)
-    const PPNoisyLayer &L = hj == 0 ? on_v : on_a;
+    __syncthreads();
+    // this tile's share of the gradients:  d/dV = g ;  d/dA_j = g * ([j == a] - 1/3)      (Q_a = V + A_a - mean A)
+    const int hj = tid >> 6, hk = tid & 63;                                    // gradient column: head row, hidden unit
+    float grad_w = 0.f, grad_b = 0.f;
+#pragma unroll 4
+    for (int rr = 0; rr < D_ROWS; ++rr) {
+        const float gr = g_s[rr];
+        const float coef = hj == 0 ? gr : gr * ((a_s[rr] == hj - 1 ? 1.0f : 0.0f) - (1.0f / 3.0f));
+        grad_w = fmaf(coef, h2s[rr * D_H2_STRIDE + hk], grad_w);
+        grad_b += coef;
+    }
+    const float loss_tile = block_sum(loss_part, scratch);
+    float *part = ws + (size_t)blockIdx.x * D_PART;
+    part[tid] = grad_w;
+    if (hk == 0) part[256 + hj] = grad_b;
+    if (tid == 0) part[260] = loss_tile;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(ticket, 1u) == (unsigned)(tiles - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- the last CTA: partials in tile order, then the outputs
+    float gw = 0.f, gb = 0.f, loss = 0.f;
+    for (int c = 0; c < tiles; ++c) {
+        const float *pc = ws + (size_t)c * D_PART;
+        gw += __ldcg(pc + tid);
+        gb += __ldcg(pc + 256 + hj);
+        loss += __ldcg(pc + 260);
+    }
+    if (tid == 0 && loss_out) *loss_out = loss * inv_b;
+    const PPNoisyLayer &L = hj == 0 ? on_v : on_a;                             // weight = mu + sigma * eps
     const int wi = hj == 0 ? hk : (hj - 1) * 64 + hk, bi = hj == 0 ? 0 : hj - 1;
     const bool noisy = noisy_online != 0;
-    if (L.grad_weight_mu) L.grad_weight_mu[wi] = grad_w;
-    if (L.grad_weight_sigma) L.grad_weight_sigma[wi] = noisy ? grad_w * L.weight_epsilon[wi] : 0.f;
+    if (L.grad_weight_mu) L.grad_weight_mu[wi] = gw;
+    if (L.grad_weight_sigma) L.grad_weight_sigma[wi] = noisy ? gw * L.weight_epsilon[wi] : 0.f;
     if (hk == 0) {
-        if (L.grad_bias_mu) L.grad_bias_mu[bi] = grad_b;
-        if (L.grad_bias_sigma) L.grad_bias_sigma[bi] = noisy ? grad_b * L.bias_epsilon[bi] : 0.f;
+        if (L.grad_bias_mu) L.grad_bias_mu[bi] = gb;
+        if (L.grad_bias_sigma) L.grad_bias_sigma[bi] = noisy ? gb * L.bias_epsilon[bi] : 0.f;
     }
+    if (prios) {               // `for idx, err in zip(idxs, errors)` :74-76 — the LAST occurrence of a slot in the batch wins
+        long long *slots = reinterpret_cast<long long *>(smem);                // the weights are no longer needed
+        __syncthreads();
+        for (int rr = tid; rr < batch; rr += D_THREADS) slots[rr] = idx[rr];
+        __syncthreads();
+        for (int rr = tid; rr < batch; rr += D_THREADS) {
+            const long long slot = slots[rr];
+            bool last = true;
+            for (int q = rr + 1; q < batch; ++q) last = last && slots[q] != slot;
+            if (last) prios[slot] = fabsf(__ldcg(ws_td + rr)) + 1e-6f;
+        }
+    }
+    if (tid == 0) *ticket = 0u;                                                // ready for the next launch
 }
 
-constexpr size_t D_SMEM = (size_t)(D_FEAT_FLOATS + 2 * 65 * 4 + D_THREADS * D_H2_STRIDE + 2 * D_THREADS + 8) * sizeof(float) +
-                          D_THREADS * sizeof(long long);
+constexpr size_t D_SMEM_USED = (size_t)(D_FEAT_FLOATS + 2 * 65 * 4 + 2 * D_ROWS * D_H2_STRIDE + 2 * D_ROWS + 8) * sizeof(float);
+constexpr size_t D_SMEM = D_SMEM_USED > D_MAX_BATCH * sizeof(long long) ? D_SMEM_USED : D_MAX_BATCH * sizeof(long long);
 
 // NoisyLinear.reset_noise for up to 8 layers: factorised Gaussian noise from Philox + Box-Muller.
 struct NoisyLayers { PPNoisyLayer l[8]; };
@@ -247,20 +294,57 @@ pack_qnet_kernel(const float *__restrict__ w1, const float *__restrict__ b1, con
     }
 }
 
+// torch.optim.Adam (no amsgrad, no weight decay) for a handful of small tensors in one launch, on the optimiser's own
+// state tensors (exp_avg, exp_avg_sq, step), so that optimizer.state_dict() keeps working for checkpoints.
+struct AdamParams { PPAdamParam p[16]; };
+
+__global__ void __launch_bounds__(256, 1)
+adam_step_kernel(const AdamParams ps, int count, double lr, double beta1, double beta2, double eps) {
+    const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), epsf = (float)eps;
+    for (int t = 0; t < count; ++t) {
+        const PPAdamParam &a = ps.p[t];
+        const double step = (double)*a.step + 1.0;                             // every thread reads the old value ...
+        // the scalars in double, like the Python floats of torch's (non-capturable) Adam: 1 - 0.999^step cancels in fp32
+        const float step_size = (float)(lr / (1.0 - pow(beta1, step)));
+        const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, step));
+        for (int64_t i = threadIdx.x; i < a.numel; i += blockDim.x) {
+            const float g = a.grad[i];
+            const float m = a.exp_avg[i] + w1 * (g - a.exp_avg[i]);                             // lerp_(grad, 1 - beta1)
+            const float v = a.exp_avg_sq[i] * b2 + w2 * (g * g);                                // mul_(beta2).addcmul_
+            a.exp_avg[i] = m; a.exp_avg_sq[i] = v;
+            a.param[i] = a.param[i] - step_size * (m / (sqrtf(v) / bc2_sqrt + epsf));          // addcdiv_
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *a.step = (float)step;                           // ... before one of them writes the new one
+    }
+}
+
 }  // namespace
 
+int adam_step_launch(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, cudaStream_t stream) {
+    AdamParams pack{};
+    for (int i = 0; i < count; ++i) pack.p[i] = params[i];
+    adam_step_kernel<<<1, 256, 0, stream>>>(pack, count, lr, beta1, beta2, eps);
+    return (int)cudaGetLastError();
+}
+
+int64_t dqn_workspace_floats(int32_t batch) { return (int64_t)((batch + D_ROWS - 1) / D_ROWS) * D_PART + batch + 8; }
+
 int dqn_head_grads_launch(const PPReplayRing &ring, const int64_t *idx, const float *iw, int32_t batch,
-                          const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &on_v, const PPNoisyLayer &on_a,
-                          const PPNoisyLayer &tg_v, const PPNoisyLayer &tg_a, int noisy_online, int noisy_target, float gamma,
-                          float *td_out, float *loss_out, float *prios, cudaStream_t stream) {
+                          const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &on_v,
+                          const PPNoisyLayer &on_a, const PPNoisyLayer &tg_v, const PPNoisyLayer &tg_a, int noisy_online,
+                          int noisy_target, float gamma, float *td_out, float *loss_out, float *prios, float *workspace,
+                          cudaStream_t stream) {
     static bool attr_set = false;                      // set once, before any stream capture replays the launch
     if (!attr_set) {
         cudaError_t err = cudaFuncSetAttribute(dqn_head_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM);
         if (err != cudaSuccess) return (int)err;
         attr_set = true;
     }
-    dqn_head_grads_kernel<<<1, D_THREADS, D_SMEM, stream>>>(ring, idx, iw, batch, w1, b1, w2, b2, on_v, on_a, tg_v, tg_a,
-                                                            noisy_online, noisy_target, gamma, td_out, loss_out, prios);
+    const unsigned tiles = (unsigned)((batch + D_ROWS - 1) / D_ROWS);
+    dqn_head_grads_kernel<<<tiles, D_THREADS, D_SMEM, stream>>>(ring, idx, iw, batch, w1, b1, w2, b2, on_v, on_a, tg_v, tg_a,
+                                                                noisy_online, noisy_target, gamma, td_out, loss_out, prios,
+                                                                workspace);
     return (int)cudaGetLastError();
 }
 

@@ -45,7 +45,9 @@ int replay_scatter_launch(int64_t n, const PPReplayRing &ring, const float *obs,
 int dqn_head_grads_launch(const PPReplayRing &ring, const int64_t *idx, const float *iw, int32_t batch,
                           const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &on_v, const PPNoisyLayer &on_a,
                           const PPNoisyLayer &tg_v, const PPNoisyLayer &tg_a, int noisy_online, int noisy_target, float gamma,
-                          float *td_out, float *loss_out, float *prios, cudaStream_t stream);
+                          float *td_out, float *loss_out, float *prios, float *workspace, cudaStream_t stream);
+int64_t dqn_workspace_floats(int32_t batch);
+int adam_step_launch(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, cudaStream_t stream);
 int noisy_reset_launch(const PPNoisyLayer *layers, int32_t count, uint64_t seed, unsigned long long *counter, cudaStream_t stream);
 int pack_qnet_launch(const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &v,
                      const PPNoisyLayer &a, int noisy, float *blob, cudaStream_t stream);

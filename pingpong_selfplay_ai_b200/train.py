@@ -109,13 +109,13 @@ class DQNTrainer:
         self.target.eval()                                                             # :100
         self.head_params = list(self.model.fc_V.parameters()) + list(self.model.fc_A.parameters())
         self.use_graph = use_graph
-        capturable = use_graph and self.device.type == "cuda"
+        self.fused = (self.device.type == "cuda") if fused is None else bool(fused)
+        capturable = (use_graph or self.fused) and self.device.type == "cuda"          # device-side step counters
         self.opt = torch.optim.Adam(self.head_params, lr=lr, capturable=capturable)    # :101-104
         self._graph, self._eager_runs = None, 0
         self.gamma, self.batch_size, self.target_update_interval = gamma, batch_size, target_update_interval
         self.beta_start, self.beta_frames = beta_start, beta_frames
         self.frame_idx = self.train_steps = 0
-        self.fused = (self.device.type == "cuda") if fused is None else bool(fused)
         if self.fused:
             self._init_fused(seed)
 
@@ -140,6 +140,23 @@ class DQNTrainer:
         self._noise_seed = int(seed) & (2 ** 64 - 1)
         self._td_buf = torch.zeros(self.batch_size, dtype=torch.float32, device=self.device)
         self._loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # Adam on the optimiser's own state tensors (created here the way a capturable torch Adam creates them lazily)
+        for p in self.head_params:
+            st = self.opt.state[p]
+            if not st:
+                st["step"] = torch.zeros((), dtype=torch.float32, device=self.device)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        self._adam = (_lib.PPAdamParam * len(self.head_params))(*[
+            _lib.PPAdamParam(_ptr(p), _ptr(p.grad), _ptr(self.opt.state[p]["exp_avg"]), _ptr(self.opt.state[p]["exp_avg_sq"]),
+                             _ptr(self.opt.state[p]["step"]), p.numel()) for p in self.head_params])
+        self._workspace = torch.zeros(int(self._lib.pp_dqn_workspace_floats(self.batch_size)), dtype=torch.float32, device=self.device)
+
+    def _adam_step(self):
+        g = self.opt.param_groups[0]
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pp_adam_step(self._adam, len(self.head_params), float(g["lr"]), float(g["betas"][0]),
+                                              float(g["betas"][1]), float(g["eps"]), _stream_ptr(self.device)), "pp_adam_step")
 
     def _feature_ptrs(self):
         f = self.model.features                          # frozen (:97) and identical in the target net
@@ -164,7 +181,7 @@ class DQNTrainer:
             _lib.check(self._lib.pp_dqn_head_grads(C.byref(ring), _ptr(idx), _ptr(iw), self.batch_size, *self._feature_ptrs(),
                                                    C.byref(self._on_v), C.byref(self._on_a), C.byref(self._tg_v), C.byref(self._tg_a),
                                                    int(self.model.training), int(self.target.training), float(self.gamma),
-                                                   _ptr(self._td_buf), _ptr(self._loss_buf), _ptr(sampler.prios), st),
+                                                   _ptr(self._td_buf), _ptr(self._loss_buf), _ptr(sampler.prios), _ptr(self._workspace), st),
                        "pp_dqn_head_grads")
         self._idx, self._td = idx, self._td_buf
         return self._loss_buf[0]
@@ -195,8 +212,10 @@ class DQNTrainer:
 
     def _post(self, sampler: PrioritizedSampler):
         """The rest of train_step(): optimiser step on the (rank-averaged) gradients, new priorities."""
-        self.opt.step()
-        if not self.fused:                                                             # the fused kernel wrote them
+        if self.fused:                                   # one launch; the priorities were written by pp_dqn_head_grads
+            self._adam_step()
+        else:
+            self.opt.step()
             sampler.update_priorities(self._idx, self._td)                             # :163-164
 
     def _body(self, sampler, beta, generator=None):

@@ -222,31 +222,6 @@ def test_selfplay_lockstep_ring_is_time_major_per_env_and_wraps(H, nets):
         ring.scatter(torch.zeros(4, 7), torch.zeros(4), torch.zeros(4), torch.zeros(4, 7), torch.zeros(4))
 
 
-def test_split_update_graphs_match_the_single_graph(H, monkeypatch):
-    """Several ranks: the update is two CUDA graphs around an eager NCCL all-reduce.  On one GPU (all-reduce = no-op)
-    the split form must produce the same training trajectory as the single graph."""
-    cfg = H["env_config_yaml"]
-    n = 1024
-    res = []
-    for split in ("0", "1"):
-        monkeypatch.setenv("PP_SPLIT_UPDATE_GRAPH", split)
-        torch.manual_seed(0); net_a = pp.QNet()
-        torch.manual_seed(1); net_b = pp.QNet()
-        env = pp.VecPongEnv2P(n, mode="f64", serve="philox", seed=5, **cfg)
-        env.reset()
-        trainer = pp.DQNTrainer(net_b, batch_size=128, target_update_interval=5, lr=1e-3)
-        eng = pp.SelfPlayEngine(env, pp.Policy.qnet(net_a, noisy=True), pp.Policy.qnet(net_b, noisy=True, eps=1.0), seed=3)
-        ring = pp.ReplayRing(n * 64, lockstep_envs=n)                           # deterministic row order (no cursor atomics)
-        sampler = pp.PrioritizedSampler(ring)
-        torch.manual_seed(77)                                                   # sampling + NoisyNet noise streams
-        torch.cuda.manual_seed(77)
-        out = pp.train_generation(eng, trainer, ring, sampler, 64, chunk=8, updates_per_chunk=2, epsilon=1.0)
-        assert out["updates"] == 16 and trainer._graph is not None and trainer._split == (split == "1")
-        res.append((out["mean_loss"], torch.cat([p.detach().flatten() for p in trainer.head_params]).cpu()))
-    assert res[0][0] == pytest.approx(res[1][0], rel=1e-5)
-    assert torch.allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-7)
-
-
 @pytest.mark.parametrize("prec,opp", [("f32", "rnn"), ("f16", "rnn"), ("f16", "qnet")])
 def test_train_rnn_generation_sequence_replay_and_drqn_updates(H, prec, opp):
     """DRQN training mode on one slab (scripts/train_rnn_iterative.py:728-800): the recurrent kernel writes the lock-step

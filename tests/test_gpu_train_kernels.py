@@ -68,9 +68,10 @@ def test_dqn_head_grads_kernel_matches_autograd(batch, online_train_mode):
     lib = _lib.load()
     _lib.check(lib.pp_dqn_head_grads(C.byref(rs), _ptr(idx), _ptr(iw), batch, *tr._feature_ptrs(), C.byref(tr._on_v),
                                      C.byref(tr._on_a), C.byref(tr._tg_v), C.byref(tr._tg_a), int(tr.model.training),
-                                     int(tr.target.training), tr.gamma, _ptr(td), _ptr(loss), _ptr(prios),
+                                     int(tr.target.training), tr.gamma, _ptr(td), _ptr(loss), _ptr(prios), _ptr(tr._workspace),
                                      _stream_ptr(torch.device("cuda"))), "pp_dqn_head_grads")
     torch.cuda.synchronize()
+    assert int(tr._workspace.view(torch.int32)[-8:].abs().sum()) == 0          # the ticket is back to zero: relaunchable
     assert torch.allclose(td, td_w, rtol=1e-5, atol=2e-6)
     assert abs(loss.item() - loss_w.item()) <= 1e-5 * abs(loss_w.item()) + 1e-7
     for p, gw in zip(tr.head_params, grads_w):
@@ -171,3 +172,56 @@ def test_fused_and_framework_updates_train_alike():
                                                 (list(net.fc_V.parameters()) + list(net.fc_A.parameters()))]))
     assert torch.allclose(heads_f, heads_t, rtol=1e-4, atol=1e-6)
     assert torch.allclose(prios_f, prios_t, rtol=1e-4, atol=2e-6)
+
+
+def test_adam_step_kernel_matches_torch_adam_on_its_own_state():
+    """pp_adam_step updates the parameters AND optimizer.state like torch.optim.Adam does: after 25 fused steps a torch
+    optimiser loaded from the fused one's state_dict continues identically."""
+    torch.manual_seed(4)
+    tr = pp.DQNTrainer(pp.QNet(), batch_size=64, fused=True, use_graph=False, lr=3e-3)
+    ref = [p.detach().clone().requires_grad_(True) for p in tr.head_params]
+    ref_opt = torch.optim.Adam(ref, lr=3e-3)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for step in range(25):
+        for p, q in zip(tr.head_params, ref):
+            grad = torch.randn(p.shape, generator=g, device="cuda") * (10.0 ** (step % 5 - 3))
+            p.grad.copy_(grad); q.grad = grad.clone()
+        tr._adam_step(); ref_opt.step()
+        for p, q in zip(tr.head_params, ref):
+            assert torch.allclose(p, q, rtol=2e-6, atol=1e-8), step
+    sd = tr.opt.state_dict()
+    assert all(float(st["step"]) == 25.0 for st in sd["state"].values()) and len(sd["state"]) == 8
+    for (k, st), q in zip(sd["state"].items(), ref):
+        rs = ref_opt.state[q]
+        assert torch.allclose(st["exp_avg"], rs["exp_avg"], rtol=1e-5, atol=2e-6)          # a running sum that cancels
+        assert torch.allclose(st["exp_avg_sq"], rs["exp_avg_sq"], rtol=1e-5, atol=1e-7)
+    # torch's own step() carries on from the fused state (checkpoint / resume compatibility)
+    for p, q in zip(tr.head_params, ref):
+        grad = torch.randn(p.shape, generator=g, device="cuda")
+        p.grad.copy_(grad); q.grad = grad.clone()
+    tr.opt.step(); ref_opt.step()
+    for p, q in zip(tr.head_params, ref):
+        assert torch.allclose(p, q, rtol=2e-6, atol=1e-8)
+
+
+def test_split_update_graphs_match_the_single_graph(monkeypatch):
+    """Several ranks: the update is two CUDA graphs around an eager NCCL all-reduce.  On one GPU (all-reduce = no-op) the
+    split form must train exactly like the single graph.  The batch is pinned (torch.cumsum behind the sampler is not
+    run-to-run deterministic in floating point, so whole trajectories through the real sampler are not comparable)."""
+    ring = _ring(8192, seed=3)
+    outs = []
+    for split in ("0", "1"):
+        monkeypatch.setenv("PP_SPLIT_UPDATE_GRAPH", split)
+        torch.manual_seed(2)
+        tr = pp.DQNTrainer(pp.QNet(), batch_size=128, target_update_interval=3, lr=1e-3)
+        sampler = pp.PrioritizedSampler(ring); sampler.note_new_rows()
+        g = torch.Generator(device="cuda").manual_seed(5)
+        idx = torch.randint(0, ring.capacity, (128,), generator=g, device="cuda")
+        iw = torch.rand(128, generator=g, device="cuda") + 0.1
+        sampler.sample = lambda *a, **k: (idx, iw)
+        losses = [float(tr.update(sampler)) for _ in range(10)]              # 3 eager updates, then graph replays
+        assert tr._graph is not None and tr._split == (split == "1") and tr.train_steps == 10
+        outs.append((losses, torch.cat([p.detach().flatten() for p in tr.head_params]).clone(), sampler.prios.clone(),
+                     float(tr.opt.state[tr.head_params[0]]["step"])))
+    assert outs[0][0] == outs[1][0] and len(set(outs[0][0])) == 10            # the loss moves, identically in both forms
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3] == 10.0
