@@ -310,6 +310,17 @@ int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float 
                       float *workspace, void *stream);
 int64_t pp_dqn_workspace_floats(int32_t batch);
 
+/* PrioritizedReplay.sample (scripts/train_iterative.py:64-73) on the device: `batch` slots drawn i.i.d. with
+ * probability prios[i]^alpha / sum (np.random.choice(p=probs), :68) by a two-level inverse-CDF search, and the importance
+ * weights (N P(i))^-beta / max (:71-72).  prios[capacity]: 0 = empty slot (never drawn).  *beta and *size (N = len(buffer),
+ * as a float) are read from device memory; *counter (device) is read and incremented, so a CUDA graph that contains the
+ * call draws a fresh batch at every replay.  chunk_sums: pp_per_sample_scratch_floats(capacity) floats of scratch.
+ * batch <= 4096.  Deterministic for a given (seed, *counter, prios). */
+int pp_per_sample(const float *prios, int64_t capacity, float alpha, const float *beta, const float *size, uint64_t seed,
+                  unsigned long long *counter, int32_t batch, float *chunk_sums, int64_t *idx_out, float *weights_out,
+                  void *stream);
+int64_t pp_per_sample_scratch_floats(int64_t capacity);
+
 /* optimizerB.step() of scripts/train_iterative.py:162 — torch.optim.Adam (betas, eps as given; no amsgrad, no weight
  * decay) for `count` <= 16 small tensors in one launch, IN PLACE on the parameter and on the optimiser's own state:
  *   step += 1;  m = lerp(m, g, 1 - beta1);  v = beta2 v + (1 - beta2) g^2;

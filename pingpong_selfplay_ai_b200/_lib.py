@@ -94,6 +94,8 @@ _PROTOTYPES = {
     "pp_dqn_head_grads": (C.c_int, [P(PPReplayRing), c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, P(PPNoisyLayer), P(PPNoisyLayer),
                                     P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pp_dqn_workspace_floats": (c_i64, [c_i32]),
+    "pp_per_sample": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_u64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "pp_per_sample_scratch_floats": (c_i64, [c_i64]),
     "pp_adam_step": (C.c_int, [P(PPAdamParam), c_i32, c_f64, c_f64, c_f64, c_f64, c_vp]),
     "pp_host_selfplay_eval": (C.c_int, [C.c_int, c_i64, c_i32, P(PPParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                         c_i64, c_i64, c_vp, c_vp, c_i64]),

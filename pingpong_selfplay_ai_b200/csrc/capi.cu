@@ -242,6 +242,22 @@ int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float 
 
 int64_t pp_dqn_workspace_floats(int32_t batch) { return batch > 0 ? pp::dqn_workspace_floats(batch) : 0; }
 
+int pp_per_sample(const float *prios, int64_t capacity, float alpha, const float *beta, const float *size, uint64_t seed,
+                  unsigned long long *counter, int32_t batch, float *chunk_sums, int64_t *idx_out, float *weights_out,
+                  void *stream) {
+    if (capacity <= 0 || batch <= 0 || batch > 4096) return fail(PP_E_SIZE, "pp_per_sample");
+    if (!prios || !beta || !size || !counter || !chunk_sums || !idx_out || !weights_out) return fail(PP_E_NULL, "pp_per_sample");
+    if (!(alpha >= 0.f)) return fail(PP_E_PARAM, "pp_per_sample");
+    return ok_or(pp::per_sample_launch(prios, capacity, alpha, beta, size, seed, counter, batch, chunk_sums, idx_out,
+                                       weights_out, (cudaStream_t)stream), "pp_per_sample");
+}
+
+int64_t pp_per_sample_scratch_floats(int64_t capacity) {
+    if (capacity <= 0) return 0;
+    const int64_t chunk = pp::per_chunk(capacity);
+    return (capacity + chunk - 1) / chunk;
+}
+
 int pp_adam_step(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, void *stream) {
     if (count < 0 || count > 16) return fail(PP_E_SIZE, "pp_adam_step");
     if (count > 0 && !params) return fail(PP_E_NULL, "pp_adam_step");

@@ -300,26 +300,201 @@ struct AdamParams { PPAdamParam p[16]; };
 
 __global__ void __launch_bounds__(256, 1)
 adam_step_kernel(const AdamParams ps, int count, double lr, double beta1, double beta2, double eps) {
+    __shared__ float s_step_size[16], s_bc2_sqrt[16], s_step[16];
     const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), epsf = (float)eps;
-    for (int t = 0; t < count; ++t) {
+    if ((int)threadIdx.x < count) {            // one thread per tensor: the scalars in double, like the Python floats of
+        const double step = (double)*ps.p[threadIdx.x].step + 1.0;      // torch's Adam (1 - 0.999^step cancels in fp32)
+        s_step[threadIdx.x] = (float)step;
+        s_step_size[threadIdx.x] = (float)(lr / (1.0 - pow(beta1, step)));
+        s_bc2_sqrt[threadIdx.x] = (float)sqrt(1.0 - pow(beta2, step));
+    }
+    __syncthreads();
+    int64_t total = 0;
+    for (int t = 0; t < count; ++t) total += ps.p[t].numel;
+    for (int64_t f = threadIdx.x; f < total; f += blockDim.x) {               // all tensors as one flat range: the small
+        int t = 0;                                                             // ones do not serialise behind each other
+        int64_t i = f;
+        while (i >= ps.p[t].numel) { i -= ps.p[t].numel; ++t; }
         const PPAdamParam &a = ps.p[t];
-        const double step = (double)*a.step + 1.0;                             // every thread reads the old value ...
-        // the scalars in double, like the Python floats of torch's (non-capturable) Adam: 1 - 0.999^step cancels in fp32
-        const float step_size = (float)(lr / (1.0 - pow(beta1, step)));
-        const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, step));
-        for (int64_t i = threadIdx.x; i < a.numel; i += blockDim.x) {
-            const float g = a.grad[i];
-            const float m = a.exp_avg[i] + w1 * (g - a.exp_avg[i]);                             // lerp_(grad, 1 - beta1)
-            const float v = a.exp_avg_sq[i] * b2 + w2 * (g * g);                                // mul_(beta2).addcmul_
-            a.exp_avg[i] = m; a.exp_avg_sq[i] = v;
-            a.param[i] = a.param[i] - step_size * (m / (sqrtf(v) / bc2_sqrt + epsf));          // addcdiv_
+        const float g = a.grad[i];
+        const float m = a.exp_avg[i] + w1 * (g - a.exp_avg[i]);                                 // lerp_(grad, 1 - beta1)
+        const float v = a.exp_avg_sq[i] * b2 + w2 * (g * g);                                    // mul_(beta2).addcmul_
+        a.exp_avg[i] = m; a.exp_avg_sq[i] = v;
+        a.param[i] = a.param[i] - s_step_size[t] * (m / (sqrtf(v) / s_bc2_sqrt[t] + epsf));    // addcdiv_
+    }
+    if ((int)threadIdx.x < count) *ps.p[threadIdx.x].step = s_step[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// PrioritizedReplay.sample (scripts/train_iterative.py:64-73): np.random.choice(len, batch, p = prios^alpha / sum) and
+// the importance weights (N p)^-beta / max, as a two-level inverse-CDF draw:
+//   per_chunk_sums_kernel : sum of prios^alpha over chunks of the priority array (one pass, fixed summation order)
+//   per_draw_kernel       : every CTA scans the chunk sums in shared memory (double); one WARP per sample picks the chunk
+//                           by binary search and walks it with a warp scan; writes the slot and (N p)^-beta
+//   per_normalise_kernel  : divides by the batch maximum
+// Deterministic for a given (seed, counter), unlike a device-wide floating-point cumsum.
+constexpr int S_THREADS = 256;
+constexpr int S_MAX_CHUNKS = 4096;                      // chunk sums every draw CTA keeps in shared memory (as double)
+
+__global__ void __launch_bounds__(S_THREADS)
+per_chunk_sums_kernel(const float *__restrict__ prios, int64_t capacity, int64_t chunk, float alpha, float *__restrict__ sums) {
+    __shared__ float scratch[S_THREADS / 32];
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < capacity ? lo + chunk : capacity;
+    float acc = 0.f;
+    if (hi - lo == chunk && (reinterpret_cast<uintptr_t>(prios + lo) & 15u) == 0) {       // whole chunk: 16-byte loads
+        const float4 *p4 = reinterpret_cast<const float4 *>(prios + lo);
+        for (int64_t i = threadIdx.x; i < chunk / 4; i += S_THREADS) {
+            const float4 p = p4[i];
+            acc += (p.x > 0.f ? __powf(p.x, alpha) : 0.f) + (p.y > 0.f ? __powf(p.y, alpha) : 0.f) +
+                   (p.z > 0.f ? __powf(p.z, alpha) : 0.f) + (p.w > 0.f ? __powf(p.w, alpha) : 0.f);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) *a.step = (float)step;                           // ... before one of them writes the new one
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += S_THREADS) {
+            const float p = prios[i];
+            acc += p > 0.f ? __powf(p, alpha) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < S_THREADS / 32; ++w) t += scratch[w];
+        sums[blockIdx.x] = t;
     }
 }
 
+__global__ void __launch_bounds__(S_THREADS)
+per_draw_kernel(const float *__restrict__ prios, int64_t capacity, int64_t chunk, int n_chunks, float alpha,
+                const float *__restrict__ sums, const float *__restrict__ beta, const float *__restrict__ size,
+                uint64_t seed, const unsigned long long *__restrict__ counter, int batch, int64_t *__restrict__ idx_out,
+                float *__restrict__ w_out) {
+    extern __shared__ double prefix[];                                         // inclusive prefix of the chunk sums
+    for (int i = threadIdx.x; i < n_chunks; i += S_THREADS) prefix[i] = (double)sums[i];
+    __syncthreads();
+    if (threadIdx.x < 32) {                                                    // one warp scans: n_chunks <= 4096
+        const int lane = threadIdx.x, per = (n_chunks + 31) / 32;
+        double run = 0.0;
+        for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < n_chunks) { run += prefix[i]; prefix[i] = run; } }
+        double off = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
+        off -= run;                                                            // exclusive offset of this lane's segment
+        for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < n_chunks) prefix[i] += off; }
+    }
+    __syncthreads();
+    const double total = prefix[n_chunks - 1];
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (S_THREADS / 32) + (threadIdx.x >> 5);          // one warp per sample
+    if (r >= batch) return;
+    const unsigned long long ctr = *counter;
+    const uint4 rnd = philox4x32_10((uint32_t)r, 0x70657273u, (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u = fmin(u53(rnd.x, rnd.y) * total, total * (1.0 - 1e-15));   // strictly inside the last live chunk
+    int lo = 0, hi = n_chunks - 1;                                             // first chunk with prefix > u
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (prefix[mid] > u) hi = mid; else lo = mid + 1; }
+    const float rem = (float)(u - (lo > 0 ? prefix[lo - 1] : 0.0));
+    const int64_t c_lo = (int64_t)lo * chunk, c_hi = c_lo + chunk < capacity ? c_lo + chunk : capacity;
+    float run = 0.f, pa_sel = 0.f;
+    int64_t pick = -1, last_pos = -1;
+    float last_pa = 0.f;
+    // 512 slots per step: every lane takes 16 consecutive ones (four independent 16-byte loads in flight), the lane sums
+    // go through a warp scan, the lane that crosses `rem` resolves the slot among its 16
+    for (int64_t base = c_lo; base < c_hi && pick < 0; base += 512) {
+        const int64_t l0 = base + lane * 16;
+        float pa[16];
+        if (l0 + 16 <= c_hi && (reinterpret_cast<uintptr_t>(prios + l0) & 15u) == 0) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(prios + l0);
+            const float4 q0 = p4[0], q1 = p4[1], q2 = p4[2], q3 = p4[3];
+            const float raw[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pa[e] = raw[e] > 0.f ? __powf(raw[e], alpha) : 0.f;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float p = l0 + e < c_hi ? prios[l0 + e] : 0.f;
+                pa[e] = p > 0.f ? __powf(p, alpha) : 0.f;
+            }
+        }
+        float lane_sum = 0.f;
+        int last_e = -1;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { lane_sum += pa[e]; if (pa[e] > 0.f) last_e = e; }
+        float inc = lane_sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        // this lane's candidate: the first of its slots whose running sum passes rem (its last live slot if rounding hides it)
+        float cum = run + (inc - lane_sum);
+        int cand = -1;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { cum += pa[e]; if (cand < 0 && pa[e] > 0.f && cum > rem) cand = e; }
+        if (cand < 0) cand = last_e;
+        float cand_pa = 0.f, last_lane_pa = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { if (e == cand) cand_pa = pa[e]; if (e == last_e) last_lane_pa = pa[e]; }
+        const unsigned hit = __ballot_sync(0xffffffffu, lane_sum > 0.f && run + inc > rem);
+        const unsigned pos = __ballot_sync(0xffffffffu, lane_sum > 0.f);
+        if (pos) {
+            const int l = 31 - __clz(pos);
+            last_pos = base + l * 16 + __shfl_sync(0xffffffffu, last_e, l);
+            last_pa = __shfl_sync(0xffffffffu, last_lane_pa, l);
+        }
+        if (hit) {
+            const int l = __ffs(hit) - 1;
+            pick = base + l * 16 + __shfl_sync(0xffffffffu, cand, l);
+            pa_sel = __shfl_sync(0xffffffffu, cand_pa, l);
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (pick < 0) { pick = last_pos; pa_sel = last_pa; }                       // rounding at the chunk's end: its last live slot
+    if (pick < 0) { pick = 0; pa_sel = 0.f; }                                  // (an all-zero chunk cannot be chosen: its sum is 0)
+    if (lane == 0) {
+        idx_out[r] = pick;
+        const float prob = (float)((double)pa_sel / total);
+        w_out[r] = powf(*size * prob, -*beta);                                 // (N * P(i))^-beta  :71
+    }
+}
+
+__global__ void __launch_bounds__(S_THREADS)
+per_normalise_kernel(float *__restrict__ w, int batch, unsigned long long *counter) {
+    __shared__ float scratch[S_THREADS / 32];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < batch; i += S_THREADS) m = fmaxf(m, w[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int k = 0; k < S_THREADS / 32; ++k) m = fmaxf(m, scratch[k]);
+    for (int i = threadIdx.x; i < batch; i += S_THREADS) w[i] = w[i] / m;      // weights /= weights.max()  :72
+    if (threadIdx.x == 0) *counter = *counter + 1;                             // the next launch draws a fresh batch
+}
+
 }  // namespace
+
+int64_t per_chunk(int64_t capacity) {                  // chunk length: a multiple of 1024, at most S_MAX_CHUNKS chunks
+    int64_t chunk = 4096;
+    while ((capacity + chunk - 1) / chunk > S_MAX_CHUNKS) chunk *= 2;
+    return chunk;
+}
+
+int per_sample_launch(const float *prios, int64_t capacity, float alpha, const float *beta, const float *size, uint64_t seed,
+                      unsigned long long *counter, int32_t batch, float *chunk_sums, int64_t *idx_out, float *w_out,
+                      cudaStream_t stream) {
+    const int64_t chunk = per_chunk(capacity);
+    const int n_chunks = (int)((capacity + chunk - 1) / chunk);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(per_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_MAX_CHUNKS * sizeof(double)));
+        if (err != cudaSuccess) return (int)err;
+        attr_set = true;
+    }
+    per_chunk_sums_kernel<<<n_chunks, S_THREADS, 0, stream>>>(prios, capacity, chunk, alpha, chunk_sums);
+    per_draw_kernel<<<(batch + S_THREADS / 32 - 1) / (S_THREADS / 32), S_THREADS, (size_t)n_chunks * sizeof(double), stream>>>(
+        prios, capacity, chunk, n_chunks, alpha, chunk_sums, beta, size, seed, counter, batch, idx_out, w_out);
+    per_normalise_kernel<<<1, S_THREADS, 0, stream>>>(w_out, batch, counter);
+    return (int)cudaGetLastError();
+}
 
 int adam_step_launch(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, cudaStream_t stream) {
     AdamParams pack{};

@@ -47,6 +47,10 @@ int dqn_head_grads_launch(const PPReplayRing &ring, const int64_t *idx, const fl
                           const PPNoisyLayer &tg_v, const PPNoisyLayer &tg_a, int noisy_online, int noisy_target, float gamma,
                           float *td_out, float *loss_out, float *prios, float *workspace, cudaStream_t stream);
 int64_t dqn_workspace_floats(int32_t batch);
+int64_t per_chunk(int64_t capacity);
+int per_sample_launch(const float *prios, int64_t capacity, float alpha, const float *beta, const float *size, uint64_t seed,
+                      unsigned long long *counter, int32_t batch, float *chunk_sums, int64_t *idx_out, float *w_out,
+                      cudaStream_t stream);
 int adam_step_launch(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, cudaStream_t stream);
 int noisy_reset_launch(const PPNoisyLayer *layers, int32_t count, uint64_t seed, unsigned long long *counter, cudaStream_t stream);
 int pack_qnet_launch(const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &v,

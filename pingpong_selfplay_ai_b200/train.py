@@ -88,6 +88,32 @@ class PrioritizedSampler:
         w = (self.size_t * (pa[idx] / total)).pow(-beta)
         return idx, w / w.max()
 
+    def sample_fused(self, batch_size: int, beta, seed: int = 0):
+        """The same draw in three hand-written launches (pp_per_sample: chunk sums, warp-per-sample two-level inverse CDF,
+        normalisation) instead of ~14 framework kernels; deterministic for a given seed and call count.  `beta`: float or
+        0-d device tensor.  Returns static buffers (valid until the next call): what a CUDA graph wants."""
+        if self.seen == 0:
+            raise RuntimeError("sampling from an empty replay ring")
+        dev = self.prios.device
+        if getattr(self, "_f_batch", None) != batch_size:
+            self._f_lib = _lib.load()
+            self._f_batch = batch_size
+            self._f_idx = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+            self._f_w = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+            self._f_sums = torch.zeros(int(self._f_lib.pp_per_sample_scratch_floats(self.ring.capacity)), dtype=torch.float32, device=dev)
+            self._f_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._f_beta = torch.zeros((), dtype=torch.float32, device=dev)
+        if torch.is_tensor(beta):
+            beta_t = beta
+        else:
+            self._f_beta.fill_(float(beta))
+            beta_t = self._f_beta
+        with torch.cuda.device(dev):
+            _lib.check(self._f_lib.pp_per_sample(_ptr(self.prios), self.ring.capacity, self.alpha, _ptr(beta_t), _ptr(self.size_t),
+                                                 int(seed) & (2 ** 64 - 1), _ptr(self._f_counter), batch_size, _ptr(self._f_sums),
+                                                 _ptr(self._f_idx), _ptr(self._f_w), _stream_ptr(dev)), "pp_per_sample")
+        return self._f_idx, self._f_w
+
     def update_priorities(self, idx, td_abs):
         self.prios[idx] = td_abs.detach().abs().to(torch.float32) + 1e-6           # :74-76
 
@@ -172,8 +198,11 @@ class DQNTrainer:
                                               _ptr(blob), st), "pp_pack_qnet")
 
     def _pre_fused(self, sampler: "PrioritizedSampler", beta, generator=None):
-        idx, iw = sampler.sample(self.batch_size, beta, generator)
-        idx, iw = idx.contiguous(), iw.to(torch.float32).contiguous()
+        if generator is None and hasattr(sampler, "sample_fused") and "sample" not in vars(sampler):
+            idx, iw = sampler.sample_fused(self.batch_size, beta, self._noise_seed)
+        else:                                            # an explicit torch generator (or a patched sampler): framework path
+            idx, iw = sampler.sample(self.batch_size, beta, generator)
+            idx, iw = idx.contiguous(), iw.to(torch.float32).contiguous()
         ring = sampler.ring.struct()
         st = _stream_ptr(self.device)
         with torch.cuda.device(self.device):

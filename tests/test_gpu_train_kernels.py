@@ -225,3 +225,45 @@ def test_split_update_graphs_match_the_single_graph(monkeypatch):
                      float(tr.opt.state[tr.head_params[0]]["step"])))
     assert outs[0][0] == outs[1][0] and len(set(outs[0][0])) == 10            # the loss moves, identically in both forms
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3] == 10.0
+
+
+@pytest.mark.parametrize("capacity", [8192, 50000, 1 << 22])
+def test_per_sample_kernels_draw_from_the_priority_distribution(capacity):
+    """pp_per_sample: slots are drawn with probability p^alpha / sum, empty slots never, importance weights are
+    (N P(i))^-beta / max (scripts/train_iterative.py:64-73)."""
+    g = torch.Generator(device="cuda").manual_seed(capacity)
+    ring = pp.ReplayRing(capacity)
+    s = pp.PrioritizedSampler(ring, alpha=0.6)
+    filled = capacity - capacity // 5                        # the tail of the ring is still empty
+    pr = torch.rand(filled, generator=g, device="cuda") ** 3 * 4 + 1e-6
+    pr[::7] = 50.0                                           # a heavy class: every 7th slot
+    s.prios[:filled] = pr
+    s.seen = filled; s.size_t.fill_(float(filled))
+    batch, reps, beta = 4096, 60, 0.7
+    counts = torch.zeros(capacity, dtype=torch.int64, device="cuda")
+    for _ in range(reps):
+        idx, w = s.sample_fused(batch, beta, seed=11)
+        counts += torch.bincount(idx, minlength=capacity)
+        assert int(idx.min()) >= 0 and int(idx.max()) < filled and float(w.max()) == 1.0 and float(w.min()) > 0
+    pa = s.prios.double() ** 0.6
+    probs = pa / pa.sum()
+    want = (filled * probs[idx]) ** (-beta)
+    assert torch.allclose(w.double(), want / want.max(), rtol=2e-5)
+    total = batch * reps
+    heavy = torch.zeros(capacity, dtype=torch.bool, device="cuda"); heavy[:filled:7] = True
+    for mask in (heavy, ~heavy):                             # class frequencies within 4 sigma
+        p = float(probs[mask].sum()); f = float(counts[mask].sum()) / total
+        assert abs(f - p) < 4 * (p * (1 - p) / total) ** 0.5 + 1e-4, (f, p)
+    # per-region frequencies (64 contiguous regions) follow the probabilities
+    edges = torch.linspace(0, capacity, 65, device="cuda").long()
+    cs_p = torch.cat([torch.zeros(1, device="cuda", dtype=torch.float64), probs.cumsum(0)])
+    cs_c = torch.cat([torch.zeros(1, device="cuda", dtype=torch.int64), counts.cumsum(0)])
+    p_reg = cs_p[edges[1:]] - cs_p[edges[:-1]]; f_reg = (cs_c[edges[1:]] - cs_c[edges[:-1]]).double() / total
+    assert float(((f_reg - p_reg).abs() - 5 * (p_reg * (1 - p_reg) / total).clamp(min=0).sqrt()).max()) < 1e-4
+    # deterministic for (seed, call count); a fresh batch per call
+    s2 = pp.PrioritizedSampler(ring, alpha=0.6); s2.prios.copy_(s.prios); s2.seen = filled; s2.size_t.fill_(float(filled))
+    s3 = pp.PrioritizedSampler(ring, alpha=0.6); s3.prios.copy_(s.prios); s3.seen = filled; s3.size_t.fill_(float(filled))
+    a1, _ = s2.sample_fused(256, beta, seed=5); a1 = a1.clone()
+    a2, _ = s2.sample_fused(256, beta, seed=5); a2 = a2.clone()
+    b1, _ = s3.sample_fused(256, beta, seed=5)
+    assert torch.equal(a1, b1) and not torch.equal(a1, a2)

@@ -31,7 +31,7 @@ def timed(name, fn, reps=200):
 timed("pp_dqn_head_grads (batch 256)", grads)
 timed("pp_noisy_reset (4 layers)", noise)
 timed("opt.step (torch Adam, capturable)", tr.opt.step)
-timed("sampler.sample (4 M rows)", lambda: sampler.sample(256, 0.5))
+timed("sampler.sample (4 M rows)", lambda: sampler.sample(256, 0.5)); timed("sampler.sample_fused", lambda: sampler.sample_fused(256, 0.5))
 if hasattr(tr, "_adam_step"):
     timed("pp_adam_step", tr._adam_step)
 g = torch.cuda.CUDAGraph()
