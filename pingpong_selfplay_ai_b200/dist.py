@@ -66,6 +66,29 @@ def allreduce_mean_grads(params) -> None:
         off += g.numel()
 
 
+def flatten_grads_(params) -> torch.Tensor:
+    """Make the .grad tensors of `params` views into ONE flat buffer (values preserved) and return it, so that the
+    all-reduce needs no gather / scatter copies: allreduce_mean_flat_(flat) then updates every p.grad in place."""
+    params = list(params)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+    off = 0
+    for p in params:
+        view = flat[off:off + p.numel()].view_as(p)
+        if p.grad is not None:
+            view.copy_(p.grad)
+        p.grad = view
+        off += p.numel()
+    return flat
+
+
+def allreduce_mean_flat_(flat: torch.Tensor) -> None:
+    """Average a flat gradient buffer over ranks: one collective and one scaling kernel."""
+    if not is_parallel():
+        return
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(dist.get_world_size())
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Timing helper: the slowest rank defines the step time."""
     if not is_parallel():

@@ -155,8 +155,8 @@ class DQNTrainer:
 
     def _init_fused(self, seed: int):
         self._lib = _lib.load()
-        for p in self.head_params:                       # the kernel writes the gradients Adam reads: fixed tensors
-            p.grad = torch.zeros_like(p)
+        # the kernel writes the gradients Adam reads: fixed tensors, all views into one flat buffer (one collective)
+        self._flat_grad = ppd.flatten_grads_(self.head_params)
         m, t = self.model, self.target
         self._on_v, self._on_a = self._layer(m.fc_V, True), self._layer(m.fc_A, True)
         self._tg_v, self._tg_a = self._layer(t.fc_V, False), self._layer(t.fc_A, False)
@@ -249,9 +249,15 @@ class DQNTrainer:
 
     def _body(self, sampler, beta, generator=None):
         loss = self._pre(sampler, beta, generator)
-        ppd.allreduce_mean_grads(self.head_params)                                     # one NCCL all-reduce of 520 floats
+        self._allreduce_grads()                                                        # one NCCL all-reduce of 520 floats
         self._post(sampler)
         return loss
+
+    def _allreduce_grads(self):
+        if getattr(self, "_flat_grad", None) is not None:
+            ppd.allreduce_mean_flat_(self._flat_grad)
+        else:
+            ppd.allreduce_mean_grads(self.head_params)
 
     def update(self, sampler: PrioritizedSampler, generator=None):
         """One train_step().  Returns the loss (a 0-d device tensor: no host sync), or None while the ring holds fewer
@@ -297,7 +303,7 @@ class DQNTrainer:
         self._beta_t.fill_(beta)
         self._graph.replay()
         if self._split:
-            ppd.allreduce_mean_grads(self.head_params)
+            self._allreduce_grads()
             self._graph_post.replay()
         return self._loss_t.clone()
 

@@ -136,6 +136,8 @@ class DRQNTrainer(DQNTrainer):
         self.gamma, self.batch_size, self.target_update_interval = gamma, batch_size, target_update_interval
         self.grad_clip_norm, self.min_episodes = float(grad_clip_norm), int(batch_size * min_episodes_factor)
         self.frame_idx = self.train_steps = 0
+        self.fused = False                               # the update is PyTorch (cuDNN LSTM backward)
+        self._flat_grad = ppd.flatten_grads_(self.params)     # .grad tensors are views of one buffer: one collective
 
     def loss_on(self, obs, act, rew, next_obs, done):
         """The loss of train_step_rnn for given windows (:468-507)."""
@@ -163,7 +165,7 @@ class DRQNTrainer(DQNTrainer):
 
     def _body(self, sampler, beta=None, generator=None):
         loss = self._pre(sampler, beta, generator)
-        ppd.allreduce_mean_grads(self.params)                                            # one NCCL all-reduce of 175 k floats
+        self._allreduce_grads()                                                          # one NCCL all-reduce of 175 k floats
         self._post(sampler)
         return loss
 

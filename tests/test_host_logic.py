@@ -132,6 +132,12 @@ gathered = [torch.zeros(520) for _ in range(2)]
 dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local_g]))
 want = (gathered[0] + gathered[1]) / 2
 assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in heads]), want, atol=1e-7)
+for p, g in zip(heads, local_g):                      # the same through one flat buffer that the .grad tensors view
+    p.grad = g.clone()
+flat = ppd.flatten_grads_(heads)
+assert flat.numel() == 520 and all(p.grad.data_ptr() >= flat.data_ptr() for p in heads)
+ppd.allreduce_mean_flat_(flat)
+assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in heads]), want, atol=1e-7) and torch.allclose(flat, want, atol=1e-7)
 assert ppd.max_over_ranks(float(rank)) == 1.0
 t = torch.full((3,), float(rank)); ppd.broadcast_(t, 0); assert t.tolist() == [0.0, 0.0, 0.0]
 dist.destroy_process_group()
