@@ -130,8 +130,9 @@ class DRQNTrainer(DQNTrainer):
         self.params = [p for p in self.model.parameters()]
         self.head_params = self.params                     # what DQNTrainer's helpers call the trainable set
         self.use_graph = use_graph
-        capturable = use_graph and self.device.type == "cuda"
-        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=capturable)           # :335
+        on_cuda = self.device.type == "cuda"
+        # fused: ONE multi-tensor kernel for the 20 parameter tensors (the capturable foreach form is ~100 tiny kernels)
+        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=use_graph and on_cuda, fused=True if on_cuda else None)  # :335
         self._graph, self._eager_runs = None, 0
         self.gamma, self.batch_size, self.target_update_interval = gamma, batch_size, target_update_interval
         self.grad_clip_norm, self.min_episodes = float(grad_clip_norm), int(batch_size * min_episodes_factor)
