@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on that fits one GPU): 65 536 lock-step
 envs per GPU, random-init QNet A (torch.manual_seed(0)) vs QNet B (seed 1), eval-mode weights, greedy, auto-reset
 with device (Philox) serves, fp64 bit-exact env arithmetic.  One "step" = one launch of the fused self-play kernel
-= `--lockstep` (64) lock-step env steps of every env.  Weak scaling: every rank owns its own 65 536-env slab; the
+= `--lockstep` (256) lock-step env steps of every env.  Weak scaling: every rank owns its own 65 536-env slab; the
 only collective is the all-reduce of the 8 counters at the end of the timed region.
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the
@@ -39,8 +39,9 @@ UNIT = "env-steps/s"
 FLOP_PER_ENV_STEP = 19200            # 2 players x 2 x 4800 MAC
 BYTES_PER_STEP_F64 = 203             # K1 single step, all outputs materialised, fp64 mode
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/):
-NCU_TRAFFIC = {"selfplay_tc_kernel": 5.083904e6 + 27.136e3,      # r01_selfplay_r01b_metrics.txt, 65536 envs x 64 steps
-               "selfplay_kernel": 5.094144e6 + 15.36e3}           # r01_selfplay_r01_metrics.txt, same shape
+NCU_TRAFFIC = {("selfplay_tc_kernel", 256): 5.086208e6 + 56.32e3,      # r01_selfplay_tc256_metrics.txt, 65536 envs x 256 steps
+               ("selfplay_tc_kernel", 64): 5.083904e6 + 27.136e3,      # r01_selfplay_r01b_metrics.txt, 65536 envs x 64 steps
+               ("selfplay_kernel", 64): 5.094144e6 + 15.36e3}           # r01_selfplay_r01_metrics.txt, same shape
 NCU_K1_TRAFFIC_PER_ENV = (293.624576e6 + 499.684352e6) / 4194304   # r01_k1_r01b_metrics.txt: 189.1 B per env-step at 4 M envs
 
 
@@ -249,7 +250,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--lockstep", type=int, default=64, help="lock-step env steps per launch")
+    ap.add_argument("--lockstep", type=int, default=None,
+                    help="lock-step env steps per launch (default: 256 for the headline workload, 64 for the others)")
     ap.add_argument("--mode", default="f64", choices=["f64", "f32"])
     ap.add_argument("--precision", default="f16", choices=["f32", "f16"],
                     help="QNet path: f16 = tcgen05 tensor cores (fp16 hi/lo operands, fp32 accumulate, ~1e-6 of fp32); "
@@ -266,6 +268,8 @@ def main():
     ap.add_argument("--k1-envs", type=int, default=16 << 20, help="envs of the single-step HBM roofline measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.lockstep is None:
+        args.lockstep = 256 if args.workload == "qnet" else 64
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -355,7 +359,7 @@ def main():
     tf = value / world * flop / 1e12
     kname = ("selfplay_rnn_tc_kernel" if args.precision == "f16" else "selfplay_rnn_kernel") if args.workload == "rnn" else \
         ("selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel")
-    traffic = NCU_TRAFFIC.get(kname) if (args.envs, args.lockstep, args.mode) == (65536, 64, "f64") else None
+    traffic = NCU_TRAFFIC.get((kname, args.lockstep)) if (args.envs, args.mode) == (65536, "f64") else None
     line["roofline"] = {"bound": "tensor", "kernel": ("selfplay_rnn_tc_kernel" if args.precision == "f16" else "selfplay_rnn_kernel") if args.workload == "rnn" else ("selfplay_tc_kernel" if args.precision == "f16" else "selfplay_kernel"), "achieved": tf, "peak": peaks["bf16_sustained"],
                         "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"], "traffic": traffic,
                         "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture of this shape (profiles/); "
