@@ -154,12 +154,22 @@ def _records(id_a, id_b, score_a, score_b, stamp):
 
 def run_tournament(env_cfg: dict, database: dict, db_path, match_plan: list, rnn_arch: dict | None = None,
                    device="cuda", precision: str = "f32", mode: str = "f64", seed: int = 0, concurrent: int = 8,
-                   root: str = ".", agents: dict | None = None, max_steps: int = 1 << 20, on_error=print) -> dict:
+                   root: str = ".", agents: dict | None = None, max_steps: int = 1 << 20, on_error=print,
+                   shard: tuple | None = None, match_factory=None) -> dict:
     """Play every pairing of `match_plan`, append one record per game to database['match_history'] and save the database
     after each pairing.  Up to `concurrent` pairings are in flight on their own CUDA streams (a pairing of 100 games
     fills one SM).  `agents` may carry already loaded Agent objects by id; the others are loaded from the database's
     model records, and a model that fails to load only cancels its own pairings, as in the reference (:268-289).
+    Several ranks (torch.distributed initialised, or shard=(rank, world)): pairing k is played by rank k % world with
+    the same seed as on one GPU, results are gathered, EVERY rank extends its database identically (plan order; timestamps aside) and
+    rank 0 alone writes the file — pairings are independent, so there is no data-path collective.
     Returns {pair: (score_a, score_b, ep_len)}."""
+    from . import dist as ppd
+    import torch.distributed as tdist
+    if shard is None and ppd.is_parallel():
+        shard = (tdist.get_rank(), tdist.get_world_size())
+    rank, world = shard if shard is not None else (0, 1)
+    make = match_factory or _Match
     device = torch.device(device)
     info = {m["id"]: m for m in database["models"]}
     agents = dict(agents or {})
@@ -171,28 +181,51 @@ def run_tournament(env_cfg: dict, database: dict, db_path, match_plan: list, rnn
         except Exception as e:                                                # noqa: BLE001 — reference behaviour
             on_error(f"[arena] loading model {mid!r} failed: {e}")
     results, flight = {}, []
-    streams = [torch.cuda.Stream(device) for _ in range(max(1, int(concurrent)))]
+    streams = [torch.cuda.Stream(device) for _ in range(max(1, int(concurrent)))] if match_factory is None else [object() for _ in range(max(1, int(concurrent)))]
 
-    def land(m: _Match):
-        sa, sb, ln = m.results()
+    def record(ida, idb, sa, sb):
         stamp = datetime.now(timezone.utc).strftime("%Y-%m-%dT%H:%M:%S.%f") + "Z"
-        database["match_history"].extend(_records(m.a.id, m.b.id, sa, sb, stamp))
-        if db_path is not None:
-            save_database(db_path, database)
+        database["match_history"].extend(_records(ida, idb, sa, sb, stamp))
+
+    def land(m):
+        sa, sb, ln = m.results()
         results[(m.a.id, m.b.id)] = (sa, sb, ln)
+        if world == 1:                                                        # one process: record and save as we go
+            record(m.a.id, m.b.id, sa, sb)
+            if db_path is not None:
+                save_database(db_path, database)
 
     for k, match in enumerate(match_plan):
         ida, idb = match["p1_id"], match["p2_id"]
         if ida not in agents or idb not in agents:
-            on_error(f"[arena] skipping {ida} vs {idb}: a model failed to load")
+            if rank == 0:
+                on_error(f"[arena] skipping {ida} vs {idb}: a model failed to load")
+            continue
+        if k % world != rank:
             continue
         if len(flight) == len(streams):
             land(flight.pop(0))
         used = {id(m.stream) for m in flight}
         stream = next(s for s in streams if id(s) not in used)
-        m = _Match(env_cfg, agents[ida], agents[idb], match["episodes_to_run"], seed + k, precision, mode, device, stream)
+        m = make(env_cfg, agents[ida], agents[idb], match["episodes_to_run"], seed + k, precision, mode, device, stream)
         m.launch(max_steps)
         flight.append(m)
     while flight:
         land(flight.pop(0))
+    if world > 1:
+        mine = {k: tuple(np.asarray(v) for v in val) for k, val in results.items()}
+        if tdist.is_available() and tdist.is_initialized():
+            parts = [None] * world
+            tdist.all_gather_object(parts, mine)
+        else:                                                                 # shard=(rank, world) without a process group:
+            parts = [mine]                                                    # the caller merges the ranks' return values
+        results = {}
+        for part in parts:
+            results.update(part)
+        for match in match_plan:                                              # plan order: identical on every rank
+            key = (match["p1_id"], match["p2_id"])
+            if key in results:
+                record(key[0], key[1], results[key][0], results[key][1])
+        if db_path is not None and rank == 0:
+            save_database(db_path, database)
     return results

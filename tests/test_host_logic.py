@@ -162,3 +162,60 @@ def test_gloo_world_size_2_counters_and_grad_allreduce(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     # the two workers share the pipe: their lines may interleave character-wise
     assert r.stdout.count("ok") == 2 and sorted(c for c in r.stdout if c.isdigit()) == ["0", "1"], r.stdout
+
+
+_ARENA_WORKER = r"""
+import copy, os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PP_ROOT"])
+from pingpong_selfplay_ai_b200 import arena, checkpoint as ck, dist as ppd
+rank, world, _ = ppd.init_from_env("gloo")
+
+class StubMatch:                                   # stands in for a pairing on the device: scores are a function of the seed
+    def __init__(self, env_cfg, a, b, episodes, seed, precision, mode, device, stream):
+        self.a, self.b, self.n, self.seed, self.stream = a, b, episodes, seed, stream
+    def launch(self, max_steps):
+        pass
+    def results(self):
+        rs = np.random.RandomState(self.seed)
+        win_a = rs.rand(self.n) < 0.5
+        lose = rs.randint(0, 3, self.n)
+        return np.where(win_a, 3, lose), np.where(win_a, lose, 3), rs.randint(5, 50, self.n)
+
+models = [{"id": f"bot{k}", "type": "HardcodedBallFollower", "path": "N/A"} for k in range(5)]
+agents = {m["id"]: ck.Agent(m) for m in models}
+db = {"models": list(models), "match_history": []}
+plan = arena.create_match_plan(db, 7)
+assert len(plan) == 10
+path = os.path.join(os.environ["PP_TMP"], f"db_rank{rank}.json")
+res = arena.run_tournament({}, db, path, plan, agents=agents, seed=5, device="cpu", match_factory=StubMatch, concurrent=3)
+one = {"models": list(models), "match_history": []}
+res1 = arena.run_tournament({}, one, None, plan, agents=agents, seed=5, device="cpu", match_factory=StubMatch, shard=(0, 1))
+strip = lambda h: [{k: v for k, v in r.items() if k != "timestamp"} for r in h]
+assert strip(db["match_history"]) == strip(one["match_history"]) and len(db["match_history"]) == 70
+assert res.keys() == res1.keys() and all(np.array_equal(res[k][0], res1[k][0]) for k in res)
+assert os.path.exists(path) == (rank == 0)          # rank 0 alone writes the file
+assert arena.create_match_plan(db, 7) == []
+dist.barrier()
+dist.destroy_process_group()
+sys.stdout.write(f"ok {rank}\n"); sys.stdout.flush()
+"""
+
+
+def test_gloo_world_size_2_tournament_pairings_shard_over_ranks(tmp_path):
+    """arena.run_tournament with two ranks: pairing k runs on rank k % 2 with the single-GPU seed, both ranks end with
+    the single-process history, rank 0 writes the database (the matches themselves are stubbed: no GPU here)."""
+    script = tmp_path / "arena_worker.py"
+    script.write_text(_ARENA_WORKER)
+    env = dict(os.environ, PP_ROOT=ROOT, PP_TMP=str(tmp_path), OMP_NUM_THREADS="1")
+    import socket
+    for attempt in range(3):
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                           capture_output=True, text=True, env=env, timeout=240)
+        if r.returncode == 0 or "AssertionError" in r.stderr:
+            break
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2 and sorted(c for c in r.stdout if c.isdigit()) == ["0", "1"], r.stdout
