@@ -38,7 +38,7 @@ __device__ __forceinline__ float4 qnet_features4(const float *__restrict__ sw, c
         acc.z = fmaf(w.z, obs[k], acc.z); acc.w = fmaf(w.w, obs[k], acc.w);
     }
     __syncwarp();                                                              // the row's previous h1 has been consumed
-    reinterpret_cast<float *>(h1row)[pt * 4 + 0] = relu(acc.x); h1row[pt * 4 + 1] = relu(acc.y);
+    h1row[pt * 4 + 0] = relu(acc.x); h1row[pt * 4 + 1] = relu(acc.y);
     h1row[pt * 4 + 2] = relu(acc.z); h1row[pt * 4 + 3] = relu(acc.w);
     __syncwarp();                                                              // the sixteen lanes of a row sit in one warp
     const float4 *w2 = reinterpret_cast<const float4 *>(sw + PP_QNET_W2T) + pt;
@@ -115,11 +115,11 @@ dqn_head_grads_kernel(const PPReplayRing ring, const int64_t *__restrict__ idx, 
     float *sw = smem;                                                          // feature weights
     float4 *head_on = reinterpret_cast<float4 *>(smem + D_FEAT_FLOATS);        // [65]
     float4 *head_tg = head_on + 65;                                            // [65]
-    float *h2s = reinterpret_cast<float *>(head_tg + 65);                      // [64][65]
-    float *g_s = h2s + D_ROWS * D_H2_STRIDE;                                   // [64] dL/dQ(s, a)
-    int *a_s = reinterpret_cast<int *>(g_s + D_ROWS);                          // [64] action taken
+    float *h2s = reinterpret_cast<float *>(head_tg + 65);                      // [D_ROWS][65] hidden activations of s
+    float *g_s = h2s + D_ROWS * D_H2_STRIDE;                                   // [D_ROWS] dL/dQ(s, a)
+    int *a_s = reinterpret_cast<int *>(g_s + D_ROWS);                          // [D_ROWS] action taken
     float *scratch = reinterpret_cast<float *>(a_s + D_ROWS);                  // [8]
-    float *h1s = scratch + 8;                                                  // [64][65] first-layer activations per row
+    float *h1s = scratch + 8;                                                  // [D_ROWS][65] first-layer activations per row
     __shared__ int is_last;
     const int tid = threadIdx.x, tiles = gridDim.x;
     float *ws_td = ws + (size_t)tiles * D_PART;
