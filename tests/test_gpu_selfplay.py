@@ -222,6 +222,55 @@ def test_selfplay_lockstep_ring_is_time_major_per_env_and_wraps(H, nets):
         ring.scatter(torch.zeros(4, 7), torch.zeros(4), torch.zeros(4), torch.zeros(4, 7), torch.zeros(4))
 
 
+@pytest.mark.parametrize("kind", ["tc_lockstep", "tc_append", "rnn_tc_lockstep", "rnn_lockstep"])
+def test_replay_rows_of_the_tensor_core_and_recurrent_kernels_match_an_oracle_replay(H, nets, kind):
+    """Players on the reduced-precision paths may act differently from the oracle's, so the ring is checked against an
+    ORACLE REPLAY OF THE KERNEL'S OWN ACTIONS: at every step B's observation, action, reward, terminal-or-next
+    observation and done flag of every env must be the oracle's, bit for bit (scripts/train_iterative.py:243)."""
+    cfg = H["env_config_yaml"]
+    n, K, T = 300, 48, 64
+    pool = gu.make_pool(9, n, 8, cfg, "f64")
+    env = pp.VecPongEnv2P(n, mode="f64", serve=pool, **cfg)
+    env.reset()
+    b = gu.oracle_batch_like(env, "f64")
+    if kind.startswith("tc"):
+        pa, pb = pp.Policy.qnet(nets["seed1"], precision="f16"), pp.Policy.qnet(nets["seed0"], precision="f16", eps=0.3)
+    else:
+        prec = "f16" if kind.startswith("rnn_tc") else "f32"
+        torch.manual_seed(3); ra = pp.QNetRNN()
+        torch.manual_seed(4); rb = pp.QNetRNN()
+        pa = pp.Policy.qnetrnn(ra, num_envs=n, precision=prec)
+        pb = pp.Policy.qnetrnn(rb, num_envs=n, precision=prec, eps=0.3)
+    lockstep = kind.endswith("lockstep")
+    ring = pp.ReplayRing(n * T, lockstep_envs=n if lockstep else 0)
+    eng = pp.SelfPlayEngine(env, pa, pb, seed=5)
+    acts = np.concatenate([gu.np_of(eng.run(k, ring=ring, want_actions=True)["actions"]) for k in (20, K - 20)])
+    assert int(ring.head.item()) == n * K
+    p = po.make_params(cfg)
+    got = {k: gu.np_of(getattr(ring, k)) for k in ("obs", "act", "rew", "next_obs", "done")}
+    dones, want_rows = 0, []
+    for t in range(K):
+        _, ob = po.observe(b)
+        tr = po.rollout(p, b, acts[t:t + 1], pool, trace=True)
+        real, flags = tr["trace_real"][0], tr["trace_int"][0, 3]              # post-step, pre-reset state
+        nxt = np.stack([real[0], real[1], real[2], real[3], real[6], real[5], real[4]], 1).astype(np.float32)   # _get_obs_for_B
+        rew = np.where(flags & 4, 1.0, np.where(flags & 2, -1.0, 0.0)).astype(np.float32)
+        done = (flags & 1).astype(np.uint8)
+        dones += int(done.sum())
+        rows = slice(t * n, (t + 1) * n)
+        if lockstep:
+            assert np.array_equal(got["obs"][rows], ob) and np.array_equal(got["next_obs"][rows], nxt), t
+            assert np.array_equal(got["act"][rows], acts[t, :, 1]) and np.array_equal(got["rew"][rows], rew)
+            assert np.array_equal(got["done"][rows], done)
+        else:
+            want_rows.append((ob, acts[t, :, 1].copy(), rew, nxt, done))
+    if not lockstep:                                       # appends arrive in warp order, not step order: compare as a set
+        g_rows = _sorted_rows(*[got[k][:n * K] for k in ("obs", "act", "rew", "next_obs", "done")])
+        assert np.array_equal(g_rows, _sorted_rows(*[np.concatenate([w[j] for w in want_rows]) for j in range(5)]))
+    assert dones > 0
+    gu.assert_state_equal(env, b)
+
+
 @pytest.mark.parametrize("prec,opp", [("f32", "rnn"), ("f16", "rnn"), ("f16", "qnet")])
 def test_train_rnn_generation_sequence_replay_and_drqn_updates(H, prec, opp):
     """DRQN training mode on one slab (scripts/train_rnn_iterative.py:728-800): the recurrent kernel writes the lock-step
