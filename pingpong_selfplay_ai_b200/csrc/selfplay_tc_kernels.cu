@@ -296,7 +296,8 @@ struct FusedMap {
     static constexpr uint32_t W = 0, GROUPS_OFF = 2 * PLAYER_W_BYTES;
     static constexpr uint32_t SERVE_OFF = GROUPS_OFF + CTA_GROUPS * GROUP_BYTES;       // next serve per thread: 3 doubles
     static constexpr uint32_t CTRL = SERVE_OFF + TC_FUSED_THREADS * 24;                // mbarriers + TMEM base
-    static constexpr uint32_t TOTAL = CTRL + 64;
+    static constexpr uint32_t STAGE_OFF = (CTRL + 64 + 127) / 128 * 128;               // replay-row staging: 896 B per warp
+    static constexpr uint32_t TOTAL = STAGE_OFF + (TC_FUSED_THREADS / 32) * 896;
 };
 static_assert(FusedMap::TOTAL <= 232448, "shared memory of the fused tensor-core kernel exceeds 227 KB");
 static_assert(2 * BLOB_BYTES <= CTA_GROUPS * GROUP_BYTES + TC_FUSED_THREADS * 24, "weight staging aliases the X rows and serve slots");
@@ -314,6 +315,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
     const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
     GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, grp, row, qa, qb);
     double *serve_slot = reinterpret_cast<double *>(smem + M::SERVE_OFF) + threadIdx.x * 3;
+    float *row_stage = reinterpret_cast<float *>(smem + M::STAGE_OFF) + warp_id * 224;
     const EnvConsts<R> c(params);
     const StatePtrs<R> s(st);
     const int64_t total_warps = (n + 31) / 32;
@@ -367,7 +369,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
                     else next_serve<R>(params, src, n, i, env_id_base, ep, vx, vy, sp);
                 };
                 step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
-                                 ring.head != nullptr && t >= ring_t0, src, serve);
+                                 ring.head != nullptr && t >= ring_t0, src, serve, row_stage);
             }
         }
         if (valid) {
