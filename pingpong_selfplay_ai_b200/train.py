@@ -16,7 +16,8 @@ How the reference's sequential schedule maps to n lock-step envs (SURVEY.md sect
   * NoisyNet noise of B is resampled per action there (:125) and per chunk here (the packed weights of a launch are
     mu + sigma * eps for one draw); player A keeps the noise it was built with, as in the reference;
   * epsilon decays per episode there (:261); here epsilon = max(min, decay ** (episodes finished / n)), i.e. every env
-    follows the reference's schedule on average.
+    follows the reference's schedule on average (on CUDA the episode count is read one chunk late, through a pinned
+    buffer, so that the host never waits for the device).
 """
 from __future__ import annotations
 
@@ -318,6 +319,8 @@ def train_generation(engine: SelfPlayEngine, trainer: DQNTrainer, ring: ReplayRi
     env.counters.zero_()
     dev = env.device
     eps0, losses, done_steps = float(epsilon), [], 0
+    episodes, counters_event = 0, None
+    counters_host = torch.zeros(8, dtype=torch.int64).pin_memory() if dev.type == "cuda" else None
     if engine.pb.weights is None:
         engine.pb = Policy.qnet(trainer.model, noisy=True, eps=epsilon, precision=precision, device=dev)
     while done_steps < lockstep_steps:
@@ -335,8 +338,18 @@ def train_generation(engine: SelfPlayEngine, trainer: DQNTrainer, ring: ReplayRi
             loss = trainer.update(sampler)
             if loss is not None:
                 losses.append(loss)
-        # epsilon follows the slab's own episode count (slabs are statistically identical; no collective needed here)
-        episodes = int(env.counters[1].item())
+        # epsilon follows the slab's own episode count (slabs are statistically identical; no collective needed here).
+        # The count is read through a pinned buffer ONE CHUNK LATE, so the host never waits for the device and keeps
+        # launching ahead (a synchronous .item() per chunk left the GPU idle for ~0.1 ms of launch latency each time).
+        if dev.type == "cuda":
+            if counters_event is not None:
+                counters_event.synchronize()                                   # recorded a whole chunk ago
+                episodes = int(counters_host[1])
+            counters_host.copy_(env.counters, non_blocking=True)
+            counters_event = torch.cuda.Event()
+            counters_event.record(torch.cuda.current_stream(dev))
+        else:
+            episodes = int(env.counters[1].item())
         epsilon = max(min_epsilon, eps0 * epsilon_decay ** (episodes / env.n))               # :261, per env on average
     total = ppd.allreduce_counters(env.counters)
     out = dict(zip(("env_steps", "episodes", "wins_a", "wins_b", "points_a", "points_b", "paddle_hits", "ep_len_sum"),
