@@ -10,7 +10,8 @@ from ._lib import PongB200Error
 from .env import COUNTER_NAMES, PongEnv2P, ServePool, VecPongEnv2P
 from .params import ENV_DEFAULTS, make_params, resolve_env_config
 from .policy import NoisyLinear, Policy, QNet, QNetRNN, pack_qnet, pack_qnetrnn
-from .selfplay import ReplayRing, SelfPlayEngine, host_selfplay_eval, qnet_act, qnetrnn_act
+from .selfplay import (ReplayRing, SelfPlayEngine, eval_vs_model, eval_vs_pool, host_selfplay_eval, qnet_act,
+                       qnetrnn_act)
 from .train import DQNTrainer, PrioritizedSampler, train_generation
 from . import arena, checkpoint
 from .checkpoint import Agent, load_agent
@@ -19,5 +20,5 @@ __all__ = [
     "PongB200Error", "PongEnv2P", "VecPongEnv2P", "ServePool", "COUNTER_NAMES", "ENV_DEFAULTS", "make_params",
     "resolve_env_config", "NoisyLinear", "QNet", "QNetRNN", "Policy", "pack_qnet", "pack_qnetrnn", "ReplayRing",
     "SelfPlayEngine", "host_selfplay_eval", "qnet_act", "qnetrnn_act", "DQNTrainer", "PrioritizedSampler", "train_generation",
-    "arena", "checkpoint", "Agent", "load_agent",
+    "arena", "checkpoint", "Agent", "load_agent", "eval_vs_model", "eval_vs_pool",
 ]

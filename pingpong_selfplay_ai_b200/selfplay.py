@@ -187,3 +187,50 @@ def host_selfplay_eval(env_kwargs: dict, n: int, quota: int, pool, weights_a, we
                                          {"f32": _lib.PREC_F32, "f16": _lib.PREC_F16}[precision], chunk, max_steps,
                                          vp(counters), vp(log), ep_log_cap), "pp_host_selfplay_eval")
     return dict(zip(COUNTER_NAMES, (int(v) for v in counters))), log
+
+
+# ------------------------------------------------------------------------------------------ the reference's evaluators
+def _play_quota(env_kwargs: dict, policy_a: Policy, policy_b: Policy, n: int, quota: int, seed: int, mode: str, device,
+                max_steps: int = 1 << 20) -> dict:
+    """n lock-step envs x `quota` games each in ONE launch (an env freezes after its last game) -> counters."""
+    env = VecPongEnv2P(n, device=device, mode=mode, serve="philox", seed=seed, **env_kwargs)
+    env.reset()
+    SelfPlayEngine(env, policy_a, policy_b, seed=seed).run(max_steps, quota=quota)
+    c = env.read_counters()
+    if c["episodes"] != n * quota:
+        raise RuntimeError(f"{c['episodes']} of {n * quota} games finished within the step limit")
+    return c
+
+
+def eval_vs_model(env_kwargs: dict, model_a, model_b, episodes: int, max_envs: int = 65536, seed: int = 0, mode: str = "f64",
+                  precision: str = "f32", device="cuda", noisy_a: bool = False, noisy_b: bool = False) -> float:
+    """eval_vs_model(env, A, B, episodes) of scripts/train_iterative.py:171-181 -> B's win rate (rB > rA on the last
+    step = B reached max_score).  `episodes` games are spread over min(episodes, max_envs) lock-step envs; when that
+    does not divide, every env plays one game more (the rate is over the games actually played).  noisy_*: play with
+    mu + sigma * epsilon, as the reference's training script does for modelA / modelB (it never calls .eval() on them)."""
+    n = max(1, min(int(episodes), int(max_envs)))
+    quota = -(-int(episodes) // n)
+    c = _play_quota(env_kwargs, Policy.qnet(model_a, noisy=noisy_a, precision=precision, device=device),
+                    Policy.qnet(model_b, noisy=noisy_b, precision=precision, device=device), n, quota, seed, mode, device)
+    return c["wins_b"] / c["episodes"]
+
+
+def eval_vs_pool(env_kwargs: dict, model_b, pool: list, episodes: int, seed: int = 0, mode: str = "f64",
+                 precision: str = "f32", device="cuda", noisy_b: bool = False, rng=None) -> float:
+    """eval_vs_pool(env, B, pool, episodes) of scripts/train_iterative.py:183-196: every game's opponent is
+    random.choice(pool) (drawn here for all games up front, from `rng` or the global `random` like the reference), the
+    games against one opponent run as one lock-step batch; an empty pool scores 1.0 (:184-185)."""
+    if not pool:
+        return 1.0
+    import random as _random
+    pick = (rng or _random).choice
+    games = [0] * len(pool)
+    for _ in range(int(episodes)):
+        games[pick(range(len(pool)))] += 1
+    pol_b = Policy.qnet(model_b, noisy=noisy_b, precision=precision, device=device)
+    wins = 0
+    for k, (opp, g) in enumerate(zip(pool, games)):
+        if g:                                            # pool models play in eval mode (:205)
+            wins += _play_quota(env_kwargs, Policy.qnet(opp, precision=precision, device=device), pol_b, g, 1, seed + k,
+                                mode, device)["wins_b"]
+    return wins / int(episodes)

@@ -118,3 +118,28 @@ def test_play_match_with_a_reference_shaped_agent_record(H):
     sa, sb, ln = arena.play_match(cfg, old, new, 64, seed=9)
     wa, wb, wl = _oracle_scores(cfg, {"old": old, "new": new}, "old", "new", 64, 9)
     assert np.array_equal(sa, wa) and np.array_equal(sb, wb) and np.array_equal(ln, wl)
+
+
+def test_eval_vs_model_and_eval_vs_pool_on_the_batched_engine(H):
+    """scripts/train_iterative.py:171-196 as lock-step batches: win rates equal the oracle's on the same serves."""
+    import random
+    cfg = H["env_config_yaml"]
+    models, agents = _agents()
+    q0, q1 = agents["q0"].net, agents["q1"].net
+    wr = pp.eval_vs_model(cfg, q0, q1, 200, seed=12)
+    wa, wb, _ = _oracle_scores(cfg, agents, "q0", "q1", 200, 12)
+    assert wr == float((wb > wa).mean())
+    assert pp.eval_vs_model(cfg, q0, q1, 300, max_envs=128, seed=3) == pytest.approx(wr, abs=0.12)   # 128 envs x 3 games
+    assert pp.eval_vs_pool(cfg, q1, [], 50) == 1.0                                                    # :184-185
+    torch.manual_seed(5); q2 = pp.QNet().eval()
+    agents2 = dict(agents, q2=ck.Agent({"id": "q2", "type": "QNet", "path": "mem"}, q2))
+    got = pp.eval_vs_pool(cfg, q1, [q0, q2], 150, seed=40, rng=random.Random(9))
+    rng = random.Random(9)
+    games = [0, 0]
+    for _ in range(150):
+        games[rng.choice(range(2))] += 1
+    wins = 0
+    for k, (opp, g) in enumerate(zip(("q0", "q2"), games)):
+        wa, wb, _ = _oracle_scores(cfg, agents2, opp, "q1", g, 40 + k)
+        wins += int((wb > wa).sum())
+    assert games[0] > 0 and games[1] > 0 and got == wins / 150
