@@ -370,21 +370,22 @@ per_draw_kernel(const float *__restrict__ prios, int64_t capacity, int64_t chunk
                 const float *__restrict__ sums, const float *__restrict__ beta, const float *__restrict__ size,
                 uint64_t seed, const unsigned long long *__restrict__ counter, int batch, int64_t *__restrict__ idx_out,
                 float *__restrict__ w_out) {
-    extern __shared__ double prefix[];                                         // inclusive prefix of the chunk sums
-    for (int i = threadIdx.x; i < n_chunks; i += S_THREADS) prefix[i] = (double)sums[i];
+    extern __shared__ double prefix[];                     // inclusive prefix of the chunk sums, one pad per 32 entries:
+    auto px = [](int i) { return i + (i >> 5); };          // a lane's segment of the scan starts in its own bank pair
+    for (int i = threadIdx.x; i < n_chunks; i += S_THREADS) prefix[px(i)] = (double)sums[i];
     __syncthreads();
     if (threadIdx.x < 32) {                                                    // one warp scans: n_chunks <= 4096
         const int lane = threadIdx.x, per = (n_chunks + 31) / 32;
         double run = 0.0;
-        for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < n_chunks) { run += prefix[i]; prefix[i] = run; } }
+        for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < n_chunks) { run += prefix[px(i)]; prefix[px(i)] = run; } }
         double off = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
         off -= run;                                                            // exclusive offset of this lane's segment
-        for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < n_chunks) prefix[i] += off; }
+        for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < n_chunks) prefix[px(i)] += off; }
     }
     __syncthreads();
-    const double total = prefix[n_chunks - 1];
+    const double total = prefix[px(n_chunks - 1)];
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (S_THREADS / 32) + (threadIdx.x >> 5);          // one warp per sample
     if (r >= batch) return;
@@ -392,8 +393,8 @@ per_draw_kernel(const float *__restrict__ prios, int64_t capacity, int64_t chunk
     const uint4 rnd = philox4x32_10((uint32_t)r, 0x70657273u, (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
     const double u = fmin(u53(rnd.x, rnd.y) * total, total * (1.0 - 1e-15));   // strictly inside the last live chunk
     int lo = 0, hi = n_chunks - 1;                                             // first chunk with prefix > u
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (prefix[mid] > u) hi = mid; else lo = mid + 1; }
-    const float rem = (float)(u - (lo > 0 ? prefix[lo - 1] : 0.0));
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (prefix[px(mid)] > u) hi = mid; else lo = mid + 1; }
+    const float rem = (float)(u - (lo > 0 ? prefix[px(lo - 1)] : 0.0));
     const int64_t c_lo = (int64_t)lo * chunk, c_hi = c_lo + chunk < capacity ? c_lo + chunk : capacity;
     float run = 0.f, pa_sel = 0.f;
     int64_t pick = -1, last_pos = -1;
@@ -485,12 +486,12 @@ int per_sample_launch(const float *prios, int64_t capacity, float alpha, const f
     const int n_chunks = (int)((capacity + chunk - 1) / chunk);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(per_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_MAX_CHUNKS * sizeof(double)));
+        cudaError_t err = cudaFuncSetAttribute(per_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((S_MAX_CHUNKS + S_MAX_CHUNKS / 32 + 1) * sizeof(double)));
         if (err != cudaSuccess) return (int)err;
         attr_set = true;
     }
     per_chunk_sums_kernel<<<n_chunks, S_THREADS, 0, stream>>>(prios, capacity, chunk, alpha, chunk_sums);
-    per_draw_kernel<<<(batch + S_THREADS / 32 - 1) / (S_THREADS / 32), S_THREADS, (size_t)n_chunks * sizeof(double), stream>>>(
+    per_draw_kernel<<<(batch + S_THREADS / 32 - 1) / (S_THREADS / 32), S_THREADS, (size_t)(n_chunks + n_chunks / 32 + 1) * sizeof(double), stream>>>(
         prios, capacity, chunk, n_chunks, alpha, chunk_sums, beta, size, seed, counter, batch, idx_out, w_out);
     per_normalise_kernel<<<1, S_THREADS, 0, stream>>>(w_out, batch, counter);
     return (int)cudaGetLastError();
