@@ -80,16 +80,19 @@ __device__ void build_weight_tiles(uint8_t *wt, const float *blob, int tid, int 
         H(W2H_OFF)[idx] = hi(w);
         H(W2L_OFF)[idx] = lo(w);
     }
-    for (int idx = tid; idx < 8 * 16 * 8; idx += nthreads) {                 // heads [8][16][8], columns 0..3 used
-        const int k = (idx >> 7) * 8 + (idx & 7), nn = (idx >> 3) & 15;
-        const float w = nn < 4 ? blob[PP_QNET_WHT + k * 4 + nn] : 0.0f;
-        H(W3H_OFF)[idx] = hi(w);
-        H(W3L_OFF)[idx] = lo(w);
-    }
-    for (int idx = tid; idx < 2 * 16 * 8; idx += nthreads) {                 // head biases [2][16][8]
-        const int k = (idx >> 7) * 8 + (idx & 7), nn = (idx >> 3) & 15;
-        const float bv = nn < 4 ? blob[PP_QNET_BH + nn] : 0.0f;
-        H(B3_OFF)[idx] = (k & 7) == 7 ? (k == 7 ? hi(bv) : lo(bv)) : zero;
+    // dueling heads stay fp32: [64] x (V, A0, A1, A2) k-major + the bias row, read as broadcast float4 by heads_epilogue
+    // (for the packed FFMA2 of sm_100: per pair of hidden units k0 = 2 kk, k1 = k0 + 1 two float4
+    //  (V[k0], V[k1], A0[k0], A0[k1]) and (A1[k0], A1[k1], A2[k0], A2[k1]); entry 64 = the bias row)
+    float4 *ht = reinterpret_cast<float4 *>(wt + W3H_OFF);
+    for (int idx = tid; idx < 65; idx += nthreads) {
+        if (idx < 64) {
+            const int kk = idx >> 1, o = (idx & 1) * 2;                      // o: first of the two outputs in this float4
+            const float *w0 = blob + PP_QNET_WHT + (2 * kk) * 4, *w1 = w0 + 4;
+            ht[idx] = make_float4(w0[o], w1[o], w0[o + 1], w1[o + 1]);
+        } else {
+            const float *b = blob + PP_QNET_BH;
+            ht[idx] = make_float4(b[0], b[1], b[2], b[3]);
+        }
     }
 }
 
@@ -104,18 +107,52 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t src, uint32_t dst) {
         tc::tmem_ld16(src + half * 32 + 16, r1);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; ++j) {                                         // residuals as one packed FADD2 per pair
             const float a = __uint_as_float(r0[2 * j]), b = __uint_as_float(r0[2 * j + 1]);
             hi[j] = tc::pack_f16x2_rz_relu(a, b);
-            lo[j] = tc::pack_f16x2<true>(a - h2f(hi[j], 0), b - h2f(hi[j], 1));
+            const float2 ra = __fadd2_rn(make_float2(a, b), make_float2(-h2f(hi[j], 0), -h2f(hi[j], 1)));
+            lo[j] = tc::pack_f16x2<true>(ra.x, ra.y);
             const float c = __uint_as_float(r1[2 * j]), d = __uint_as_float(r1[2 * j + 1]);
             hi[8 + j] = tc::pack_f16x2_rz_relu(c, d);
-            lo[8 + j] = tc::pack_f16x2<true>(c - h2f(hi[8 + j], 0), d - h2f(hi[8 + j], 1));
+            const float2 rc = __fadd2_rn(make_float2(c, d), make_float2(-h2f(hi[8 + j], 0), -h2f(hi[8 + j], 1)));
+            lo[8 + j] = tc::pack_f16x2<true>(rc.x, rc.y);
         }
         tc::tmem_st16(dst + half * 16, hi);
         tc::tmem_st16(dst + TM_LO + half * 16, lo);
     }
     tc::tmem_st_wait();
+}
+
+// Second hidden layer's accumulator row (64 fp32 columns at `src`) -> ReLU -> the four head outputs in fp32 on the CUDA
+// cores (256 FMAs against a broadcast float4 table) -> dueling Q.  This replaces a third MMA batch (13 small MMAs at the
+// 45-cycle instruction floor, one more accumulator round trip and group barrier per player) and keeps the heads exact.
+__device__ __forceinline__ void heads_epilogue(uint32_t src, const uint8_t *table, float (&q)[3]) {
+    const float4 *ht = reinterpret_cast<const float4 *>(table);
+    float2 v = make_float2(0.f, 0.f), a0 = v, a1 = v, a2 = v;                   // (even-k, odd-k) partial sums per output
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t r0[16], r1[16];
+        tc::tmem_ld16(src + half * 32, r0);
+        tc::tmem_ld16(src + half * 32 + 16, r1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {                                          // 16 pairs of hidden units
+            const uint32_t *r = j < 8 ? r0 + 2 * j : r1 + 2 * (j - 8);
+            const float2 h = make_float2(fmaxf(__uint_as_float(r[0]), 0.0f), fmaxf(__uint_as_float(r[1]), 0.0f));
+            const float4 w01 = ht[(half * 16 + j) * 2], w23 = ht[(half * 16 + j) * 2 + 1];
+            v = __ffma2_rn(make_float2(w01.x, w01.y), h, v);
+            a0 = __ffma2_rn(make_float2(w01.z, w01.w), h, a0);
+            a1 = __ffma2_rn(make_float2(w23.x, w23.y), h, a1);
+            a2 = __ffma2_rn(make_float2(w23.z, w23.w), h, a2);
+        }
+    }
+    const float4 bias = ht[64];
+    const float V = __fadd_rn(__fadd_rn(v.x, v.y), bias.x), A0 = __fadd_rn(__fadd_rn(a0.x, a0.y), bias.y);
+    const float A1 = __fadd_rn(__fadd_rn(a1.x, a1.y), bias.z), A2 = __fadd_rn(__fadd_rn(a2.x, a2.y), bias.w);
+    const float mean = __fdiv_rn(__fadd_rn(__fadd_rn(A0, A1), A2), 3.0f);               // V + (A - mean(A))  models/qnet.py:75
+    q[0] = __fadd_rn(V, __fsub_rn(A0, mean));
+    q[1] = __fadd_rn(V, __fsub_rn(A1, mean));
+    q[2] = __fadd_rn(V, __fsub_rn(A2, mean));
 }
 
 // MMA batches, issued by one thread per group.  d / a_tm are TMEM addresses with lane 0.
@@ -191,14 +228,13 @@ __device__ __forceinline__ void group_wait(GroupCtx &g) {
     tc::tc_fence_after();
 }
 
-// 0 = L1, 1 = L2, 2 = L3 of player p; an elected lane of the group's first warp issues, everybody waits
+// 0 = L1, 1 = L2 of player p; an elected lane of the group's first warp issues, everybody waits
 __device__ __forceinline__ void group_mma(GroupCtx &g, const PlayerTiles &p, int layer) {
     if (g.issuer_warp) {                      // warp-uniform branch
         if (tc::elect_one()) {
             tc::tc_fence_after();
             if (layer == 0) issue_l1(g.r0, p);
-            else if (layer == 1) issue_dense<64>(g.r0, g.r0 + TM_R1, p, W2H_OFF, W2L_OFF, B2_OFF);
-            else issue_dense<16>(g.r0, g.r0 + TM_R1, p, W3H_OFF, W3L_OFF, B3_OFF);
+            else issue_dense<64>(g.r0, g.r0 + TM_R1, p, W2H_OFF, W2L_OFF, B2_OFF);
             tc::umma_commit(g.bar);
         }
         __syncwarp();
@@ -206,7 +242,7 @@ __device__ __forceinline__ void group_mma(GroupCtx &g, const PlayerTiles &p, int
     group_wait(g);
 }
 
-// per QNet player: L1 -> H1 -> L2 -> H2 -> L3 -> Q, all in the group's two TMEM regions
+// per QNet player: L1 -> H1 -> L2 -> (ReLU, fp32 heads on the CUDA cores) -> Q, in the group's two TMEM regions
 __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
     bool first = true;
 #pragma unroll 1
@@ -219,14 +255,11 @@ __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], floa
         }
         first = false;
         group_mma(g, p, 0);
-#pragma unroll 1
-        for (int layer = 1; layer <= 2; ++layer) {
-            hidden_epilogue(g.r0 + g.lane_addr, g.r0 + TM_R1 + g.lane_addr);
-            tc::tc_fence_before();
-            tc::bar_sync(g.bar_id, G_ROWS);
-            group_mma(g, p, layer);
-        }
-        if (pl) dueling_q(g.r0 + g.lane_addr, q_b); else dueling_q(g.r0 + g.lane_addr, q_a);
+        hidden_epilogue(g.r0 + g.lane_addr, g.r0 + TM_R1 + g.lane_addr);
+        tc::tc_fence_before();
+        tc::bar_sync(g.bar_id, G_ROWS);
+        group_mma(g, p, 1);
+        if (pl) heads_epilogue(g.r0 + g.lane_addr, p.w + W3H_OFF, q_b); else heads_epilogue(g.r0 + g.lane_addr, p.w + W3H_OFF, q_a);
     }
 }
 
