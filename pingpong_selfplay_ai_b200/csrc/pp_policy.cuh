@@ -13,6 +13,15 @@ namespace pp {
 
 __device__ __forceinline__ float relu(float v) { return v > 0.0f ? v : 0.0f; }
 
+// acc += w * x for four outputs: two packed FFMA2 (sm_100: two IEEE fp32 FMAs per instruction — the same bits as four
+// fmaf, half the issue slots; this kernel is issue-bound)
+__device__ __forceinline__ void fma4(float4 &acc, const float4 &w, float x) {
+    const float2 xx = make_float2(x, x);
+    const float2 lo = __ffma2_rn(make_float2(w.x, w.y), xx, make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(make_float2(w.z, w.w), xx, make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // sw: blob in shared memory (16-byte aligned).  q[3] out.
 __device__ __forceinline__ void qnet_forward(const float *__restrict__ sw, const float (&obs)[7], float (&q)[3]) {
     float h1[64];
@@ -24,9 +33,7 @@ __device__ __forceinline__ void qnet_forward(const float *__restrict__ sw, const
             float4 acc = b1[j4];
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
-                const float4 w = w1[k * 16 + j4];
-                acc.x = fmaf(w.x, obs[k], acc.x); acc.y = fmaf(w.y, obs[k], acc.y);
-                acc.z = fmaf(w.z, obs[k], acc.z); acc.w = fmaf(w.w, obs[k], acc.w);
+                fma4(acc, w1[k * 16 + j4], obs[k]);
             }
             h1[j4 * 4 + 0] = relu(acc.x); h1[j4 * 4 + 1] = relu(acc.y);
             h1[j4 * 4 + 2] = relu(acc.z); h1[j4 * 4 + 3] = relu(acc.w);
@@ -44,18 +51,13 @@ __device__ __forceinline__ void qnet_forward(const float *__restrict__ sw, const
             const float x = h1[k];
             const float4 u0 = w2[k * 16 + jb * 4 + 0], u1 = w2[k * 16 + jb * 4 + 1];
             const float4 u2 = w2[k * 16 + jb * 4 + 2], u3 = w2[k * 16 + jb * 4 + 3];
-            a0.x = fmaf(u0.x, x, a0.x); a0.y = fmaf(u0.y, x, a0.y); a0.z = fmaf(u0.z, x, a0.z); a0.w = fmaf(u0.w, x, a0.w);
-            a1.x = fmaf(u1.x, x, a1.x); a1.y = fmaf(u1.y, x, a1.y); a1.z = fmaf(u1.z, x, a1.z); a1.w = fmaf(u1.w, x, a1.w);
-            a2.x = fmaf(u2.x, x, a2.x); a2.y = fmaf(u2.y, x, a2.y); a2.z = fmaf(u2.z, x, a2.z); a2.w = fmaf(u2.w, x, a2.w);
-            a3.x = fmaf(u3.x, x, a3.x); a3.y = fmaf(u3.y, x, a3.y); a3.z = fmaf(u3.z, x, a3.z); a3.w = fmaf(u3.w, x, a3.w);
+            fma4(a0, u0, x); fma4(a1, u1, x); fma4(a2, u2, x); fma4(a3, u3, x);
         }
         const float h2[16] = {relu(a0.x), relu(a0.y), relu(a0.z), relu(a0.w), relu(a1.x), relu(a1.y), relu(a1.z), relu(a1.w),
                               relu(a2.x), relu(a2.y), relu(a2.z), relu(a2.w), relu(a3.x), relu(a3.y), relu(a3.z), relu(a3.w)};
 #pragma unroll
         for (int i = 0; i < 16; ++i) {            // heads accumulate in ascending hidden index, like the oracle
-            const float4 w = wh[jb * 16 + i];
-            head.x = fmaf(w.x, h2[i], head.x); head.y = fmaf(w.y, h2[i], head.y);
-            head.z = fmaf(w.z, h2[i], head.z); head.w = fmaf(w.w, h2[i], head.w);
+            fma4(head, wh[jb * 16 + i], h2[i]);
         }
     }
     // V + (A - mean(A))                                                       models/qnet.py:75
