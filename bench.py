@@ -571,7 +571,6 @@ def measure_k1(pp, dev, peaks, mode, n):
 def measure_e2e(pp, net_a, net_b, args):
     """The same metric through the reference-facing host-buffer call: numpy serves + packed weights in, counters out;
     H2D / D2H copies and every sync inside the timed region (wall clock around the synchronous C-ABI call)."""
-    from pingpong_selfplay_ai_b200.params import make_params, resolve_env_config  # noqa: F401
     n, quota = args.envs, 8
     rs = np.random.RandomState(0)
     speed = rs.uniform(0.03, 0.05, size=(quota, n))

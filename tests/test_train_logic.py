@@ -2,7 +2,6 @@
 line-by-line restatement of the reference's train_step (scripts/train_iterative.py:132-168) on the same batch."""
 import copy
 
-import numpy as np
 import pytest
 import torch
 

@@ -1,5 +1,5 @@
 """Cost of replay rows and of epsilon-greedy exploration inside the fused tensor-core rollout."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pingpong_selfplay_ai_b200 as pp

@@ -3,7 +3,6 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pingpong_selfplay_ai_b200 as pp
-from pingpong_selfplay_ai_b200.policy import pack_qnet
 
 n, k, prec = 65536, 64, "f16"
 cfg = dict(pp.ENV_DEFAULTS)
