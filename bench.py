@@ -39,7 +39,7 @@ UNIT = "env-steps/s"
 FLOP_PER_ENV_STEP = 19200            # 2 players x 2 x 4800 MAC
 BYTES_PER_STEP_F64 = 203             # K1 single step, all outputs materialised, fp64 mode
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/):
-NCU_TRAFFIC = {("selfplay_tc_kernel", 256): 5.086208e6 + 56.32e3,      # r01_selfplay_tc256_metrics.txt, 65536 envs x 256 steps
+NCU_TRAFFIC = {("selfplay_tc_kernel", 256): 5.088512e6 + 95.744e3,     # r01_selfplay_tc256_final_metrics.txt, 65536 envs x 256 steps
                ("selfplay_tc_kernel", 64): 5.083904e6 + 27.136e3,      # r01_selfplay_r01b_metrics.txt, 65536 envs x 64 steps
                ("selfplay_kernel", 64): 5.094144e6 + 15.36e3}           # r01_selfplay_r01_metrics.txt, same shape
 NCU_K1_TRAFFIC_PER_ENV = (293.624576e6 + 499.684352e6) / 4194304   # r01_k1_r01b_metrics.txt: 189.1 B per env-step at 4 M envs
