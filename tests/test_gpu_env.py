@@ -123,6 +123,33 @@ def test_config2_4096_envs_rollout_bit_exact_vs_oracle(H, mode):
 
 
 @pytest.mark.parametrize("mode", ["f64", "f32"])
+def test_rollout_bit_exact_on_random_constructor_configs(H, mode):
+    """The device env against the oracle on RANDOM constructor keyword sets (paddle geometry, restitution, friction incl.
+    0 and > 1, mass, radius, spin on / off, speed-scaling schedule, max_score 1..5): every step's state, the counters
+    and the final state are bit-exact — the kernels bake no constant of config.yaml in."""
+    rs = np.random.RandomState(20260 + (mode == "f32"))
+    pick = lambda xs: xs[rs.randint(len(xs))]
+    for trial in range(10):
+        cfg = dict(H["env_config_yaml"])
+        cfg.update(paddle_width=pick([0.05, 0.2, 0.35, 0.9]), paddle_speed=pick([0.01, 0.03, 0.08]), max_score=int(rs.randint(1, 6)),
+                   enable_spin=bool(rs.randint(2)), magnus_factor=pick([0.0, 0.025, 0.1]), restitution=pick([0.5, 0.9, 1.0, 1.1]),
+                   friction=pick([0.0, 0.3, 0.6, 1.5]), ball_mass=pick([0.5, 1.0, 2.0]), world_ball_radius=pick([0.01, 0.03, 0.05]),
+                   speed_scale_every=int(rs.randint(1, 7)), speed_increment=pick([0.0, 0.1, 0.2, 0.5]))
+        n, K = 257, 300
+        pool = gu.make_pool(100 + trial, n, 8, cfg, mode)
+        acts = gu.random_actions(trial, K, n, with_invalid=True)
+        env = pp.VecPongEnv2P(n, mode=mode, serve=pool, **cfg)
+        env.reset()
+        b = gu.oracle_batch_like(env, mode)
+        got = env.rollout(torch.from_numpy(acts).cuda(), trace=True)
+        want = po.rollout(po.make_params(cfg), b, acts, pool, trace=True)
+        assert np.array_equal(gu.bits(gu.np_of(got["trace_real"])), gu.bits(want["trace_real"])), (trial, cfg)
+        assert np.array_equal(gu.np_of(got["trace_int"]), want["trace_int"]), (trial, cfg)
+        gu.assert_state_equal(env, b, what=str(cfg))
+        assert np.array_equal(gu.np_of(env.counters), want["counters"]) and want["counters"][1] > 0
+
+
+@pytest.mark.parametrize("mode", ["f64", "f32"])
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 513, 1024, 4099])
 def test_step_kernel_ragged_sizes_and_vector_paths(H, mode, n):
     """Scalar and 16-byte vector variants of the single-step kernel, full and partial tiles."""
