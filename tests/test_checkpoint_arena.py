@@ -150,3 +150,22 @@ def test_h2h_matrix_and_database_files(A, tmp_path):
     recs = arena._records("a", "b", np.array([3, 1, 2]), np.array([0, 3, 2]), "t")
     assert [r["winner"] for r in recs] == ["a", "b", "draw"]
     assert list(recs[0].keys()) == ["p1", "p2", "winner", "p1_score", "p2_score", "timestamp"]   # tests/arena.py:311-318
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "arena_database.json")), reason="the reference tree lives in the build container only")
+def test_the_reference_s_own_database_gives_the_reference_s_own_report():
+    """arena_database.json as shipped by the reference (10 models, 4 500 games): our plan / summary / head-to-head equal
+    the outputs of the unmodified tests/arena.py functions on it."""
+    from oracle import ref_shim
+    ref_arena = ref_shim.load_reference_round_robin("arena.py")
+    with open(os.path.join(REF, "arena_database.json"), encoding="utf-8") as f:
+        db = json.load(f)
+    assert arena.load_database(os.path.join(REF, "arena_database.json")) == db
+    for target in (100, 120):
+        assert arena.create_match_plan(copy.deepcopy(db), target) == ref_arena.create_match_plan(copy.deepcopy(db), target)
+    want = ref_arena.generate_summary_report(copy.deepcopy(db)).reset_index().to_dict(orient="records")
+    got = arena.generate_summary_report(db)
+    assert sorted(got, key=lambda r: r["model_id"]) == sorted(want, key=lambda r: r["model_id"])
+    assert [r["win_rate"] for r in got] == [r["win_rate"] for r in want]
+    ids, wins = arena.h2h_wins(db)
+    assert wins.sum() == sum(r["win"] for r in got) == 4500 - sum(r["draw"] for r in got) // 2
