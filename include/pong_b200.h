@@ -267,8 +267,9 @@ int pp_replay_scatter(int64_t n, const PPReplayRing *ring, const float *obs, con
 
 /* Whole evaluation from HOST buffers (what a reference caller holds): eval_vs_model of
  * scripts/train_iterative.py:171-181 for n envs x quota episodes each, QNet A vs QNet B.
- * Copies serves and weights to the device, runs pp_selfplay_rollout in chunks of `chunk` steps until
- * every env has finished its quota (or max_steps), copies counters[8] and per-episode records back.
+ * Copies serves and weights to the device, plays the n x quota serves as ONE queue (PP_SERVE_QUEUE: an env that
+ * finishes claims the next unplayed serve) in a single launch of at most max_steps lock-step steps (`chunk` is kept
+ * in the signature and ignored), copies counters[8] and per-episode records back.
  * host_ep_log may be NULL.  Returns after the results are in the host buffers. */
 int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *params,
                           const void *host_pool_vx, const void *host_pool_vy, const void *host_pool_spin,
