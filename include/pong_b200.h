@@ -110,8 +110,8 @@ typedef struct PPPolicy {
     int32_t kind;
     int32_t precision;
     uint64_t eps_threshold;     /* explore iff (uint64)philox.x < eps_threshold; floor(eps * 2^32), 0 = greedy */
-    float follower_tol;         /* tests/arena.py:213                                                       */
-    int32_t reserved;
+    double follower_tol;        /* tests/arena.py:213 — a Python float: the reference (numpy 1.24.3, requirements.txt:2)
+                                 * evaluates `np.float32 - 0.02` and the compares in float64, and so does the engine   */
     const float *weights;       /* packed blob, see PP_QNET_* / PP_RNN_* offsets (QNetRNN with PP_PREC_F16: the
                                  * fp16 image PP_RNNTC_*)                                                     */
     float *h, *c;               /* QNetRNN only: [n][128] each, zeroed by the engine at episode start       */
@@ -231,6 +231,12 @@ int pp_env_serve(int mode, int64_t n, const PPEnvState *state, const uint8_t *ma
  * reset envs (the reference consumes one serve per reset() call). */
 int pp_env_reset(int mode, int64_t n, const PPParams *params, const PPEnvState *state, const uint8_t *mask,
                  const PPServeSource *serve, int64_t env_id_base, int advance, void *stream);
+
+/* collide_sphere_with_moving_plane(vn, vt, u, omega, e, mu, m, R) for n independent impacts   envs/physics.py:3-23
+ * all arrays real[n]; of `params` only neg_e, m_1pe, inertia, two_m_over_7, mu, mass and radius are read (the
+ * constants the reference computes per call at physics.py:7-11, precomputed "the Python way" by the host). */
+int pp_collide(int mode, int64_t n, const PPParams *params, const void *vn, const void *vt, const void *u,
+               const void *omega, void *vn_out, void *vt_out, void *omega_out, void *stream);
 
 /* k lock-step steps with an injected action stream actions[k][n][2] and auto-reset; state stays in
  * registers between steps.  An env whose ep_idx reached `quota` (> 0) is frozen.

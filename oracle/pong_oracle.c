@@ -67,14 +67,55 @@ typedef struct OracleParams {       /* host-precomputed "the Python way" (oracle
 
 static inline float relu(float v) { return v > 0.0f ? v : 0.0f; }
 
+/* Function multiversioning: on a CPU with FMA3 the clone compiled for it turns fmaf() into one vfmadd instruction;
+ * elsewhere the default clone calls libm's fmaf().  Both are the correctly rounded fused multiply-add: same bits. */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define ORACLE_CLONES __attribute__((target_clones("arch=x86-64-v3", "default"), optimize("no-tree-vectorize", "no-tree-slp-vectorize")))
+#else
+#define ORACLE_CLONES
+#endif
+
+/* y[j] = chain_j = init[j] (+ init2[j]); then acc = fmaf(W1[j][k], x1[k], acc) for k ascending, then the same over
+ * (W2, x2) if W2 != NULL.  Eight outputs are advanced together: their chains are independent, so they overlap in
+ * the FMA pipeline (one chain alone is bound by the FMA latency) — every output still sees exactly its own chain. */
+ORACLE_CLONES
+static void chains(const float *W1, const float *x1, int n1, const float *W2, const float *x2, int n2,
+                   const float *init, const float *init2, float *y, int n_out, int do_relu)
+{
+    enum { B = 8 };
+    for (int j0 = 0; j0 < n_out; j0 += B) {
+        const int nb = n_out - j0 < B ? n_out - j0 : B;
+        float acc[B];
+        for (int jj = 0; jj < nb; ++jj) acc[jj] = init2 ? init[j0 + jj] + init2[j0 + jj] : init[j0 + jj];
+        if (nb == B) {
+            float a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], a4 = acc[4], a5 = acc[5], a6 = acc[6], a7 = acc[7];
+            for (int pass = 0; pass < (W2 ? 2 : 1); ++pass) {
+                const int nk = pass ? n2 : n1;
+                const float *xx = pass ? x2 : x1;
+                const float *w0 = (pass ? W2 : W1) + (size_t)j0 * nk;
+                const float *w1 = w0 + nk, *w2 = w1 + nk, *w3 = w2 + nk, *w4 = w3 + nk, *w5 = w4 + nk, *w6 = w5 + nk,
+                            *w7 = w6 + nk;
+                for (int k = 0; k < nk; ++k) {
+                    const float xk = xx[k];
+                    a0 = fmaf(w0[k], xk, a0); a1 = fmaf(w1[k], xk, a1); a2 = fmaf(w2[k], xk, a2); a3 = fmaf(w3[k], xk, a3);
+                    a4 = fmaf(w4[k], xk, a4); a5 = fmaf(w5[k], xk, a5); a6 = fmaf(w6[k], xk, a6); a7 = fmaf(w7[k], xk, a7);
+                }
+            }
+            acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3; acc[4] = a4; acc[5] = a5; acc[6] = a6; acc[7] = a7;
+        } else {
+            for (int jj = 0; jj < nb; ++jj) {
+                for (int k = 0; k < n1; ++k) acc[jj] = fmaf(W1[(size_t)(j0 + jj) * n1 + k], x1[k], acc[jj]);
+                if (W2) for (int k = 0; k < n2; ++k) acc[jj] = fmaf(W2[(size_t)(j0 + jj) * n2 + k], x2[k], acc[jj]);
+            }
+        }
+        for (int jj = 0; jj < nb; ++jj) y[j0 + jj] = do_relu ? relu(acc[jj]) : acc[jj];
+    }
+}
+
 /* dense layer, row-major W[out][in] as in a torch state_dict; acc = b; acc = fmaf(W[j][k], x[k], acc) */
 static void dense(const float *W, const float *b, const float *x, float *y, int n_out, int n_in, int do_relu)
 {
-    for (int j = 0; j < n_out; ++j) {
-        float acc = b[j];
-        for (int k = 0; k < n_in; ++k) acc = fmaf(W[(size_t)j * n_in + k], x[k], acc);
-        y[j] = do_relu ? relu(acc) : acc;
-    }
+    chains(W, x, n_in, NULL, NULL, 0, b, NULL, y, n_out, do_relu);
 }
 
 /* dueling combine exactly as the CUDA path: mean = ((a0 + a1) + a2) / 3 ; q_i = v + (a_i - mean) */
@@ -136,12 +177,8 @@ void oracle_qnetrnn_forward(int64_t n, int F, int H, int S /* head hidden, >0 */
         float *he = h + e * H, *ce = c + e * H;
         dense(Wf1, bf1, obs + e * 7, f1, F / 2, 7, 1);
         dense(Wf2, bf2, f1, f2, F, F / 2, 1);
-        for (int j = 0; j < 4 * H; ++j) {
-            float acc = bih[j] + bhh[j];
-            for (int k = 0; k < F; ++k) acc = fmaf(Wih[(size_t)j * F + k], f2[k], acc);
-            for (int k = 0; k < H; ++k) acc = fmaf(Whh[(size_t)j * H + k], he[k], acc);
-            gates[j] = acc;
-        }
+        /* gates[j] = (bih[j] + bhh[j]) then fmaf over Wih[j] . f2, then over Whh[j] . h */
+        chains(Wih, f2, F, Whh, he, H, bih, bhh, gates, 4 * H, 0);
         for (int j = 0; j < H; ++j) {
             float ig = sigmoidf_(gates[j]);
             float fg = sigmoidf_(gates[H + j]);
@@ -188,8 +225,7 @@ typedef struct OraclePolicy {
     int32_t kind;
     int32_t pad_;
     uint64_t eps_threshold;     /* explore iff (uint64)r0 < eps_threshold ; floor(eps * 2^32) */
-    float follower_tol;         /* tests/arena.py:213 (0.02) / tests/test_round_robin.py:224 (0.01) */
-    float pad2_;
+    double follower_tol;        /* tests/arena.py:213 (0.02) / tests/test_round_robin.py:224 (0.01): a Python float */
     const float *W1, *b1, *W2, *b2, *Wv, *bv, *Wa, *ba;   /* QNet effective weights */
 } OraclePolicy;
 
@@ -205,8 +241,9 @@ static int policy_act(const OraclePolicy *pi, const float *obs, uint32_t env_id,
         return (int)(((uint64_t)r[1] * 3u) >> 32);
     }
     if (pi->kind == POLICY_FOLLOWER) {
-        float lo = obs[4] - pi->follower_tol, hi = obs[4] + pi->follower_tol;
-        a = obs[0] < lo ? 0 : (obs[0] > hi ? 2 : 1);
+        /* np.float32 - python float -> float64 under the pinned numpy 1.24.3 (requirements.txt:2); compares in double */
+        double x = (double)obs[0], lo = (double)obs[4] - pi->follower_tol, hi = (double)obs[4] + pi->follower_tol;
+        a = x < lo ? 0 : (x > hi ? 2 : 1);
     } else {
         uint8_t g;
         oracle_qnet_forward(1, obs, pi->W1, pi->b1, pi->W2, pi->b2, pi->Wv, pi->bv, pi->Wa, pi->ba, 0, &g);

@@ -26,7 +26,7 @@ class OracleParams(C.Structure):
 
 class OraclePolicy(C.Structure):
     _fields_ = [("kind", C.c_int32), ("pad_", C.c_int32), ("eps_threshold", C.c_uint64),
-                ("follower_tol", C.c_float), ("pad2_", C.c_float)] + [
+                ("follower_tol", C.c_double)] + [
         (n, C.c_void_p) for n in ("W1", "b1", "W2", "b2", "Wv", "bv", "Wa", "ba")]
 
 
@@ -315,3 +315,73 @@ def serve_pool_from_reference_rng(seed: int, n: int, depth: int, cfg: dict):
         for j in range(depth):
             out[:, j, i] = draw_serve(rng, cfg["ball_speed_range"], ang, cfg["spin_range"])
     return out[0], out[1], out[2]
+
+
+# ------------------------------------------------------------------------------------------ env slabs on threads
+# Envs are independent, so a batch can be cut into contiguous slabs that run on their own host threads (ctypes
+# releases the GIL inside the C calls).  Results are those of the single call except for the ORDER of ep_log /
+# replay rows (slab-major instead of step-major) — callers that compare them sort first.
+def _slab_view(b: EnvBatch, lo: int, hi: int) -> EnvBatch:
+    v = EnvBatch.__new__(EnvBatch)
+    v.n, v.mode = hi - lo, b.mode
+    for k in STATE_REAL + STATE_INT + ("ep_idx", "ep_len"):
+        setattr(v, k, getattr(b, k)[lo:hi])             # contiguous views: the C code updates the parent in place
+    return v
+
+
+def _slabs(n: int, threads):
+    import os
+    t = max(1, min(int(threads or len(os.sched_getaffinity(0))), max(1, n // 256)))
+    cuts = np.linspace(0, n, t + 1).astype(np.int64)
+    return [(int(lo), int(hi)) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+
+
+def _run_slabs(fn, slabs):
+    from concurrent.futures import ThreadPoolExecutor
+    if len(slabs) == 1:
+        return [fn(*slabs[0])]
+    with ThreadPoolExecutor(max_workers=len(slabs)) as ex:
+        return list(ex.map(lambda s: fn(*s), slabs))
+
+
+def selfplay_parallel(p, b, polA, polB, K, pool, threads=None, env_id_base=0, log_cap=0, want_actions=False,
+                      replay_cap=0, **kw):
+    """selfplay() over env slabs on host threads; log_cap / replay_cap are per-batch totals."""
+    slabs = _slabs(b.n, threads)
+    pool = tuple(np.asarray(a) for a in pool)
+
+    def one(lo, hi):
+        sub = tuple(np.ascontiguousarray(a[:, lo:hi]) for a in pool)
+        frac = (hi - lo) / b.n
+        return selfplay(p, _slab_view(b, lo, hi), polA, polB, K, sub, env_id_base=env_id_base + lo, log_cap=log_cap,
+                        want_actions=want_actions, replay_cap=int(np.ceil(replay_cap * frac)) if replay_cap else 0, **kw)
+    parts = _run_slabs(one, slabs)
+    out = dict(counters=sum(r["counters"] for r in parts), ep_log=np.concatenate([r["ep_log"] for r in parts]),
+               n_log=sum(r["n_log"] for r in parts),
+               actions=np.concatenate([r["actions"] for r in parts], axis=1) if want_actions else None)
+    if replay_cap:
+        out["replay"] = {k: np.concatenate([r["replay"][k] for r in parts]) for k in parts[0]["replay"]}
+        out["n_replay"] = sum(r["n_replay"] for r in parts)
+    return out
+
+
+def rollout_parallel(p, b, actions, pool, threads=None, env_id_base=0, log_cap=0, quota=0):
+    """rollout() (injected action stream) over env slabs on host threads."""
+    slabs = _slabs(b.n, threads)
+    pool = tuple(np.asarray(a) for a in pool)
+
+    def one(lo, hi):
+        sub = tuple(np.ascontiguousarray(a[:, lo:hi]) for a in pool)
+        return rollout(p, _slab_view(b, lo, hi), np.ascontiguousarray(actions[:, lo:hi]), sub, quota=quota,
+                       env_id_base=env_id_base + lo, log_cap=log_cap)
+    parts = _run_slabs(one, slabs)
+    return dict(counters=sum(r["counters"] for r in parts), ep_log=np.concatenate([r["ep_log"] for r in parts]),
+                n_log=sum(r["n_log"] for r in parts))
+
+
+def qnetrnn_forward_parallel(w: dict, obs, h, c, threads=None):
+    """qnetrnn_forward() over row slabs on host threads; h, c updated in place."""
+    n = obs.shape[0]
+    obs = np.ascontiguousarray(obs, dtype=np.float32)
+    parts = _run_slabs(lambda lo, hi: qnetrnn_forward(w, obs[lo:hi], h[lo:hi], c[lo:hi]), _slabs(n, threads))
+    return np.concatenate([q for q, _ in parts]), np.concatenate([a for _, a in parts])

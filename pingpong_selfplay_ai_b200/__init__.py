@@ -7,7 +7,8 @@ Host side: Python/PyTorch (buffers, streams, torch.distributed).  Compute: hand-
 """
 from . import _lib
 from ._lib import PongB200Error
-from .env import COUNTER_NAMES, PongEnv2P, ServePool, VecPongEnv2P
+from .env import (COUNTER_NAMES, PongEnv2P, ServePool, VecPongEnv2P, collide_batch,
+                  collide_sphere_with_moving_plane)
 from .params import ENV_DEFAULTS, make_params, resolve_env_config
 from .policy import NoisyLinear, Policy, QNet, QNetRNN, pack_qnet, pack_qnetrnn
 from .selfplay import (ReplayRing, SelfPlayEngine, eval_vs_model, eval_vs_pool, host_selfplay_eval, qnet_act,
@@ -18,7 +19,7 @@ from .checkpoint import Agent, load_agent
 
 __all__ = [
     "PongB200Error", "PongEnv2P", "VecPongEnv2P", "ServePool", "COUNTER_NAMES", "ENV_DEFAULTS", "make_params",
-    "resolve_env_config", "NoisyLinear", "QNet", "QNetRNN", "Policy", "pack_qnet", "pack_qnetrnn", "ReplayRing",
+    "resolve_env_config", "collide_batch", "collide_sphere_with_moving_plane", "NoisyLinear", "QNet", "QNetRNN", "Policy", "pack_qnet", "pack_qnetrnn", "ReplayRing",
     "SelfPlayEngine", "host_selfplay_eval", "qnet_act", "qnetrnn_act", "DQNTrainer", "PrioritizedSampler", "train_generation",
     "arena", "checkpoint", "Agent", "load_agent", "eval_vs_model", "eval_vs_pool",
 ]

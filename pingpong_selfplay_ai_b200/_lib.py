@@ -48,8 +48,8 @@ class PPServeSource(C.Structure):
 
 
 class PPPolicy(C.Structure):
-    _fields_ = [("kind", c_i32), ("precision", c_i32), ("eps_threshold", c_u64), ("follower_tol", c_f32),
-                ("reserved", c_i32), ("weights", c_vp), ("h", c_vp), ("c", c_vp)]
+    _fields_ = [("kind", c_i32), ("precision", c_i32), ("eps_threshold", c_u64), ("follower_tol", c_f64),
+                ("weights", c_vp), ("h", c_vp), ("c", c_vp)]
 
 
 class PPRolloutOut(C.Structure):
@@ -81,6 +81,7 @@ _PROTOTYPES = {
     "pp_env_observe": (C.c_int, [C.c_int, c_i64, P(PPEnvState), c_vp, c_vp, c_vp]),
     "pp_env_serve": (C.c_int, [C.c_int, c_i64, P(PPEnvState), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pp_env_reset": (C.c_int, [C.c_int, c_i64, P(PPParams), P(PPEnvState), c_vp, P(PPServeSource), c_i64, C.c_int, c_vp]),
+    "pp_collide": (C.c_int, [C.c_int, c_i64, P(PPParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pp_env_rollout": (C.c_int, [C.c_int, c_i64, c_i64, P(PPParams), P(PPEnvState), c_vp, P(PPServeSource), c_i32,
                                  c_i64, P(PPRolloutOut), c_vp]),
     "pp_qnet_act": (C.c_int, [c_i64, c_vp, P(PPPolicy), c_u64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),

@@ -112,10 +112,15 @@ def h2h_wins(database: dict):
 class _Match:
     """One pairing in flight: its own env slab, players, stream and episode log."""
 
-    def __init__(self, env_cfg, agent_a: Agent, agent_b: Agent, episodes: int, seed: int, precision, mode, device, stream):
+    def __init__(self, env_cfg, agent_a: Agent, agent_b: Agent, episodes: int, seed: int, precision, mode, device, stream,
+                 first_game: int = 0):
+        """first_game: games of this pairing already in the database.  Game g of a pairing is served from Philox
+        (seed, g, episode 0), so a top-up (first_game = played) continues the pairing's serve sequence instead of
+        replaying games that are already recorded."""
         self.a, self.b, self.n, self.stream = agent_a, agent_b, int(episodes), stream
         with torch.cuda.stream(stream):
-            self.env = VecPongEnv2P(self.n, device=device, mode=mode, serve="philox", seed=seed, **env_cfg)
+            self.env = VecPongEnv2P(self.n, device=device, mode=mode, serve="philox", seed=seed, env_id_base=int(first_game),
+                                    **env_cfg)
             self.env.reset()
             self.log = torch.zeros(self.n, 4, dtype=torch.int32, device=device)
             self.engine = SelfPlayEngine(self.env, agent_a.policy(self.n, precision, device),
@@ -137,9 +142,10 @@ class _Match:
 
 
 def play_match(env_cfg: dict, agent_a: Agent, agent_b: Agent, episodes: int, seed: int = 0, precision: str = "f32",
-               mode: str = "f64", device="cuda", max_steps: int = 1 << 20):
+               mode: str = "f64", device="cuda", max_steps: int = 1 << 20, first_game: int = 0):
     """`episodes` games of A (top paddle) against B (bottom paddle), all in one launch.  -> (score_a, score_b, ep_len)."""
-    m = _Match(env_cfg, agent_a, agent_b, episodes, seed, precision, mode, torch.device(device), torch.cuda.Stream(device))
+    m = _Match(env_cfg, agent_a, agent_b, episodes, seed, precision, mode, torch.device(device), torch.cuda.Stream(device),
+               first_game=first_game)
     m.launch(max_steps)
     return m.results()
 
@@ -160,6 +166,10 @@ def run_tournament(env_cfg: dict, database: dict, db_path, match_plan: list, rnn
     after each pairing.  Up to `concurrent` pairings are in flight on their own CUDA streams (a pairing of 100 games
     fills one SM).  `agents` may carry already loaded Agent objects by id; the others are loaded from the database's
     model records, and a model that fails to load only cancels its own pairings, as in the reference (:268-289).
+    Serves: the pairing with index j among ALL pairs of registered models (registration order, i.e. the order of a
+    first full plan) plays with seed + j, and its game g takes the Philox serve (seed + j, g, 0) where g counts the
+    pairing's games already in the database — a top-up after raising episodes_per_match plays NEW serves, like the
+    reference's process-wide RNG does on resume, instead of replaying recorded games.
     Several ranks (torch.distributed initialised, or shard=(rank, world)): pairing k is played by rank k % world with
     the same seed as on one GPU, results are gathered, EVERY rank extends its database identically (plan order; timestamps aside) and
     rank 0 alone writes the file — pairings are independent, so there is no data-path collective.
@@ -180,6 +190,8 @@ def run_tournament(env_cfg: dict, database: dict, db_path, match_plan: list, rnn
             agents[mid] = load_agent(info[mid], rnn_arch, root)
         except Exception as e:                                                # noqa: BLE001 — reference behaviour
             on_error(f"[arena] loading model {mid!r} failed: {e}")
+    pair_index = {pair: j for j, pair in enumerate(itertools.combinations([m["id"] for m in database["models"]], 2))}
+    played = Counter(tuple(sorted((r["p1"], r["p2"]))) for r in database["match_history"])
     results, flight = {}, []
     streams = [torch.cuda.Stream(device) for _ in range(max(1, int(concurrent)))] if match_factory is None else [object() for _ in range(max(1, int(concurrent)))]
 
@@ -207,7 +219,8 @@ def run_tournament(env_cfg: dict, database: dict, db_path, match_plan: list, rnn
             land(flight.pop(0))
         used = {id(m.stream) for m in flight}
         stream = next(s for s in streams if id(s) not in used)
-        m = make(env_cfg, agents[ida], agents[idb], match["episodes_to_run"], seed + k, precision, mode, device, stream)
+        m = make(env_cfg, agents[ida], agents[idb], match["episodes_to_run"], seed + pair_index.get((ida, idb), k), precision,
+                 mode, device, stream, first_game=played[tuple(sorted((ida, idb)))])
         m.launch(max_steps)
         flight.append(m)
     while flight:

@@ -15,7 +15,7 @@ On-disk formats (all present under the reference's checkpoints/ and checkpoints_
      V + (A - mean A) = A (tests/test_round_robin.py:155-164).  Sigma / epsilon keep their construction values: they
      do not enter an eval-mode forward.
   2. dueling NoisyNet QNet: `features.* / fc_V.* / fc_A.*` under 'modelB' / 'modelA'.
-  3. QNetRNN: `features_extractor.* / lstm.* / head_hidden_layer.* / fc_V.* / fc_A.*` under 'modelB_state' / 'modelA_state'.
+  3. QNetRNN: `features_extractor.* / lstm.* / fc_shared_head.0.* / fc_V.* / fc_A.*` under 'modelB_state' / 'modelA_state'.
 A bare state_dict (keys starting with `fc.` / `features`) is accepted as well (test_round_robin.py:145-147).
 
 tests/arena.py loads a legacy file with `load_state_dict(strict=False)` and NO remap (arena.py:185-187), which silently
@@ -39,7 +39,7 @@ AGENT_TYPES = ("QNet", "QNetRNN", "HardcodedBallFollower")
 
 def _looks_like_state_dict(obj) -> bool:
     return (isinstance(obj, dict) and len(obj) > 0 and all(not isinstance(v, dict) for v in obj.values())
-            and any(str(k).startswith(("fc.", "fc_", "features", "lstm.", "head_hidden_layer.")) for k in obj))
+            and any(str(k).startswith(("fc.", "fc_", "features", "lstm.", "fc_shared_head.")) for k in obj))
 
 
 def extract_state_dict(ckpt, order=EVAL_KEYS) -> dict:

@@ -102,6 +102,17 @@ int pp_env_reset(int mode, int64_t n, const PPParams *params, const PPEnvState *
                  "pp_env_reset");
 }
 
+int pp_collide(int mode, int64_t n, const PPParams *params, const void *vn, const void *vt, const void *u, const void *omega,
+               void *vn_out, void *vt_out, void *omega_out, void *stream) {
+    if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_collide");
+    if (n < 0) return fail(PP_E_SIZE, "pp_collide");
+    if (!params) return fail(PP_E_PARAM, "pp_collide");
+    if (!vn || !vt || !u || !omega || !vn_out || !vt_out || !omega_out) return fail(PP_E_NULL, "pp_collide");
+    if (n == 0) return 0;
+    return ok_or(pp::collide_launch(mode, n, *params, vn, vt, u, omega, vn_out, vt_out, omega_out, (cudaStream_t)stream),
+                 "pp_collide");
+}
+
 int pp_env_rollout(int mode, int64_t n, int64_t k, const PPParams *params, const PPEnvState *state, const uint8_t *actions,
                    const PPServeSource *serve, int32_t quota, int64_t env_id_base, const PPRolloutOut *out, void *stream) {
     if (!mode_ok(mode)) return fail(PP_E_MODE, "pp_env_rollout");
@@ -355,8 +366,8 @@ int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *pa
     PPServeSource src{PP_SERVE_QUEUE, quota, pvx, pvy, psp, 0, qhead, total};
     rc = pp::env_reset_launch(mode, n, *params, es, nullptr, src, 0, /*advance=*/0, st);     // env i starts on serve i
     if (rc) return fail(rc, fn);
-    PPPolicy pa{PP_POLICY_QNET, precision, 0, 0.f, 0, wa, nullptr, nullptr};
-    PPPolicy pb{PP_POLICY_QNET, precision, 0, 0.f, 0, wb, nullptr, nullptr};
+    PPPolicy pa{PP_POLICY_QNET, precision, 0, 0.0, wa, nullptr, nullptr};
+    PPPolicy pb{PP_POLICY_QNET, precision, 0, 0.0, wb, nullptr, nullptr};
     PPRolloutOut out{ctr, dlog, host_ep_log ? ep_log_cap : 0, ctr + 8, nullptr, nullptr, nullptr};
     const int64_t k = max_steps < 0x7fffffff ? max_steps : 0x7ffffffe;
     (void)chunk;                                                          // kept in the ABI; one launch needs no chunks

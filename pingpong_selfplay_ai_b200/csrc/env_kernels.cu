@@ -229,6 +229,18 @@ rollout_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_
     if (out.counters) tally.flush(out.counters);
 }
 
+// collide_sphere_with_moving_plane for n independent impacts (envs/physics.py:3-23): the arithmetic of paddle_event,
+// exposed so that the reference's `envs.physics` import has a device-backed drop-in and the known answers can be
+// checked through the C ABI.
+template <typename R>
+__global__ void collide_kernel(const PPParams params, int64_t n, const R *__restrict__ vn, const R *__restrict__ vt,
+                               const R *__restrict__ u, const R *__restrict__ om, R *__restrict__ vn_out,
+                               R *__restrict__ vt_out, R *__restrict__ om_out) {
+    const EnvConsts<R> c(params);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        impact<R>(c, vn[i], vt[i], u[i], om[i], vn_out[i], vt_out[i], om_out[i]);
+}
+
 // ------------------------------------------------------------------ host launchers
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -286,6 +298,19 @@ int env_reset_launch(int mode, int64_t n, const PPParams &p, const PPEnvState &s
         reset_kernel<double, true><<<blocks, 256, 0, stream>>>(p, st, n, mask, nullptr, nullptr, nullptr, src, env_id_base, advance);
     else
         reset_kernel<float, true><<<blocks, 256, 0, stream>>>(p, st, n, mask, nullptr, nullptr, nullptr, src, env_id_base, advance);
+    return (int)cudaGetLastError();
+}
+
+int collide_launch(int mode, int64_t n, const PPParams &p, const void *vn, const void *vt, const void *u, const void *om,
+                   void *vn_out, void *vt_out, void *om_out, cudaStream_t stream) {
+    const int64_t want = (n + 255) / 256;
+    const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+    if (mode == PP_MODE_F64)
+        collide_kernel<double><<<blocks, 256, 0, stream>>>(p, n, (const double *)vn, (const double *)vt, (const double *)u,
+                                                           (const double *)om, (double *)vn_out, (double *)vt_out, (double *)om_out);
+    else
+        collide_kernel<float><<<blocks, 256, 0, stream>>>(p, n, (const float *)vn, (const float *)vt, (const float *)u,
+                                                          (const float *)om, (float *)vn_out, (float *)vt_out, (float *)om_out);
     return (int)cudaGetLastError();
 }
 

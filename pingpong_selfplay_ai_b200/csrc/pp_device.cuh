@@ -82,6 +82,22 @@ template <typename R> __device__ __forceinline__ R move_paddle(R pos, int act, R
     return pos;
 }
 
+// collide_sphere_with_moving_plane(vn, vt, u, omega, e, mu, m, R)            envs/physics.py:3-23
+template <typename R>
+__device__ __forceinline__ void impact(const EnvConsts<R> &c, R vn, R vt, R u, R om, R &vn_post, R &vt_post, R &om_post) {
+    using X = Exact<R>;
+    vn_post = X::mul(c.neg_e, vn);                                                // (-e)*vn
+    const R jn = X::mul(c.m_1pe, X::abs(vn));                                     // (m*(1+e))*|vn|
+    R jt = X::mul(c.two_m_7, X::sub(X::add(u, X::mul(c.radius, om)), vt));        // ((2m)/7)*((u+R*w)-vt)
+    const R cap = X::mul(c.mu, jn);
+    if (!(X::abs(jt) <= cap)) {                                                   // slip
+        const R vrel = X::sub(X::sub(vt, u), X::mul(c.radius, om));
+        jt = X::mul(-cap, X::sign1(vrel));
+    }
+    vt_post = X::add(vt, X::div(jt, c.mass));
+    om_post = X::sub(om, X::div(X::mul(c.radius, jt), c.inertia));
+}
+
 // Ball beyond the top (bottom_side = false) or bottom line.  Hit: rigid impact
 // (envs/physics.py:3-23), snap to the line, bounce count, speed scaling (:227-232); returns true.
 template <typename R>
@@ -90,18 +106,12 @@ __device__ __forceinline__ bool paddle_event(const EnvConsts<R> &c, Env<R> &e, R
     const R lo = X::sub(pad, c.hw), hi = X::add(pad, c.hw);
     if (!(lo <= e.x && e.x <= hi)) return false;
     const R u = act == 0 ? -c.ps : (act == 2 ? c.ps : (R)0);
-    const R vn = bottom_side ? -e.vy : e.vy, vt = e.vx, om = e.spin;
-    const R vn_post = X::mul(c.neg_e, vn);                                        // (-e)*vn
-    const R jn = X::mul(c.m_1pe, X::abs(vn));                                     // (m*(1+e))*|vn|
-    R jt = X::mul(c.two_m_7, X::sub(X::add(u, X::mul(c.radius, om)), vt));        // ((2m)/7)*((u+R*w)-vt)
-    const R cap = X::mul(c.mu, jn);
-    if (!(X::abs(jt) <= cap)) {                                                   // slip
-        const R vrel = X::sub(X::sub(vt, u), X::mul(c.radius, om));
-        jt = X::mul(-cap, X::sign1(vrel));
-    }
+    const R vn = bottom_side ? -e.vy : e.vy;
+    R vn_post, vt_post, om_post;
+    impact<R>(c, vn, e.vx, u, e.spin, vn_post, vt_post, om_post);
     e.vy = bottom_side ? -vn_post : vn_post;
-    e.vx = X::add(vt, X::div(jt, c.mass));
-    e.spin = X::sub(om, X::div(X::mul(c.radius, jt), c.inertia));
+    e.vx = vt_post;
+    e.spin = om_post;
     e.y = bottom_side ? (R)1 : (R)0;
     e.bounce += 1;
     if (e.bounce % c.scale_every == 0) {

@@ -13,6 +13,8 @@ int env_serve_launch(int mode, int64_t n, const PPEnvState &st, const uint8_t *m
                      const void *spin, cudaStream_t stream);
 int env_reset_launch(int mode, int64_t n, const PPParams &p, const PPEnvState &st, const uint8_t *mask,
                      const PPServeSource &src, int64_t env_id_base, int advance, cudaStream_t stream);
+int collide_launch(int mode, int64_t n, const PPParams &p, const void *vn, const void *vt, const void *u, const void *om,
+                   void *vn_out, void *vt_out, void *om_out, cudaStream_t stream);
 int env_rollout_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const uint8_t *actions,
                        const PPServeSource &src, int32_t quota, int64_t env_id_base, const PPRolloutOut &out,
                        cudaStream_t stream);

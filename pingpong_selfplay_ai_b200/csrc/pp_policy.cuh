@@ -85,9 +85,12 @@ static __device__ __noinline__ int qnet_greedy_global(const float *__restrict__ 
 }
 
 // HardcodedBallFollower                                                      tests/arena.py:211-217
-__device__ __forceinline__ int follower_action(const float (&obs)[7], float tol) {
-    const float lo = __fsub_rn(obs[4], tol), hi = __fadd_rn(obs[4], tol);
-    return obs[0] < lo ? 0 : (obs[0] > hi ? 2 : 1);
+// obs are np.float32 scalars and the tolerance a Python float: under the reference's pinned numpy 1.24.3 (value-based
+// scalar promotion) `my_paddle_x - tolerance` and both compares are evaluated in float64.
+__device__ __forceinline__ int follower_action(const float (&obs)[7], double tol) {
+    const double x = (double)obs[0], pad = (double)obs[4];
+    const double lo = __dsub_rn(pad, tol), hi = __dadd_rn(pad, tol);
+    return x < lo ? 0 : (x > hi ? 2 : 1);
 }
 
 // epsilon-greedy overlay                                        scripts/train_iterative.py:124-130

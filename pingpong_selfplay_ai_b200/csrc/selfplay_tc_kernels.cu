@@ -54,6 +54,11 @@ template <int GROUPS> struct SmemMap {
     static constexpr uint32_t CTRL = GROUPS_OFF + (GROUPS * GROUP_BYTES > 2 * BLOB_BYTES ? GROUPS * GROUP_BYTES : 2 * BLOB_BYTES);
     static constexpr uint32_t TOTAL = CTRL + 64;                            // mbarriers + TMEM base
 };
+// control block (64 B): mbarriers [0] weights, [1 + g] group g at CTRL + 8 * b; the TMEM base slot follows them
+template <int GROUPS> struct CtrlMap {
+    static constexpr uint32_t TMEM_SLOT = (8 * (1 + GROUPS) + 15) / 16 * 16;
+    static_assert(8 * (1 + GROUPS) <= TMEM_SLOT && TMEM_SLOT + 4 <= 64, "TMEM base slot must not overlap the mbarriers");
+};
 
 struct PlayerTiles {     // shared-memory (generic) pointers of one player's operands
     uint8_t *w, *x;
@@ -182,7 +187,7 @@ __device__ __forceinline__ void issue_dense(uint32_t d, uint32_t a_tm, const Pla
 template <int GROUPS, typename M>
 __device__ __forceinline__ uint32_t tc_prologue(uint8_t *smem, const PPPolicy &pol_a, const PPPolicy &pol_b) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + M::CTRL);           // [0] weights, [1 + g] group g
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + M::CTRL + 32);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + M::CTRL + CtrlMap<GROUPS>::TMEM_SLOT);
     const int tid = threadIdx.x;
     const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
     if (tid == 0) {

@@ -102,3 +102,25 @@ def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if is_parallel():
         dist.broadcast(t, src)
     return t
+
+
+def all_ranks_ready(local_ready: bool, device=None) -> bool:
+    """True iff EVERY rank is ready (all-reduce MIN of a flag).  Whether an update step runs — and with it the gradient
+    all-reduce — must be ONE decision for all ranks: slabs of unequal size (slab_bounds) or different episode counts
+    cross the `enough replay data` threshold at different chunks, and ranks that issue different numbers of collectives
+    pair a gradient all-reduce with a counter all-reduce (hang or garbage)."""
+    if not is_parallel():
+        return bool(local_ready)
+    t = torch.tensor([1 if local_ready else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
+def broadcast_module_(module: torch.nn.Module, src: int = 0) -> None:
+    """Replicas start from rank `src`'s parameters and buffers (data-parallel training averages gradients, which keeps
+    replicas equal only if they start equal)."""
+    if not is_parallel():
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src)

@@ -238,6 +238,33 @@ class VecPongEnv2P:
         pass
 
 
+def collide_batch(vn, vt, u, omega, e, mu, m, R, mode: str = "f64", device="cuda"):
+    """collide_sphere_with_moving_plane (envs/physics.py:3-23) for arrays of impacts on the device (pp_collide) ->
+    (vn_post, vt_post, omega_post) tensors.  e, mu, m, R are scalars; their derived constants are formed with the
+    reference's own Python expressions (physics.py:7-11)."""
+    dev = _require_cuda(device)
+    lib = _lib.load()
+    dt = torch.float64 if mode == "f64" else torch.float32
+    ins = [torch.as_tensor(np.asarray(a, dtype=np.float64)).to(dev, dt).reshape(-1).contiguous() for a in (vn, vt, u, omega)]
+    n = ins[0].numel()
+    if any(t.numel() != n for t in ins):
+        raise ValueError("vn, vt, u, omega must have the same number of elements")
+    p = _lib.PPParams()
+    p.neg_e, p.m_1pe, p.inertia = float(-e), float(m * (1 + e)), float((2 / 5) * m * R ** 2)
+    p.two_m_over_7, p.mu, p.mass, p.radius = float(2 * m / 7.0), float(mu), float(m), float(R)
+    outs = [torch.empty(n, dtype=dt, device=dev) for _ in range(3)]
+    with torch.cuda.device(dev):
+        _lib.check(lib.pp_collide(_lib.MODE_F64 if mode == "f64" else _lib.MODE_F32, n, C.byref(p), *[_ptr(t) for t in ins],
+                                  *[_ptr(t) for t in outs], _stream_ptr(dev)), "pp_collide")
+    return tuple(outs)
+
+
+def collide_sphere_with_moving_plane(vn, vt, u, omega, e, mu, m, R):
+    """Drop-in for envs/physics.py:3 — one impact, Python floats in, a tuple of Python floats out."""
+    out = collide_batch([vn], [vt], [u], [omega], e, mu, m, R)
+    return tuple(float(t.item()) for t in out)
+
+
 class _MultiDiscrete:
     def __init__(self, nvec):
         self.nvec = np.asarray(nvec, dtype=np.int64)

@@ -284,5 +284,5 @@ class Policy:
 
     def struct(self) -> _lib.PPPolicy:
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-        return _lib.PPPolicy(self.kind, self.precision, eps_threshold(self.eps), self.tol, 0,
+        return _lib.PPPolicy(self.kind, self.precision, eps_threshold(self.eps), self.tol,
                              p(self.weights), p(self.h), p(self.c))

@@ -130,6 +130,7 @@ class DQNTrainer:
         are tested against and what runs on the CPU."""
         self.device = torch.device(device)
         self.model = model_b.to(self.device)
+        ppd.broadcast_module_(self.model)                # several ranks: every replica starts from rank 0's weights
         for p in self.model.features.parameters():                                   # :97
             p.requires_grad = False
         self.target = copy.deepcopy(self.model)
@@ -260,11 +261,17 @@ class DQNTrainer:
         else:
             ppd.allreduce_mean_grads(self.head_params)
 
-    def update(self, sampler: PrioritizedSampler, generator=None):
+    def ready(self, sampler) -> bool:
+        """This rank's ring holds enough rows for a batch (:134-135)."""
+        return len(sampler) >= self.batch_size
+
+    def update(self, sampler: PrioritizedSampler, generator=None, ready: bool | None = None):
         """One train_step().  Returns the loss (a 0-d device tensor: no host sync), or None while the ring holds fewer
         than batch_size rows (:134-135).  On CUDA the update is captured into CUDA graphs after three eager calls
-        (~150 tiny kernels per update are otherwise bound by launch overhead, 2.7 ms of host time each)."""
-        if len(sampler) < self.batch_size:
+        (~150 tiny kernels per update are otherwise bound by launch overhead, 2.7 ms of host time each).
+        `ready`: the decision to run, when the caller has made it collectively (dist.all_ranks_ready) — with several
+        ranks every rank must run the same number of updates, because each one contains a gradient all-reduce."""
+        if not (self.ready(sampler) if ready is None else ready):
             return None
         self.frame_idx += 1
         beta = min(1.0, self.beta_start + self.frame_idx * (1.0 - self.beta_start) / self.beta_frames)
@@ -323,6 +330,11 @@ def train_generation(engine: SelfPlayEngine, trainer: DQNTrainer, ring: ReplayRi
     counters_host = torch.zeros(8, dtype=torch.int64).pin_memory() if dev.type == "cuda" else None
     if engine.pb.weights is None:
         engine.pb = Policy.qnet(trainer.model, noisy=True, eps=epsilon, precision=precision, device=dev)
+    if ring.capacity < env.n * min(chunk, lockstep_steps):
+        # the kernel would keep only the last capacity / n steps of a launch while note_new_rows() counts n * k rows:
+        # the host's cursor would drift away from the device head and max-priority marking would hit the wrong slots
+        raise ValueError(f"replay ring of {ring.capacity} rows is smaller than one chunk ({env.n} envs x {chunk} steps)")
+    all_ready = False                                    # once every rank's ring holds a batch it stays that way
     while done_steps < lockstep_steps:
         k = min(chunk, lockstep_steps - done_steps)
         if trainer.fused:                                                              # B's noise: one draw per chunk
@@ -334,8 +346,10 @@ def train_generation(engine: SelfPlayEngine, trainer: DQNTrainer, ring: ReplayRi
         engine.run(k, ring=ring)
         done_steps += k
         sampler.note_new_rows(env.n * k)                 # no quota in training mode: every env writes a row per step
+        if not all_ready:
+            all_ready = ppd.all_ranks_ready(trainer.ready(sampler), dev)
         for _ in range(updates_per_chunk):
-            loss = trainer.update(sampler)
+            loss = trainer.update(sampler, ready=all_ready)
             if loss is not None:
                 losses.append(loss)
         # epsilon follows the slab's own episode count (slabs are statistically identical; no collective needed here).

@@ -122,6 +122,7 @@ class DRQNTrainer(DQNTrainer):
                  device="cuda", use_graph: bool = True):
         self.device = torch.device(device)
         self.model = model_b.to(self.device)
+        ppd.broadcast_module_(self.model)                # several ranks: every replica starts from rank 0's weights
         self.model.train()                                                               # :729
         self.target = copy.deepcopy(self.model)
         self.target.eval()                                                               # :337-338
@@ -170,9 +171,14 @@ class DRQNTrainer(DQNTrainer):
         self._post(sampler)
         return loss
 
-    def update(self, sampler: SequenceSampler, generator=None):
-        """One train_step_rnn().  None while fewer than batch_size episodes are stored (:404-407)."""
-        if len(sampler) < max(self.min_episodes, 1):
+    def ready(self, sampler) -> bool:
+        """This rank's ring stores at least batch_size complete episodes (:404-407)."""
+        return len(sampler) >= max(self.min_episodes, 1)
+
+    def update(self, sampler: SequenceSampler, generator=None, ready: bool | None = None):
+        """One train_step_rnn().  None while fewer than batch_size episodes are stored (:404-407).  `ready`: the
+        decision when the caller made it collectively (every rank must issue the same gradient all-reduces)."""
+        if not (self.ready(sampler) if ready is None else ready):
             return None
         if self.use_graph and generator is None and self.device.type == "cuda":
             loss = self._graphed(sampler, 0.0)
@@ -206,8 +212,10 @@ def train_rnn_generation(engine: SelfPlayEngine, trainer: DRQNTrainer, ring: Rep
         engine.run(k, ring=ring)
         done_steps += k
         sampler.refresh()
+        # stored-episode counts differ between slabs: ONE decision per chunk for all ranks (all-reduce MIN of the flag)
+        ready = ppd.all_ranks_ready(trainer.ready(sampler), dev)
         for _ in range(updates_per_chunk):
-            loss = trainer.update(sampler)
+            loss = trainer.update(sampler, ready=ready)
             if loss is not None:
                 losses.append(loss)
         episodes = int(env.counters[1].item())

@@ -77,6 +77,12 @@ def test_round_robin_tournament_on_the_device(H, tmp_path):
     assert len(plan2) == 6 and all(m["episodes_to_run"] == 3 for m in plan2)
     arena.run_tournament(cfg, db, db_path, plan2, agents=agents, seed=900, concurrent=2)
     assert len(db["match_history"]) == 6 * 40 and arena.create_match_plan(db, 40) == []
+    # ... and a top-up continues the pairing's serve sequence: its games are NEW games (Philox serve (seed + pair, g, 0)
+    # with g counting from the games already recorded), not copies of the first ones
+    sa, sb, ln = arena.play_match(cfg, agents["q0"], agents["q1"], 3, seed=100, first_game=37)
+    wa, wb, wl = _oracle_scores(cfg, agents, "q0", "q1", 40, 100)
+    assert np.array_equal(sa, wa[37:]) and np.array_equal(sb, wb[37:]) and np.array_equal(ln, wl[37:])
+    assert not np.array_equal(ln, wl[:3])
     # the same plan and seed replay the same games, whatever the number of pairings in flight
     db_b = {"models": list(models), "match_history": []}
     res_b = arena.run_tournament(cfg, db_b, None, plan, agents=agents, seed=100, concurrent=1)

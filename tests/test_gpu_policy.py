@@ -54,8 +54,15 @@ def test_follower_random_and_epsilon_greedy_match_oracle_rng(qg):
     obs[::5, 0] = obs[::5, 4]                                                  # inside the tolerance band
     dobs = torch.from_numpy(obs).cuda()
     a, _ = pp.qnet_act(dobs, pp.Policy.follower(tol=0.02), seed=seed, step_index=step, env_id_base=base)
-    lo, hi = obs[:, 4] - np.float32(0.02), obs[:, 4] + np.float32(0.02)
-    want = np.where(obs[:, 0] < lo, 0, np.where(obs[:, 0] > hi, 2, 1))
+    obs[1::5, 0] = obs[1::5, 4] - np.float32(0.02)                             # on the band's edge: float32 and float64
+    obs[2::5, 0] = obs[2::5, 4] + np.float32(0.02)                             # arithmetic decide differently here
+    dobs = torch.from_numpy(obs).cuda()
+    a, _ = pp.qnet_act(dobs, pp.Policy.follower(tol=0.02), seed=seed, step_index=step, env_id_base=base)
+    # the reference pins numpy 1.24.3: `np.float32 - 0.02` and the compares are float64 (tests/arena.py:211-217)
+    x, pad = obs[:, 0].astype(np.float64), obs[:, 4].astype(np.float64)
+    want = np.where(x < pad - 0.02, 0, np.where(x > pad + 0.02, 2, 1))
+    f32 = np.where(obs[:, 0] < obs[:, 4] - np.float32(0.02), 0, np.where(obs[:, 0] > obs[:, 4] + np.float32(0.02), 2, 1))
+    assert (want != f32).any()                                                 # the edge cases do tell the two apart
     assert np.array_equal(gu.np_of(a), want) and len(set(want.tolist())) == 3
     for stream in (1, 2):
         a, _ = pp.qnet_act(dobs, pp.Policy.random(), seed=seed, step_index=step, env_id_base=base, stream_id=stream)

@@ -347,7 +347,7 @@ def test_selfplay_tensor_core_env_bit_exact_under_its_own_actions(H, nets, mode,
     first_diff = np.where(same.all(axis=0), K, np.argmin(same, axis=0))
     agree = first_diff.sum() / (K * n)
     print(f"tensor-core closed loop: {100 * agree:.2f}% of env-steps before the first action disagreement")
-    assert agree > 0.9
+    assert agree >= 0.999                                       # measured 99.94 - 100 %
 
 
 def test_selfplay_tensor_core_mixed_players_and_win_rates(H, nets):
@@ -362,8 +362,8 @@ def test_selfplay_tensor_core_mixed_players_and_win_rates(H, nets):
         eng = pp.SelfPlayEngine(env, pp.Policy.qnet(nets["seed0"], precision=prec), pp.Policy.qnet(nets["seed1"], precision=prec), seed=3)
         res[prec] = eng.evaluate(quota, chunk=96)
         assert res[prec]["episodes"] == n * quota
-    assert abs(res["f32"]["win_rate_b"] - res["f16"]["win_rate_b"]) < 0.02
-    assert abs(res["f32"]["env_steps"] - res["f16"]["env_steps"]) < 0.03 * res["f32"]["env_steps"]
+    assert abs(res["f32"]["win_rate_b"] - res["f16"]["win_rate_b"]) <= 0.005
+    assert abs(res["f32"]["env_steps"] - res["f16"]["env_steps"]) <= 0.005 * res["f32"]["env_steps"]
     for a in (pp.Policy.follower(), pp.Policy.random()):
         env = pp.VecPongEnv2P(n, mode="f64", serve=pool, **cfg)
         env.reset()

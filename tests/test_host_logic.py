@@ -171,8 +171,8 @@ from pingpong_selfplay_ai_b200 import arena, checkpoint as ck, dist as ppd
 rank, world, _ = ppd.init_from_env("gloo")
 
 class StubMatch:                                   # stands in for a pairing on the device: scores are a function of the seed
-    def __init__(self, env_cfg, a, b, episodes, seed, precision, mode, device, stream):
-        self.a, self.b, self.n, self.seed, self.stream = a, b, episodes, seed, stream
+    def __init__(self, env_cfg, a, b, episodes, seed, precision, mode, device, stream, first_game=0):
+        self.a, self.b, self.n, self.seed, self.stream = a, b, episodes, seed + 1000 * first_game, stream
     def launch(self, max_steps):
         pass
     def results(self):
@@ -195,6 +195,15 @@ assert strip(db["match_history"]) == strip(one["match_history"]) and len(db["mat
 assert res.keys() == res1.keys() and all(np.array_equal(res[k][0], res1[k][0]) for k in res)
 assert os.path.exists(path) == (rank == 0)          # rank 0 alone writes the file
 assert arena.create_match_plan(db, 7) == []
+# a top-up continues each pairing's serve sequence (first_game = games already recorded) with the pairing's own seed
+plan2 = arena.create_match_plan(db, 9)
+seen = []
+class Spy(StubMatch):
+    def __init__(self, *a, first_game=0, **k):
+        seen.append((a[1].id, a[2].id, a[4], first_game))
+        super().__init__(*a, first_game=first_game, **k)
+arena.run_tournament({}, db, None, plan2[3:], agents=agents, seed=5, device="cpu", match_factory=Spy, shard=(0, 1))
+assert [s[3] for s in seen] == [7] * 7 and [s[2] for s in seen] == [5 + j for j in range(3, 10)]
 dist.barrier()
 dist.destroy_process_group()
 sys.stdout.write(f"ok {rank}\n"); sys.stdout.flush()
