@@ -37,6 +37,7 @@ ENV_CFG = dict(  # the env: block of the reference's config.yaml (values restate
 METRIC = "self-play env-steps/sec (env + both players' QNet action)"
 UNIT = "env-steps/s"
 FLOP_PER_ENV_STEP = 19200            # 2 players x 2 x 4800 MAC
+E2E_QUOTA = 32                       # episodes per env of one end-to-end call (eval_vs_model over 65536 x 32 = 2 M games)
 BYTES_PER_STEP_F64 = 203             # K1 single step, all outputs materialised, fp64 mode
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/):
 NCU_TRAFFIC = {("selfplay_tc_kernel", 256): 5.088512e6 + 95.744e3,     # r01_selfplay_tc256_final_metrics.txt, 65536 envs x 256 steps
@@ -264,6 +265,7 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=1500, help="reference arm: env-steps per process per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-calls", type=int, default=50, help="timed calls of the host-buffer entry")
     ap.add_argument("--no-k1", action="store_true", help="skip the single-step env kernel HBM roofline measurement")
     ap.add_argument("--k1-envs", type=int, default=16 << 20, help="envs of the single-step HBM roofline measurement")
     args = ap.parse_args()
@@ -370,10 +372,8 @@ def main():
 
     if rank == 0 and not args.no_k1:
         line["roofline_env_step"] = measure_k1(pp, dev, peaks, args.mode, args.k1_envs)
-    if rank == 0 and not args.no_e2e:
-        line["e2e"] = measure_e2e(pp, net_a, net_b, args)
-        if world > 1:
-            line["e2e"]["note"] = "measured on rank 0's GPU only (host-buffer entry is single-GPU)"
+    if not args.no_e2e:
+        line["e2e"] = measure_e2e(pp, net_a, net_b, args, rank, world, local, dev)
     if cpu_baseline is not None:
         line.update(cpu_baseline)
     if rank == 0:
@@ -568,33 +568,44 @@ def measure_k1(pp, dev, peaks, mode, n):
             "note": f"{per} algorithmic B per env-step (SURVEY.md 8d), working set {n * per / 2**20:.0f} MiB >> L2"}
 
 
-def measure_e2e(pp, net_a, net_b, args):
-    """The same metric through the reference-facing host-buffer call: numpy serves + packed weights in, counters out;
-    H2D / D2H copies and every sync inside the timed region (wall clock around the synchronous C-ABI call)."""
-    n, quota = args.envs, 8
-    rs = np.random.RandomState(0)
-    speed = rs.uniform(0.03, 0.05, size=(quota, n))
-    ang = np.radians(np.where(rs.rand(quota, n) < 0.5, rs.uniform(-60, -30, size=(quota, n)), rs.uniform(30, 60, size=(quota, n))))
-    rt = np.float64 if args.mode == "f64" else np.float32
+def measure_e2e(pp, net_a, net_b, args, rank=0, world=1, local=0, dev=None):
+    """The same metric through the reference-facing host-buffer call (pp_host_selfplay_eval = eval_vs_model,
+    scripts/train_iterative.py:171-181, for `envs` envs x `E2E_QUOTA` episodes each): packed weights in PINNED host memory
+    in, counters out; the H2D / D2H copies and every sync are inside the timed region (wall clock around the synchronous
+    C-ABI call).  Serves are drawn on the device from a host-supplied seed (the counterpart of random.seed()).  Every
+    rank calls the entry for ITS device and slab (device ordinal + env_id_base); value = all ranks' env-steps / slowest
+    rank's wall time."""
+    from pingpong_selfplay_ai_b200 import dist as ppd
+    n, quota, reps = args.envs, E2E_QUOTA, args.e2e_calls
+    keep = []
+
     def pinned(a):                                      # the step's inputs live in PINNED host memory (bench contract)
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         keep.append(t)
         return t.numpy()
-    keep = []
-    pool = tuple(pinned(a) for a in ((speed * np.cos(ang)).astype(rt), (speed * np.sin(ang)).astype(rt),
-                                     rs.uniform(-5, 5, size=(quota, n)).astype(rt)))
     wa, wb = pinned(pp.pack_qnet(net_a).cpu().numpy()), pinned(pp.pack_qnet(net_b).cpu().numpy())
-    pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep, precision=args.precision)  # warm-up
-    reps, steps_total, t0 = 3, 0, time.perf_counter()
-    for _ in range(reps):
-        c, _ = pp.host_selfplay_eval(ENV_CFG, n, quota, pool, wa, wb, mode=args.mode, chunk=args.lockstep, precision=args.precision)
-        steps_total += c["env_steps"]
+    call = lambda s: pp.host_selfplay_eval(ENV_CFG, n, quota, None, wa, wb, mode=args.mode, precision=args.precision,
+                                           device=local, seed=s, env_id_base=rank * n)
+    for s in range(3):
+        call(1000 + s)                                  # warm-up (staging buffers, kernel attributes)
+    if world > 1:
+        torch.distributed.barrier()
+    steps_total, episodes, t0 = 0, 0, time.perf_counter()
+    for s in range(reps):
+        c, _ = call(s)
+        steps_total += c["env_steps"]; episodes += c["episodes"]
     wall = time.perf_counter() - t0
-    h2d = 3 * quota * n * np.dtype(rt).itemsize + 2 * wa.nbytes
-    return {"value": steps_total / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 72,
-            "call": "pp_host_selfplay_eval (eval_vs_model for 65536 envs x 8 episodes each; pinned host numpy buffers in, "
-                    "counters out; serve queue, one launch)",
-            "episodes_per_call": int(c["episodes"]), "env_steps_per_call": int(c["env_steps"]), "ms_per_call": 1e3 * wall / reps}
+    wall_max = ppd.max_over_ranks(wall, dev)
+    if world > 1:
+        t = torch.tensor([steps_total, episodes], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(t)
+        steps_total, episodes = int(t[0].item()), int(t[1].item())
+    in_bytes = 2 * ((wa.nbytes + 255) // 256 * 256) + 256
+    return {"value": steps_total / wall_max, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": 72,
+            "call": f"pp_host_selfplay_eval on every rank (eval_vs_model for {n} envs x {quota} episodes per GPU; pinned host "
+                    "weight blobs in, counters out; serves drawn on the device from a host seed; serve queue, one launch)",
+            "calls": reps, "ranks": world, "episodes_per_call_per_gpu": episodes // (reps * world),
+            "env_steps_per_call_per_gpu": steps_total // (reps * world), "ms_per_call": 1e3 * wall_max / reps}
 
 
 if __name__ == "__main__":

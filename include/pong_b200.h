@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 5
+#define PP_ABI_VERSION 6
 
 enum { PP_MODE_F64 = 0, PP_MODE_F32 = 1 };
 
@@ -83,7 +83,8 @@ typedef struct PPEnvState {
  *   PP_SERVE_PHILOX  Philox4x32-10 keyed by (seed; global env id, episode index): same formula,
  *                    distribution-equal, and independent of how envs are sharded over GPUs.
  *   PP_SERVE_QUEUE   evaluation mode: the pool is ONE queue of queue_total serves (flat index q = j * n + i, the
- *                    same memory as a [depth][n] pool) and an env that finishes an episode claims the next
+ *                    same memory as a [depth][n] pool; or, with all three pool pointers NULL, serve q is the Philox
+ *                    serve (seed; env q % n, episode q / n)) and an env that finishes an episode claims the next
  *                    unplayed serve with an atomic on *queue_head instead of waiting for its own next one.  Every
  *                    serve is still played exactly once and an episode depends on nothing but its serve and the
  *                    (greedy) players, so counters and episode-log rows (env = q % n, episode = q / n) equal
@@ -272,16 +273,24 @@ int pp_replay_scatter(int64_t n, const PPReplayRing *ring, const float *obs, con
                       void *stream);
 
 /* Whole evaluation from HOST buffers (what a reference caller holds): eval_vs_model of
- * scripts/train_iterative.py:171-181 for n envs x quota episodes each, QNet A vs QNet B.
- * Copies serves and weights to the device, plays the n x quota serves as ONE queue (PP_SERVE_QUEUE: an env that
- * finishes claims the next unplayed serve) in a single launch of at most max_steps lock-step steps (`chunk` is kept
- * in the signature and ignored), copies counters[8] and per-episode records back.
- * host_ep_log may be NULL.  Returns after the results are in the host buffers. */
-int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *params,
+ * scripts/train_iterative.py:171-181 for n envs x quota episodes each, QNet A vs QNet B, on GPU `device`.
+ * Serves: host_pool_* = real[quota][n] arrays drawn by the caller (the reference's env.reset() formula, any RNG), or
+ * all three NULL = drawn on the device from Philox keyed by (seed; env_id_base + i, episode j) — the counterpart of
+ * random.seed(seed) before the reference's loop; nothing but the two weight blobs (39 KB) then crosses PCIe.
+ * Copies inputs to the device, plays the n x quota serves as ONE queue (PP_SERVE_QUEUE: an env that finishes claims the
+ * next unplayed serve) in a single launch of at most max_steps lock-step steps, copies counters[8] and the per-episode
+ * records back (host_ep_log may be NULL).  Returns after the results are in the host buffers.
+ * Sharding: one call per GPU with its own `device`, slab size n and env_id_base (results do not depend on the split);
+ * calls for different devices may run concurrently from different host threads or processes, calls for one device
+ * are serialised.  The staging buffers of a device are kept between calls; pp_host_release(device) frees them
+ * (device = -1: all).  The caller's current CUDA device is left unchanged. */
+int pp_host_selfplay_eval(int device, int mode, int64_t n, int32_t quota, const PPParams *params,
                           const void *host_pool_vx, const void *host_pool_vy, const void *host_pool_spin,
+                          uint64_t seed, int64_t env_id_base,
                           const float *host_weights_a, const float *host_weights_b, int32_t precision,
-                          int64_t chunk, int64_t max_steps,
+                          int64_t max_steps,
                           unsigned long long *host_counters, int32_t *host_ep_log, int64_t ep_log_cap);
+int pp_host_release(int device);
 
 /* ---- training mode (scripts/train_iterative.py): three small launches per update instead of ~130 framework kernels */
 

@@ -55,23 +55,25 @@ def load_reference():
     if not reference_available():
         raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
     _install_stubs()
-    # the reference's top-level packages are `envs` and `models`; this repo must not
-    # shadow them, so put the reference root FIRST for the duration of the import.
-    for name in ("envs", "envs.physics", "envs.my_pong_env_2p", "models", "models.qnet", "models.qnet_rnn"):
-        mod = sys.modules.get(name)
-        if mod is None:
-            continue
+    # The reference's top-level packages are `envs` and `models` (namespace packages: no __init__.py).  This repository
+    # ships import-compatible shims under the same names as REGULAR packages, which win over namespace packages
+    # whatever the order of sys.path — so bind the two package names to the reference's directories explicitly.
+    import importlib
+    for name in [m for m in sys.modules if m.split(".")[0] in ("envs", "models")]:
+        mod = sys.modules[name]
         where = getattr(mod, "__file__", None) or next(iter(getattr(mod, "__path__", [])), "")
         if not str(where).startswith(REFERENCE_ROOT):
             del sys.modules[name]
-    sys.path.insert(0, REFERENCE_ROOT)
-    try:
-        from envs.my_pong_env_2p import PongEnv2P
-        from envs.physics import collide_sphere_with_moving_plane
-        from models.qnet import QNet
-        from models.qnet_rnn import QNetRNN
-    finally:
-        sys.path.remove(REFERENCE_ROOT)
+    for pkg in ("envs", "models"):
+        if pkg not in sys.modules:
+            mod = types.ModuleType(pkg)
+            mod.__path__ = [os.path.join(REFERENCE_ROOT, pkg)]
+            sys.modules[pkg] = mod
+    PongEnv2P = importlib.import_module("envs.my_pong_env_2p").PongEnv2P
+    collide_sphere_with_moving_plane = importlib.import_module("envs.physics").collide_sphere_with_moving_plane
+    QNet = importlib.import_module("models.qnet").QNet
+    QNetRNN = importlib.import_module("models.qnet_rnn").QNetRNN
+    assert sys.modules["envs.my_pong_env_2p"].__file__.startswith(REFERENCE_ROOT)
     return PongEnv2P, collide_sphere_with_moving_plane, QNet, QNetRNN
 
 

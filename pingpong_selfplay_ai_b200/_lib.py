@@ -13,7 +13,7 @@ from . import build as _build
 
 c_i32, c_i64, c_u64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_void_p
 
-PP_ABI_VERSION = 5
+PP_ABI_VERSION = 6
 MODE_F64, MODE_F32 = 0, 1
 SERVE_POOL, SERVE_PHILOX, SERVE_QUEUE = 0, 1, 2
 POLICY_QNET, POLICY_QNETRNN, POLICY_FOLLOWER, POLICY_RANDOM = 0, 1, 2, 3
@@ -98,8 +98,9 @@ _PROTOTYPES = {
     "pp_per_sample": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_u64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "pp_per_sample_scratch_floats": (c_i64, [c_i64]),
     "pp_adam_step": (C.c_int, [P(PPAdamParam), c_i32, c_f64, c_f64, c_f64, c_f64, c_vp]),
-    "pp_host_selfplay_eval": (C.c_int, [C.c_int, c_i64, c_i32, P(PPParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
-                                        c_i64, c_i64, c_vp, c_vp, c_i64]),
+    "pp_host_selfplay_eval": (C.c_int, [C.c_int, C.c_int, c_i64, c_i32, P(PPParams), c_vp, c_vp, c_vp, c_u64, c_i64,
+                                        c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_i64]),
+    "pp_host_release": (C.c_int, [C.c_int]),
 }
 
 EXPORTS = tuple(_PROTOTYPES)

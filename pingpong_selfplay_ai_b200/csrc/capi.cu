@@ -2,6 +2,7 @@
 // and the HOST-buffer evaluation entry (pp_host_selfplay_eval).  No kernel code lives here.
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "pp_host.h"
@@ -29,7 +30,10 @@ bool params_ok(const PPParams *p) { return p && p->speed_scale_every > 0 && p->m
 bool serve_ok(const PPServeSource *s) {
     if (!s) return false;
     if (s->kind == PP_SERVE_POOL) return s->depth > 0 && s->pool_vx && s->pool_vy && s->pool_spin;
-    if (s->kind == PP_SERVE_QUEUE) return s->queue_total > 0 && s->queue_total < 0x7fffffff && s->queue_head && s->pool_vx && s->pool_vy && s->pool_spin;
+    if (s->kind == PP_SERVE_QUEUE) {                 // with a pool, or (all three NULL) Philox serves keyed by `seed`
+        const int have = (s->pool_vx != nullptr) + (s->pool_vy != nullptr) + (s->pool_spin != nullptr);
+        return s->queue_total > 0 && s->queue_total < 0x7fffffff && s->queue_head && (have == 0 || have == 3);
+    }
     return s->kind == PP_SERVE_PHILOX;
 }
 bool policy_ok(const PPPolicy *p, bool allow_rnn) {
@@ -283,19 +287,29 @@ int pp_adam_step(const PPAdamParam *params, int32_t count, double lr, double bet
 }
 
 // ---------------------------------------------------------------------------------------------
-// Host-buffer evaluation.  Owns a small cache of device staging buffers (grown on demand, freed at
-// process exit) so repeated calls do not pay cudaMalloc; everything runs on one private stream.
+// Host-buffer evaluation.  One context per device ordinal (stream + device staging + pinned staging, grown on demand,
+// released by pp_host_release): calls for different devices run concurrently from different host threads, calls for
+// the same device are serialised by the context's mutex.  Nothing is bound to "the current device" of the process.
 namespace {
-struct HostEvalCache {
+struct HostEvalCtx {
+    std::mutex mu;
     cudaStream_t stream = nullptr;
     void *dev = nullptr;
     size_t dev_bytes = 0;
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
 };
-HostEvalCache g_cache;
+constexpr int MAX_DEVICES = 64;
+std::mutex g_ctx_mu;
+HostEvalCtx *g_ctx[MAX_DEVICES] = {};
 
-int ensure(HostEvalCache &c, size_t dev_bytes, size_t pinned_bytes) {
+HostEvalCtx *ctx_for(int device) {
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    if (!g_ctx[device]) g_ctx[device] = new HostEvalCtx();
+    return g_ctx[device];
+}
+
+int ensure(HostEvalCtx &c, size_t dev_bytes, size_t pinned_bytes) {          // the context's device is current
     cudaError_t e;
     if (!c.stream && (e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
     if (dev_bytes > c.dev_bytes) {
@@ -312,78 +326,121 @@ int ensure(HostEvalCache &c, size_t dev_bytes, size_t pinned_bytes) {
     }
     return 0;
 }
+void release(HostEvalCtx &c) {
+    if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); c.stream = nullptr; }
+    if (c.dev) { cudaFree(c.dev); c.dev = nullptr; c.dev_bytes = 0; }
+    if (c.pinned) { cudaFreeHost(c.pinned); c.pinned = nullptr; c.pinned_bytes = 0; }
+}
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DeviceGuard {             // make `device` current for the call, restore the caller's device afterwards
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 }  // namespace
 
-int pp_host_selfplay_eval(int mode, int64_t n, int32_t quota, const PPParams *params, const void *host_pool_vx,
-                          const void *host_pool_vy, const void *host_pool_spin, const float *host_weights_a,
-                          const float *host_weights_b, int32_t precision, int64_t chunk, int64_t max_steps,
-                          unsigned long long *host_counters, int32_t *host_ep_log, int64_t ep_log_cap) {
+int pp_host_selfplay_eval(int device, int mode, int64_t n, int32_t quota, const PPParams *params,
+                          const void *host_pool_vx, const void *host_pool_vy, const void *host_pool_spin, uint64_t seed,
+                          int64_t env_id_base, const float *host_weights_a, const float *host_weights_b, int32_t precision,
+                          int64_t max_steps, unsigned long long *host_counters, int32_t *host_ep_log, int64_t ep_log_cap) {
     const char *fn = "pp_host_selfplay_eval";
     if (!mode_ok(mode) || (precision != PP_PREC_F32 && precision != PP_PREC_F16)) return fail(PP_E_MODE, fn);
-    if (n <= 0 || quota <= 0 || chunk <= 0 || max_steps <= 0 || ep_log_cap < 0) return fail(PP_E_SIZE, fn);
+    if (device < 0 || device >= MAX_DEVICES) return fail(PP_E_SIZE, fn);
+    if (n <= 0 || quota <= 0 || max_steps <= 0 || ep_log_cap < 0 || env_id_base < 0) return fail(PP_E_SIZE, fn);
     if (!params_ok(params)) return fail(PP_E_PARAM, fn);
-    if (!host_pool_vx || !host_pool_vy || !host_pool_spin || !host_weights_a || !host_weights_b || !host_counters)
-        return fail(PP_E_NULL, fn);
+    const int pools = (host_pool_vx != nullptr) + (host_pool_vy != nullptr) + (host_pool_spin != nullptr);
+    if ((pools != 0 && pools != 3) || !host_weights_a || !host_weights_b || !host_counters) return fail(PP_E_NULL, fn);
+    const int64_t total = (int64_t)n * quota;
+    if (total >= 0x7fffffff) return fail(PP_E_SIZE, fn);
+
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail((int)guard.err, fn);
+    HostEvalCtx &ctx = *ctx_for(device);
+    std::lock_guard<std::mutex> lock(ctx.mu);
+
     const size_t rs = mode == PP_MODE_F64 ? 8 : 4;
-    const size_t pool_bytes = align_up((size_t)quota * n * rs, 256);
+    const size_t pool_bytes = pools ? align_up((size_t)total * rs, 256) : 0;
     const size_t real_bytes = align_up((size_t)n * rs, 256), int_bytes = align_up((size_t)n * 4, 256);
     const size_t blob_bytes = align_up(PP_QNET_BLOB_FLOATS * sizeof(float), 256);
+    const size_t in_bytes = 2 * blob_bytes + 256;                             // [weights A][weights B][queue head]
     const size_t log_bytes = align_up((size_t)(host_ep_log ? ep_log_cap : 0) * 16, 256);
-    const size_t dev_bytes = 3 * pool_bytes + 7 * real_bytes + 5 * int_bytes + 2 * blob_bytes + 256 + log_bytes;
-    int rc = ensure(g_cache, dev_bytes, 256);                 // pinned: counters[8] + log count + queue head
+    const size_t dev_bytes = 3 * pool_bytes + 7 * real_bytes + 5 * int_bytes + in_bytes + 256 + log_bytes;
+    int rc = ensure(ctx, dev_bytes, in_bytes + 256);                          // pinned: the inputs + counters[8] + log count
     if (rc) return fail(rc, fn);
-    cudaStream_t st = g_cache.stream;
-    char *d = (char *)g_cache.dev;
+    cudaStream_t st = ctx.stream;
+    char *d = (char *)ctx.dev;
     auto take = [&](size_t b) { char *p = d; d += b; return (void *)p; };
-    void *pvx = take(pool_bytes), *pvy = take(pool_bytes), *psp = take(pool_bytes);
+    char *d_in = (char *)take(in_bytes);
+    float *wa = (float *)d_in, *wb = (float *)(d_in + blob_bytes);
+    unsigned long long *qhead = (unsigned long long *)(d_in + 2 * blob_bytes);
+    unsigned long long *ctr = (unsigned long long *)take(256);                // counters[8] + ep_log_count
     PPEnvState es{};
     es.ball_x = take(real_bytes); es.ball_y = take(real_bytes); es.ball_vx = take(real_bytes); es.ball_vy = take(real_bytes);
     es.spin = take(real_bytes); es.top_paddle_x = take(real_bytes); es.bottom_paddle_x = take(real_bytes);
     es.score_a = (int32_t *)take(int_bytes); es.score_b = (int32_t *)take(int_bytes); es.bounce_count = (int32_t *)take(int_bytes);
     es.ep_idx = (int32_t *)take(int_bytes); es.ep_len = (int32_t *)take(int_bytes);
-    float *wa = (float *)take(blob_bytes), *wb = (float *)take(blob_bytes);
-    unsigned long long *ctr = (unsigned long long *)take(256);          // counters[8] + ep_log_count
     int32_t *dlog = host_ep_log ? (int32_t *)take(log_bytes) : nullptr;
+    void *pvx = pools ? take(pool_bytes) : nullptr, *pvy = pools ? take(pool_bytes) : nullptr, *psp = pools ? take(pool_bytes) : nullptr;
 
     cudaError_t e;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return fail((int)e, fn); } while (0)
-    CK(cudaMemcpyAsync(pvx, host_pool_vx, (size_t)quota * n * rs, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(pvy, host_pool_vy, (size_t)quota * n * rs, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(psp, host_pool_spin, (size_t)quota * n * rs, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(wa, host_weights_a, PP_QNET_BLOB_FLOATS * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(wb, host_weights_b, PP_QNET_BLOB_FLOATS * sizeof(float), cudaMemcpyHostToDevice, st));
+    // the small inputs travel as ONE copy from the pinned staging block: both weight blobs + the queue cursor
+    char *h_in = (char *)ctx.pinned;
+    unsigned long long *h_out = (unsigned long long *)(h_in + in_bytes);
+    memcpy(h_in, host_weights_a, PP_QNET_BLOB_FLOATS * sizeof(float));
+    memcpy(h_in + blob_bytes, host_weights_b, PP_QNET_BLOB_FLOATS * sizeof(float));
+    *(unsigned long long *)(h_in + 2 * blob_bytes) = (unsigned long long)(n < total ? n : total);   // serves 0..n-1 are taken at reset
+    CK(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctr, 0, 256, st));
+    if (pools) {
+        CK(cudaMemcpyAsync(pvx, host_pool_vx, (size_t)total * rs, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pvy, host_pool_vy, (size_t)total * rs, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(psp, host_pool_spin, (size_t)total * rs, cudaMemcpyHostToDevice, st));
+    }
     // The n x quota serves form ONE queue (PP_SERVE_QUEUE): an env that finishes an episode claims the next unplayed
     // serve, so no env idles while others still have episodes to play; outcomes per serve are unchanged.  The whole
     // evaluation is a single launch: every group leaves the step loop once the queue is drained and its envs are done.
-    unsigned long long *h = (unsigned long long *)g_cache.pinned;
-    const int64_t total = (int64_t)n * quota;
-    if (total >= 0x7fffffff) return fail(PP_E_SIZE, fn);
-    h[16] = (unsigned long long)n;                                        // queue_head: serves 0..n-1 are taken at reset
-    unsigned long long *qhead = ctr + 16;
-    CK(cudaMemcpyAsync(qhead, h + 16, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-    PPServeSource src{PP_SERVE_QUEUE, quota, pvx, pvy, psp, 0, qhead, total};
-    rc = pp::env_reset_launch(mode, n, *params, es, nullptr, src, 0, /*advance=*/0, st);     // env i starts on serve i
+    PPServeSource src{PP_SERVE_QUEUE, quota, pvx, pvy, psp, seed, qhead, total};
+    rc = pp::env_reset_launch(mode, n, *params, es, nullptr, src, env_id_base, /*advance=*/0, st);   // env i starts on serve i
     if (rc) return fail(rc, fn);
     PPPolicy pa{PP_POLICY_QNET, precision, 0, 0.0, wa, nullptr, nullptr};
     PPPolicy pb{PP_POLICY_QNET, precision, 0, 0.0, wb, nullptr, nullptr};
     PPRolloutOut out{ctr, dlog, host_ep_log ? ep_log_cap : 0, ctr + 8, nullptr, nullptr, nullptr};
     const int64_t k = max_steps < 0x7fffffff ? max_steps : 0x7ffffffe;
-    (void)chunk;                                                          // kept in the ABI; one launch needs no chunks
     rc = precision == PP_PREC_F16
-             ? pp::selfplay_tc_launch(mode, n, k, *params, es, pa, pb, 0, 0, src, (int32_t)total, 0, out, nullptr, st)
-             : pp::selfplay_launch(mode, n, k, *params, es, pa, pb, 0, 0, src, (int32_t)total, 0, out, nullptr, st);
+             ? pp::selfplay_tc_launch(mode, n, k, *params, es, pa, pb, seed, 0, src, (int32_t)total, env_id_base, out, nullptr, st)
+             : pp::selfplay_launch(mode, n, k, *params, es, pa, pb, seed, 0, src, (int32_t)total, env_id_base, out, nullptr, st);
     if (rc) return fail(rc, fn);
-    CK(cudaMemcpyAsync(h, ctr, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_out, ctr, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    memcpy(host_counters, h, 8 * sizeof(unsigned long long));
+    memcpy(host_counters, h_out, 8 * sizeof(unsigned long long));
     if (host_ep_log) {
-        const unsigned long long rows = h[8] < (unsigned long long)ep_log_cap ? h[8] : (unsigned long long)ep_log_cap;
+        const unsigned long long rows = h_out[8] < (unsigned long long)ep_log_cap ? h_out[8] : (unsigned long long)ep_log_cap;
         CK(cudaMemcpyAsync(host_ep_log, dlog, rows * 16, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
 #undef CK
+    return 0;
+}
+
+int pp_host_release(int device) {
+    if (device < -1 || device >= MAX_DEVICES) return fail(PP_E_SIZE, "pp_host_release");
+    for (int dv = 0; dv < MAX_DEVICES; ++dv) {
+        if (device != -1 && dv != device) continue;
+        HostEvalCtx *c;
+        { std::lock_guard<std::mutex> lock(g_ctx_mu); c = g_ctx[dv]; }
+        if (!c) continue;
+        std::lock_guard<std::mutex> lock(c->mu);
+        if (!c->stream && !c->dev && !c->pinned) continue;
+        DeviceGuard guard(dv);
+        if (guard.err != cudaSuccess) return fail((int)guard.err, "pp_host_release");
+        release(*c);
+    }
     return 0;
 }
 

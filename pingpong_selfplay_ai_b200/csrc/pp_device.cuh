@@ -198,12 +198,15 @@ static __device__ __noinline__ void philox_serve(const PPParams &p, uint64_t see
 template <typename R>
 __device__ __forceinline__ void next_serve(const PPParams &p, const PPServeSource &src, int64_t n, int64_t i,
                                            int64_t env_id_base, int ep, R &vx, R &vy, R &spin) {
-    if (src.kind != PP_SERVE_PHILOX) {
-        const int64_t j = src.kind == PP_SERVE_QUEUE ? (int64_t)ep : (int64_t)(ep % src.depth) * n + i;
+    const bool queue = src.kind == PP_SERVE_QUEUE;
+    if (src.kind == PP_SERVE_POOL || (queue && src.pool_vx != nullptr)) {
+        const int64_t j = queue ? (int64_t)ep : (int64_t)(ep % src.depth) * n + i;
         vx = ((const R *)src.pool_vx)[j]; vy = ((const R *)src.pool_vy)[j]; spin = ((const R *)src.pool_spin)[j];
-    } else {
+    } else {                     // Philox; a queue without a pool: serve q is (env q % n, episode q / n) of the same stream
+        const int64_t env = queue ? (int64_t)ep % n : i;
+        const uint32_t episode = queue ? (uint32_t)(ep / n) : (uint32_t)ep;
         double dvx, dvy, ds;
-        philox_serve(p, src.seed, (uint32_t)(env_id_base + i), (uint32_t)ep, dvx, dvy, ds);
+        philox_serve(p, src.seed, (uint32_t)(env_id_base + env), episode, dvx, dvy, ds);
         vx = (R)dvx; vy = (R)dvy; spin = (R)ds;
     }
 }

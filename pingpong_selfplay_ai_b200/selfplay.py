@@ -168,23 +168,31 @@ class SelfPlayEngine:
         return c
 
 
-def host_selfplay_eval(env_kwargs: dict, n: int, quota: int, pool, weights_a, weights_b, mode="f64", chunk=64,
-                       max_steps=1 << 20, ep_log_cap=0, precision="f32"):
-    """eval_vs_model for n envs x quota episodes from HOST buffers through the C ABI (pp_host_selfplay_eval):
-    serves [quota, n] x3 and the two packed QNet blobs are numpy arrays; returns (counters dict, ep_log)."""
+def host_selfplay_eval(env_kwargs: dict, n: int, quota: int, pool, weights_a, weights_b, mode="f64", chunk=None,
+                       max_steps=1 << 20, ep_log_cap=0, precision="f32", device: int = 0, seed: int = 0,
+                       env_id_base: int = 0):
+    """eval_vs_model for n envs x quota episodes from HOST buffers through the C ABI (pp_host_selfplay_eval) on GPU
+    `device`: the two packed QNet blobs are numpy arrays; serves are `pool` = three numpy arrays [quota, n], or
+    pool=None = drawn on the device from Philox(seed; env_id_base + i, episode).  Returns (counters dict, ep_log).
+    Needs no torch CUDA context: everything below this call is the C library's."""
+    del chunk                                            # one launch; kept for callers of the round-1 signature
     lib = _lib.load()
     rt = np.float64 if mode == "f64" else np.float32
     params = make_params(resolve_env_config(env_kwargs))
-    pvx, pvy, psp = (np.ascontiguousarray(a, dtype=rt) for a in pool)
-    assert pvx.shape == (quota, n)
+    if pool is not None:
+        pvx, pvy, psp = (np.ascontiguousarray(a, dtype=rt) for a in pool)
+        assert pvx.shape == (quota, n)
+    else:
+        pvx = pvy = psp = None
     wa = np.ascontiguousarray(weights_a, dtype=np.float32)
     wb = np.ascontiguousarray(weights_b, dtype=np.float32)
     counters = np.zeros(8, np.uint64)
     log = np.zeros((max(ep_log_cap, 1), 4), np.int32) if ep_log_cap else None
     vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-    _lib.check(lib.pp_host_selfplay_eval(_lib.MODE_F64 if mode == "f64" else _lib.MODE_F32, n, quota, C.byref(params),
-                                         vp(pvx), vp(pvy), vp(psp), vp(wa), vp(wb),
-                                         {"f32": _lib.PREC_F32, "f16": _lib.PREC_F16}[precision], chunk, max_steps,
+    _lib.check(lib.pp_host_selfplay_eval(int(device), _lib.MODE_F64 if mode == "f64" else _lib.MODE_F32, n, quota,
+                                         C.byref(params), vp(pvx), vp(pvy), vp(psp), int(seed) & (2 ** 64 - 1),
+                                         int(env_id_base), vp(wa), vp(wb),
+                                         {"f32": _lib.PREC_F32, "f16": _lib.PREC_F16}[precision], max_steps,
                                          vp(counters), vp(log), ep_log_cap), "pp_host_selfplay_eval")
     return dict(zip(COUNTER_NAMES, (int(v) for v in counters))), log
 

@@ -124,6 +124,37 @@ def test_host_selfplay_eval_from_host_buffers(H, nets):
     assert np.array_equal(key(log[:n * quota]), key(w["ep_log"]))
 
 
+def test_host_selfplay_eval_device_serves_sharded_and_vs_oracle(H, nets):
+    """pool=None: serves are drawn on the device from Philox(seed; global env id, episode).  One call for n envs ==
+    two calls for the two half slabs (device ordinal, env_id_base per call: the sharded form of the entry), from host
+    threads at the same time; and the games are the oracle's for the same serves."""
+    from concurrent.futures import ThreadPoolExecutor
+    cfg = H["env_config_yaml"]
+    n, quota, seed = 900, 2, 4242
+    wa, wb = pp.pack_qnet(nets["seed0"]).numpy(), pp.pack_qnet(nets["seed1"]).numpy()
+    key = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]
+    for prec in ("f32", "f16"):
+        call = lambda lo, hi: pp.host_selfplay_eval(cfg, hi - lo, quota, None, wa, wb, ep_log_cap=(hi - lo) * quota,
+                                                    precision=prec, seed=seed, env_id_base=lo, device=0)
+        c, log = call(0, n)
+        with ThreadPoolExecutor(2) as ex:
+            (c0, log0), (c1, log1) = ex.map(lambda s: call(*s), [(0, n // 3), (n // 3, n)])
+        assert c["episodes"] == n * quota and all(c[k] == c0[k] + c1[k] for k in pp.COUNTER_NAMES)
+        assert np.array_equal(key(log), key(np.concatenate([log0, log1])))
+        if prec == "f32":
+            serves = np.array([[po.philox_serve(seed, i, j, cfg) for i in range(n)] for j in range(quota)])   # [quota, n, 3]
+            pool = tuple(np.ascontiguousarray(serves[:, :, k]) for k in range(3))
+            b = po.EnvBatch(n, "f64")
+            b.serve(pool[0][0], pool[1][0], pool[2][0])
+            w = po.selfplay(po.make_params(cfg), b, _oracle_policy(po.POLICY_QNET, nets["seed0"]),
+                            _oracle_policy(po.POLICY_QNET, nets["seed1"]), 4096, pool, quota=quota, log_cap=n * quota)
+            assert np.array_equal(key(log), key(w["ep_log"]))
+            assert all(c[k] == w["counters"][i] for i, k in enumerate(pp.COUNTER_NAMES))
+    assert pp._lib.load().pp_host_release(-1) == 0
+    c2, _ = pp.host_selfplay_eval(cfg, n, quota, None, wa, wb, precision="f16", seed=seed)      # buffers come back on demand
+    assert c2 == c
+
+
 def test_shard_invariance_philox(H, nets):
     """n envs on one slab == the same envs as two slabs with env_id_base offsets (serves, exploration and random
     players are keyed by the GLOBAL env id), so multi-GPU sharding cannot change any outcome."""
