@@ -247,12 +247,15 @@ def workload_config(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--lockstep", type=int, default=None,
-                    help="lock-step env steps per launch (default: 256 for the headline workload, 64 for the others)")
+                    help="lock-step env steps per launch (default: 16384 for the headline workload = 0.1 s per launch, so "
+                         "that the timed region of --steps 20 is seconds of sustained load; 64 for the others)")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the config4_rnn / config5_train objects (BASELINE.json configs[3] and configs[4])")
     ap.add_argument("--mode", default="f64", choices=["f64", "f32"])
     ap.add_argument("--precision", default="f16", choices=["f32", "f16"],
                     help="QNet path: f16 = tcgen05 tensor cores (fp16 hi/lo operands, fp32 accumulate, ~1e-6 of fp32); "
@@ -271,7 +274,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.lockstep is None:
-        args.lockstep = 256 if args.workload == "qnet" else 64
+        args.lockstep = 16384 if args.workload == "qnet" else 64
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -370,10 +373,17 @@ def main():
                         "note": f"algorithmic {flop} FLOP per env-step (both players' net) x env-steps per launch / "
                                 "CUDA-event launch time, per GPU"}
 
+    line["timed_region_s"] = dev_ms * 1e-3
     if rank == 0 and not args.no_k1:
         line["roofline_env_step"] = measure_k1(pp, dev, peaks, args.mode, args.k1_envs)
     if not args.no_e2e:
         line["e2e"] = measure_e2e(pp, net_a, net_b, args, rank, world, local, dev)
+    if args.workload == "qnet" and not args.no_secondary:
+        del eng, env, flush
+        torch.cuda.empty_cache()
+        line["config4_rnn"] = measure_config4_rnn(pp, ppd, args, dev, rank, world, local, peaks)
+        torch.cuda.empty_cache()
+        line["config5_train"] = measure_config5_train(pp, ppd, args, dev, rank, world, local, peaks)
     if cpu_baseline is not None:
         line.update(cpu_baseline)
     if rank == 0:
@@ -538,6 +548,183 @@ def measure_cpu_baseline() -> dict:
     except Exception as e:  # an extra data point, not part of the contract
         out["cpu_baseline_c_oracle"] = {"error": str(e)}
     return out
+
+
+RNN_ENV_CFG = dict(ENV_CFG, speed_scale_every=5, speed_increment=0.2)      # config_rnn.yaml:27-28 (restated)
+RNN_FLOP_PER_ENV_STEP = 626432       # 2 players x 2 x 156 608 MAC
+CONFIG4_ENVS, CONFIG5_ENVS = 262144, 1048576
+
+
+def _port_rnn_loop(n_steps: int) -> float:
+    """QNetRNN A vs B on the CPU port (tests/arena.py:294-308 shaped: batch-1 recurrent forwards) -> env-steps/s."""
+    import random
+
+    from oracle import pong_port
+    from oracle.policy_torch import QNetRNNPort
+    torch.set_num_threads(1)
+    random.seed(1)
+    torch.manual_seed(0); net_a = QNetRNNPort().eval()
+    torch.manual_seed(1); net_b = QNetRNNPort().eval()
+    env = pong_port.PongPort(**RNN_ENV_CFG)
+    oa, ob = env.reset()
+    ha, hb = net_a.init_hidden(1, "cpu"), net_b.init_hidden(1, "cpu")
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(n_steps):
+            qa, ha = net_a(torch.tensor(oa, dtype=torch.float32).unsqueeze(0).unsqueeze(0), ha)
+            qb, hb = net_b(torch.tensor(ob, dtype=torch.float32).unsqueeze(0).unsqueeze(0), hb)
+            (oa, ob), _, done, _ = env.step(int(qa.argmax(1).item()), int(qb.argmax(1).item()))
+            if done:
+                oa, ob = env.reset()
+                ha, hb = net_a.init_hidden(1, "cpu"), net_b.init_hidden(1, "cpu")
+    return n_steps / (time.perf_counter() - t0)
+
+
+def _port_train_loop(n_steps: int) -> float:
+    """The reference's training loop (scripts/train_iterative.py:238-261: env step + both forwards + memory.push +
+    train_step of batch 256 per env step) on the CPU port -> env-steps/s."""
+    from oracle import pong_port
+    from oracle.policy_torch import QNetPort
+    from oracle.train_port import TrainLoopPort
+    import random
+    torch.set_num_threads(1)
+    random.seed(3); np.random.seed(3)
+    torch.manual_seed(0); a = QNetPort()
+    torch.manual_seed(1); b = QNetPort()
+    loop = TrainLoopPort(pong_port.PongPort(**ENV_CFG), a, b, memory_size=100000)
+    loop.run(300)                                       # fills the first batch: train_step runs from step 256 on
+    t0 = time.perf_counter()
+    loop.run(n_steps)
+    return n_steps / (time.perf_counter() - t0)
+
+
+def _sum_over_ranks(values, dev, world):
+    if world == 1:
+        return [int(v) for v in values]
+    t = torch.tensor(list(values), dtype=torch.int64, device=dev)
+    torch.distributed.all_reduce(t)
+    return [int(v) for v in t.tolist()]
+
+
+def measure_config4_rnn(pp, ppd, args, dev, rank, world, local, peaks):
+    """BASELINE.json configs[3]: QNetRNN (LSTM) A vs B rollout with per-env hidden state, 262 144 envs SPLIT over the
+    ranks (strong scaling), fused obs -> QNetRNN -> argmax + env step on the tensor-core recurrent kernel."""
+    lo, hi = ppd.slab_bounds(CONFIG4_ENVS, world, rank)
+    n, k, launches, warm = hi - lo, 32, 16, 3
+    env = pp.VecPongEnv2P(n, device=dev, mode=args.mode, serve="philox", seed=2026, env_id_base=lo, **RNN_ENV_CFG)
+    env.reset()
+    torch.manual_seed(0); net_a = pp.QNetRNN()
+    torch.manual_seed(1); net_b = pp.QNetRNN()
+    eng = pp.SelfPlayEngine(env, pp.Policy.qnetrnn(net_a, num_envs=n, device=dev, precision=args.precision),
+                            pp.Policy.qnetrnn(net_b, num_envs=n, device=dev, precision=args.precision), seed=7)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warm):
+        eng.run(k)
+    torch.cuda.synchronize()
+    env.counters.zero_()
+    sampler = ClockSampler(local).start()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(launches)]
+    for s, e in ev:
+        flush.zero_()
+        s.record(); eng.run(k); e.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = ppd.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev), dev)
+    steps, episodes = _sum_over_ranks([env.counters[0].item(), env.counters[1].item()], dev, world)
+    assert steps == CONFIG4_ENVS * k * launches, (steps, CONFIG4_ENVS, k, launches)
+    value = steps / (ms * 1e-3)
+    tf = value / world * RNN_FLOP_PER_ENV_STEP / 1e12
+    out = {"metric": "QNetRNN self-play env-steps/sec (env + both players' LSTM action)", "value": value, "unit": UNIT,
+           "n_gpus": world, "scaling": "strong", "envs_total": CONFIG4_ENVS, "envs_per_gpu": n, "lockstep_steps_per_launch": k,
+           "launches": launches, "warmup": warm, "ms_per_launch": ms / launches, "env_steps_per_s_per_gpu": value / world,
+           "dtype": f"{args.mode} env state + {args.precision} QNetRNN", "clocks": clocks, "episodes": episodes,
+           "roofline": {"bound": "tensor", "kernel": "selfplay_rnn_tc_kernel" if args.precision == "f16" else "selfplay_rnn_kernel",
+                        "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"],
+                        "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained",
+                        "note": f"algorithmic {RNN_FLOP_PER_ENV_STEP} FLOP per env-step (both players' net) x env-steps per "
+                                "launch / CUDA-event launch time, per GPU"},
+           "config": {"workload": "configs[3]: QNetRNN (LSTM) A vs B rollout with per-env hidden state, 262144 envs split over "
+                                  "the GPUs, greedy, auto-reset (Philox serves), config_rnn.yaml env params",
+                      "l2": "flushed between timed launches"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v = _port_rnn_loop(2500)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": "2500 env-steps of the reference-shaped recurrent loop (pure-Python env port + torch "
+                                         "batch-1 QNetRNN A and B), one process"}
+    return out
+
+
+def measure_config5_train(pp, ppd, args, dev, rank, world, local, peaks):
+    """BASELINE.json configs[4]: a train_iterative generation chunk loop, 1 048 576 envs SPLIT over the ranks:
+    epsilon-greedy rollout of the learner B (train-mode NoisyNet weights) + replay rows + PER Double-DQN updates of
+    batch 256 per rank with the NCCL all-reduce of the 520 head gradients inside every update + counter all-reduce."""
+    lo, hi = ppd.slab_bounds(CONFIG5_ENVS, world, rank)
+    n, k, upc = hi - lo, 64, 4
+    chunks, warm = 24 * world, 6                        # every rank times the same number of chunks (collectives inside)
+    env = pp.VecPongEnv2P(n, device=dev, mode=args.mode, serve="philox", seed=2027, env_id_base=lo, **ENV_CFG)
+    env.reset()
+    torch.manual_seed(0); net_a = pp.QNet()
+    torch.manual_seed(1); net_b = pp.QNet()
+    trainer = pp.DQNTrainer(net_b, batch_size=256, device=dev)
+    eng = pp.SelfPlayEngine(env, pp.Policy.qnet(net_a, noisy=True, precision=args.precision, device=dev),
+                            pp.Policy.qnet(net_b, noisy=True, eps=0.5, precision=args.precision, device=dev), seed=7)
+    ring = pp.ReplayRing(max(1 << 20, n * k), device=dev)
+    sampler = pp.PrioritizedSampler(ring)
+    kw = dict(chunk=k, updates_per_chunk=upc, epsilon=0.5, precision=args.precision)
+    pp.train_generation(eng, trainer, ring, sampler, k * warm, **kw)
+    torch.cuda.synchronize()
+    clock = ClockSampler(local).start()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = pp.train_generation(eng, trainer, ring, sampler, k * chunks, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = clock.stop()
+    sec = ppd.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    assert out["env_steps"] == CONFIG5_ENVS * k * chunks and out["updates"] == upc * chunks
+    # the collective alone: the flat 520-float gradient buffer, 200 all-reduces back to back
+    ar_us = None
+    if world > 1:
+        flat = trainer._flat_grad
+        for _ in range(10):
+            ppd.allreduce_mean_flat_(flat)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(200):
+            ppd.allreduce_mean_flat_(flat)
+        a1.record(); torch.cuda.synchronize()
+        ar_us = ppd.max_over_ranks(a0.elapsed_time(a1) * 1e3 / 200, dev)
+    value = out["env_steps"] / sec
+    tf = value / world * FLOP_PER_ENV_STEP / 1e12
+    res = {"metric": "training-mode env-steps/sec (epsilon-greedy rollout + replay rows + PER Double-DQN updates)",
+           "value": value, "unit": UNIT, "n_gpus": world, "scaling": "strong", "envs_total": CONFIG5_ENVS, "envs_per_gpu": n,
+           "lockstep_steps_per_chunk": k, "updates_per_chunk": upc, "batch_per_rank": 256, "chunks": chunks, "warmup_chunks": warm,
+           "ms_per_chunk": 1e3 * sec / chunks, "updates_per_s": out["updates"] / sec, "grad_allreduce_us": ar_us,
+           "grad_allreduce": ("captured inside the update's CUDA graph" if getattr(trainer, "_split", True) is False and world > 1
+                              else ("eager NCCL all-reduce between two CUDA graphs" if world > 1 else "single rank: none")),
+           "mean_loss": out["mean_loss"], "epsilon": out["epsilon"], "episodes": out["episodes"], "replay_capacity": ring.capacity,
+           "dtype": f"{args.mode} env state + {args.precision} QNet rollout, fp32 update", "clocks": clocks,
+           "roofline": {"bound": "tensor", "kernel": "selfplay_tc_kernel (rollout with replay rows)", "achieved": tf,
+                        "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"], "traffic": None,
+                        "peak_source": f"{peaks['src']} bf16 sustained",
+                        "note": f"algorithmic {FLOP_PER_ENV_STEP} FLOP per env-step x env-steps / chunk-loop time incl. the "
+                                "updates, per GPU; replay rows add 62 B of HBM writes per env-step"},
+           "config": {"workload": "configs[4]: train_iterative generation chunk loop, 1048576 envs split over the GPUs, "
+                                  "epsilon-greedy rollout + replay scatter + batched PER Double-DQN + NCCL all-reduce of "
+                                  "gradients and counters"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v = _port_train_loop(400)
+        res["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": "400 env-steps of the reference's training loop restated on the CPU port (env step + "
+                                         "both forwards + PER push + one train_step of batch 256 per env step), one process"}
+    return res
 
 
 def measure_k1(pp, dev, peaks, mode, n):

@@ -45,7 +45,13 @@ constexpr uint32_t W1H_OFF = 0, W1L_OFF = W1H_OFF + W1_BYTES, W2H_OFF = W1L_OFF 
                    B3_OFF = W3L_OFF + W3_BYTES, PLAYER_W_BYTES = B3_OFF + B3_BYTES;              // 27136
 constexpr uint32_t X_BYTES = 2 * G_ROWS * 16;                                                    // 4096
 constexpr uint32_t GROUP_BYTES = 2 * X_BYTES;                                                    // X rows of both players
-constexpr uint32_t TM_R1 = 64, TM_LO = 32;      // TMEM columns: region R1 = R0 + 64; inside R1: hi at +0, lo at +32
+constexpr uint32_t H_BYTES = 16 * G_ROWS * 16;  // one hidden-activation A tile in shared memory: [16 chunks][128 rows][8 halves],
+                                                // chunks 0..7 = hi (K = 64), 8..15 = lo                                  32768
+constexpr uint32_t TM_R1 = 64;                  // TMEM columns of a group: region R0 at +0, R1 at +64 (64 columns each)
+// A hidden-activation operand written IN PLACE over the accumulator it was computed from: accumulator columns
+// [32 h, 32 h + 32) become packed hi pairs [32 h, +16) and packed lo pairs [32 h + 16, +16).  K step j (16 units) of the
+// hi part therefore starts at column tm_hi(j), of the lo part at tm_hi(j) + 16.
+__device__ __forceinline__ constexpr uint32_t tm_hi(int j) { return (uint32_t)((j >> 1) * 32 + (j & 1) * 8); }
 constexpr uint32_t BLOB_BYTES = PP_QNET_BLOB_FLOATS * 4;                                         // 19728
 
 template <int GROUPS> struct SmemMap {
@@ -101,31 +107,54 @@ __device__ void build_weight_tiles(uint8_t *wt, const float *blob, int tid, int 
     }
 }
 
-// Accumulator row (64 fp32 columns at `src`) -> ReLU -> hi/lo fp16 -> this thread's row of the next A operand in
-// TMEM (`dst`: 32 columns of packed hi pairs, then 32 columns of packed lo pairs).  hi = rz(relu(x)) <= relu(x), so
-// for x >= 0 the residual x - hi is >= 0 and for x < 0 it is x < 0: one more ReLU-convert yields lo = relu(x) - hi.
-__device__ __forceinline__ void hidden_epilogue(uint32_t src, uint32_t dst) {
+// 32 accumulator values -> ReLU -> packed fp16 hi pairs and lo pairs.  hi = rz(relu(x)) <= relu(x), so for x >= 0 the
+// residual x - hi is >= 0 and for x < 0 it is x < 0: one more ReLU-convert yields lo = relu(x) - hi.
+__device__ __forceinline__ void split32(const uint32_t (&r0)[16], const uint32_t (&r1)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                                             // residuals as one packed FADD2 per pair
+        const float a = __uint_as_float(r0[2 * j]), b = __uint_as_float(r0[2 * j + 1]);
+        hi[j] = tc::pack_f16x2_rz_relu(a, b);
+        const float2 ra = __fadd2_rn(make_float2(a, b), make_float2(-h2f(hi[j], 0), -h2f(hi[j], 1)));
+        lo[j] = tc::pack_f16x2<true>(ra.x, ra.y);
+        const float c = __uint_as_float(r1[2 * j]), d = __uint_as_float(r1[2 * j + 1]);
+        hi[8 + j] = tc::pack_f16x2_rz_relu(c, d);
+        const float2 rc = __fadd2_rn(make_float2(c, d), make_float2(-h2f(hi[8 + j], 0), -h2f(hi[8 + j], 1)));
+        lo[8 + j] = tc::pack_f16x2<true>(rc.x, rc.y);
+    }
+}
+
+// Accumulator row (64 fp32 columns at `acc`) -> ReLU -> hi/lo fp16 -> written IN PLACE over the same columns as this
+// thread's row of the next A operand (layout: tm_hi()).  Hidden activations never touch shared memory.
+__device__ __forceinline__ void hidden_epilogue_inplace(uint32_t acc) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t r0[16], r1[16], hi[16], lo[16];
-        tc::tmem_ld16(src + half * 32, r0);
-        tc::tmem_ld16(src + half * 32 + 16, r1);
+        tc::tmem_ld16(acc + half * 32, r0);
+        tc::tmem_ld16(acc + half * 32 + 16, r1);
         tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {                                         // residuals as one packed FADD2 per pair
-            const float a = __uint_as_float(r0[2 * j]), b = __uint_as_float(r0[2 * j + 1]);
-            hi[j] = tc::pack_f16x2_rz_relu(a, b);
-            const float2 ra = __fadd2_rn(make_float2(a, b), make_float2(-h2f(hi[j], 0), -h2f(hi[j], 1)));
-            lo[j] = tc::pack_f16x2<true>(ra.x, ra.y);
-            const float c = __uint_as_float(r1[2 * j]), d = __uint_as_float(r1[2 * j + 1]);
-            hi[8 + j] = tc::pack_f16x2_rz_relu(c, d);
-            const float2 rc = __fadd2_rn(make_float2(c, d), make_float2(-h2f(hi[8 + j], 0), -h2f(hi[8 + j], 1)));
-            lo[8 + j] = tc::pack_f16x2<true>(rc.x, rc.y);
-        }
-        tc::tmem_st16(dst + half * 16, hi);
-        tc::tmem_st16(dst + TM_LO + half * 16, lo);
+        split32(r0, r1, hi, lo);
+        tc::tmem_st16(acc + half * 32, hi);
+        tc::tmem_st16(acc + half * 32 + 16, lo);
     }
     tc::tmem_st_wait();
+}
+
+// The same, but the operand goes to a shared-memory A tile (H_BYTES, K-major, no swizzle): it frees the accumulator
+// region at once, which is what lets the two players' second layers follow each other without a drain in between.
+__device__ __forceinline__ void hidden_epilogue_smem(uint32_t acc, uint8_t *tile, int row) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t r0[16], r1[16], hi[16], lo[16];
+        tc::tmem_ld16(acc + half * 32, r0);
+        tc::tmem_ld16(acc + half * 32 + 16, r1);
+        tc::tmem_ld_wait();
+        split32(r0, r1, hi, lo);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                         // chunk = 8 hidden units = 4 packed words
+            *reinterpret_cast<uint4 *>(tile + (half * 4 + q) * A_LBO + row * 16) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            *reinterpret_cast<uint4 *>(tile + (8 + half * 4 + q) * A_LBO + row * 16) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+    }
 }
 
 // Second hidden layer's accumulator row (64 fp32 columns at `src`) -> ReLU -> the four head outputs in fp32 on the CUDA
@@ -166,21 +195,27 @@ __device__ __forceinline__ void issue_l1(uint32_t d, const PlayerTiles &p) {
     tc::umma_f16(d, x, tc::smem_desc(tc::smem_u32(p.w + W1H_OFF), 64 * 16, SBO), tc::idesc_f16(128, 64), false);
     tc::umma_f16(d, x, tc::smem_desc(tc::smem_u32(p.w + W1L_OFF), 64 * 16, SBO), tc::idesc_f16(128, 64), true);
 }
-// D = Hh*Wh + Hl*Wh + Hh*Wl + X*B'   (N = 64 hidden layer or N = 16 heads); H = [hi | lo] in TMEM at a_tm
-template <int N>
-__device__ __forceinline__ void issue_dense(uint32_t d, uint32_t a_tm, const PlayerTiles &p, uint32_t wh_off, uint32_t wl_off,
-                                            uint32_t b_off) {
-    const uint32_t wh = tc::smem_u32(p.w + wh_off), wl = tc::smem_u32(p.w + wl_off);
-    constexpr uint32_t B_LBO = N * 16;
+// D = Hh*Wh + Hl*Wh + Hh*Wl + X*B'  (second layer, N = 64): H = the in-place operand in TMEM at a_tm (A_SMEM = false)
+// or the shared-memory tile `h_tile` (A_SMEM = true)
+template <bool A_SMEM>
+__device__ __forceinline__ void issue_l2(uint32_t d, uint32_t a_tm, const uint8_t *h_tile, const PlayerTiles &p) {
+    const uint32_t wh = tc::smem_u32(p.w + W2H_OFF), wl = tc::smem_u32(p.w + W2L_OFF);
+    constexpr uint32_t B_LBO = 64 * 16;
+    const uint32_t ht = A_SMEM ? tc::smem_u32(h_tile) : 0u;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = pass == 1 ? a_tm + TM_LO : a_tm, b = pass == 2 ? wl : wh;
+        const uint32_t b = pass == 2 ? wl : wh;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)         // K = 16 per MMA = 8 TMEM columns of A, 2 shared-memory chunks of B
-            tc::umma_f16_ts(d, a + j * 8, tc::smem_desc(b + j * 2 * B_LBO, B_LBO, SBO), tc::idesc_f16(128, N), (pass | j) != 0);
+        for (int j = 0; j < 4; ++j) {       // K = 16 per MMA = 8 TMEM columns / 2 shared-memory chunks of A, 2 chunks of B
+            const uint64_t bd = tc::smem_desc(b + j * 2 * B_LBO, B_LBO, SBO);
+            if (A_SMEM)
+                tc::umma_f16(d, tc::smem_desc(ht + ((pass == 1 ? 8 : 0) + 2 * j) * A_LBO, A_LBO, SBO), bd, tc::idesc_f16(128, 64), (pass | j) != 0);
+            else
+                tc::umma_f16_ts(d, a_tm + tm_hi(j) + (pass == 1 ? 16u : 0u), bd, tc::idesc_f16(128, 64), (pass | j) != 0);
+        }
     }
-    tc::umma_f16(d, tc::smem_desc(tc::smem_u32(p.x), A_LBO, SBO), tc::smem_desc(tc::smem_u32(p.w + b_off), B_LBO, SBO),
-                 tc::idesc_f16(128, N), true);
+    tc::umma_f16(d, tc::smem_desc(tc::smem_u32(p.x), A_LBO, SBO), tc::smem_desc(tc::smem_u32(p.w + B2_OFF), B_LBO, SBO),
+                 tc::idesc_f16(128, 64), true);
 }
 
 // Shared prologue: barriers, TMEM, weights.  Returns the TMEM base of the CTA.
@@ -222,8 +257,10 @@ template <int GROUPS> __device__ __forceinline__ void tc_epilogue(uint32_t tmem)
 // One policy evaluation round for a group: X rows are already written and published by a group barrier.
 struct GroupCtx {
     PlayerTiles pa, pb;
+    uint8_t *h_tile;                             // shared-memory A tile of player B's hidden activations (fused kernel only)
     uint64_t *bar;
     uint32_t parity, r0, bar_id, lane_addr;      // r0: the group's first TMEM column (lane 0); R1 = r0 + TM_R1
+    int row;
     bool qa, qb, issuer_warp;
 };
 
@@ -233,49 +270,76 @@ __device__ __forceinline__ void group_wait(GroupCtx &g) {
     tc::tc_fence_after();
 }
 
-// 0 = L1, 1 = L2 of player p; an elected lane of the group's first warp issues, everybody waits
-__device__ __forceinline__ void group_mma(GroupCtx &g, const PlayerTiles &p, int layer) {
+// an elected lane of the group's first warp runs `issue` and commits to the group's mbarrier
+template <typename F> __device__ __forceinline__ void group_issue(GroupCtx &g, F &&issue) {
     if (g.issuer_warp) {                      // warp-uniform branch
         if (tc::elect_one()) {
             tc::tc_fence_after();
-            if (layer == 0) issue_l1(g.r0, p);
-            else issue_dense<64>(g.r0, g.r0 + TM_R1, p, W2H_OFF, W2L_OFF, B2_OFF);
+            issue();
             tc::umma_commit(g.bar);
         }
         __syncwarp();
     }
-    group_wait(g);
 }
 
-// per QNet player: L1 -> H1 -> L2 -> (ReLU, fp32 heads on the CUDA cores) -> Q, in the group's two TMEM regions
+// ONE QNet player p: L1 -> R0; H in place; L2 -> R1; (ReLU, fp32 heads on the CUDA cores) -> Q
+__device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles &p, float (&q)[3]) {
+    group_issue(g, [&] { issue_l1(g.r0, p); });
+    group_wait(g);
+    hidden_epilogue_inplace(g.r0 + g.lane_addr);
+    tc::tc_fence_before();
+    tc::bar_sync(g.bar_id, G_ROWS);
+    group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, p); });
+    group_wait(g);
+    heads_epilogue(g.r0 + TM_R1 + g.lane_addr, p.w + W3H_OFF, q);
+}
+
+// BOTH players (the self-play hot path).  A group owns two 64-column TMEM regions R0, R1 and one shared-memory A tile:
+//   both first layers at once   L1_A -> R0, L1_B -> R1                                        (one round trip)
+//   epilogues                   H_A written IN PLACE over R0;  H_B to the shared-memory tile, which frees R1
+//   L2_A (A = R0 in TMEM) -> R1
+//   as soon as L2_A has completed (R0 is dead):  L2_B (A = shared-memory tile) -> R0, issued BEFORE heads_A, so that its
+//   flight is covered by the 260 instructions of heads_A (reads R1)
+//   heads_B (reads R0)
+// Two exposed MMA round trips and two group barriers per lock-step step (the serial A-then-B chain had four and four).
+__device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
+    group_issue(g, [&] { issue_l1(g.r0, g.pa); issue_l1(g.r0 + TM_R1, g.pb); });
+    group_wait(g);
+    hidden_epilogue_smem(g.r0 + TM_R1 + g.lane_addr, g.h_tile, g.row);
+    hidden_epilogue_inplace(g.r0 + g.lane_addr);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    tc::bar_sync(g.bar_id, G_ROWS);
+    group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, g.pa); });
+    group_wait(g);
+    group_issue(g, [&] { issue_l2<true>(g.r0, 0u, g.h_tile, g.pb); });
+    heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pa.w + W3H_OFF, q_a);
+    group_wait(g);
+    heads_epilogue(g.r0 + g.lane_addr, g.pb.w + W3H_OFF, q_b);
+}
+
 __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
-    bool first = true;
-#pragma unroll 1
-    for (int pl = 0; pl < 2; ++pl) {
-        if (!(pl ? g.qb : g.qa)) continue;
-        const PlayerTiles &p = pl ? g.pb : g.pa;
-        if (!first) {                          // R0 still holds the first player's head outputs until everyone has read them
+    if (g.qa && g.qb && g.h_tile != nullptr) group_forward_both(g, q_a, q_b);
+    else {
+        if (g.qa) group_forward_one(g, g.pa, q_a);
+        if (g.qa && g.qb) {                    // R0 / R1 still hold the first player's operands until everyone has read them
             tc::tc_fence_before();
             tc::bar_sync(g.bar_id, G_ROWS);
         }
-        first = false;
-        group_mma(g, p, 0);
-        hidden_epilogue(g.r0 + g.lane_addr, g.r0 + TM_R1 + g.lane_addr);
-        tc::tc_fence_before();
-        tc::bar_sync(g.bar_id, G_ROWS);
-        group_mma(g, p, 1);
-        if (pl) heads_epilogue(g.r0 + g.lane_addr, p.w + W3H_OFF, q_b); else heads_epilogue(g.r0 + g.lane_addr, p.w + W3H_OFF, q_a);
+        if (g.qb) group_forward_one(g, g.pb, q_b);
     }
 }
 
 // `grp` and `tmem` must be warp-uniform VALUES THE COMPILER CAN SEE as uniform (shfl broadcasts), so that the UMMA
 // descriptors derived from them live in uniform registers instead of being re-broadcast before every MMA.
 __device__ __forceinline__ GroupCtx make_group(uint8_t *smem, uint32_t groups_off, uint32_t ctrl_off, uint32_t tmem, int grp,
-                                               int row, bool qa, bool qb) {
+                                               int row, bool qa, bool qb, uint32_t group_stride = GROUP_BYTES, bool with_h_tile = false) {
     GroupCtx g;
-    uint8_t *gb = smem + groups_off + grp * GROUP_BYTES;
+    uint8_t *gb = smem + groups_off + grp * group_stride;
     g.pa = PlayerTiles{smem, gb};
     g.pb = PlayerTiles{smem + PLAYER_W_BYTES, gb + X_BYTES};
+    g.h_tile = with_h_tile ? gb + GROUP_BYTES : nullptr;
+    g.row = row;
     g.bar = reinterpret_cast<uint64_t *>(smem + ctrl_off) + 1 + grp;
     g.parity = 0;
     g.r0 = tmem + grp * 128;
@@ -332,13 +396,16 @@ qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol,
 constexpr int TC_FUSED_THREADS = G_ROWS * CTA_GROUPS;
 struct FusedMap {
     static constexpr uint32_t W = 0, GROUPS_OFF = 2 * PLAYER_W_BYTES;
-    static constexpr uint32_t SERVE_OFF = GROUPS_OFF + CTA_GROUPS * GROUP_BYTES;       // next serve per thread: 3 doubles
+    static constexpr uint32_t GROUP_STRIDE = GROUP_BYTES + H_BYTES;                    // X rows of both players + player B's H tile
+    static constexpr uint32_t SERVE_OFF = GROUPS_OFF + CTA_GROUPS * GROUP_STRIDE;      // next serve per thread: 3 doubles
     static constexpr uint32_t CTRL = SERVE_OFF + TC_FUSED_THREADS * 24;                // mbarriers + TMEM base
-    static constexpr uint32_t STAGE_OFF = (CTRL + 64 + 127) / 128 * 128;               // replay-row staging: 896 B per warp
-    static constexpr uint32_t TOTAL = STAGE_OFF + (TC_FUSED_THREADS / 32) * 896;
+    static constexpr uint32_t TOTAL = CTRL + 64;
+    // replay-row staging (896 B per warp) aliases the group's H tile: rows are staged after heads_B, when the tile is dead
+    // until the next step's epilogue, and that comes after the group barrier every warp reaches after its staging
 };
 static_assert(FusedMap::TOTAL <= 232448, "shared memory of the fused tensor-core kernel exceeds 227 KB");
-static_assert(2 * BLOB_BYTES <= CTA_GROUPS * GROUP_BYTES + TC_FUSED_THREADS * 24, "weight staging aliases the X rows and serve slots");
+static_assert(2 * BLOB_BYTES <= CTA_GROUPS * FusedMap::GROUP_STRIDE, "weight staging aliases the group tiles");
+static_assert(4 * 896 <= H_BYTES, "replay-row staging of a group's four warps aliases its H tile");
 
 template <typename R>
 __global__ void __launch_bounds__(TC_FUSED_THREADS, 1)
@@ -351,9 +418,9 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
     const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler too
     const int grp = warp_id >> 2, gw = warp_id & 3, row = threadIdx.x & 127, lane = threadIdx.x & 31;
     const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
-    GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, grp, row, qa, qb);
+    GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, grp, row, qa, qb, M::GROUP_STRIDE, true);
     double *serve_slot = reinterpret_cast<double *>(smem + M::SERVE_OFF) + threadIdx.x * 3;
-    float *row_stage = reinterpret_cast<float *>(smem + M::STAGE_OFF) + warp_id * 224;
+    float *row_stage = reinterpret_cast<float *>(g.h_tile) + gw * 224;
     const EnvConsts<R> c(params);
     const StatePtrs<R> s(st);
     const int64_t total_warps = (n + 31) / 32;
