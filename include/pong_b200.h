@@ -211,6 +211,24 @@ typedef struct PPAdamParam {
     int64_t numel;
 } PPAdamParam;
 
+/* One QNetRNN in torch's layout (models/qnet_rnn.py:53-105; default dims 7-64-128 / LSTM 128 / head 128): device
+ * pointers to the module's own parameter tensors.  The grad_* pointers inside the three PPNoisyLayer are ignored here. */
+typedef struct PPQNetRNNParams {
+    const float *f0_w, *f0_b;            /* features_extractor.0  [64][7], [64]                          */
+    const float *f2_w, *f2_b;            /* features_extractor.2  [128][64], [128]                       */
+    const float *w_ih, *w_hh;            /* lstm.weight_ih_l0 / weight_hh_l0  [512][128] (gates i, f, g, o) */
+    const float *b_ih, *b_hh;            /* lstm.bias_ih_l0 / bias_hh_l0  [512]                          */
+    PPNoisyLayer shared, v, a;           /* fc_shared_head.0 [128][128], fc_V [1][128], fc_A [3][128]    */
+} PPQNetRNNParams;
+
+/* Where pp_drqn_grads writes d loss / d parameter (written, not accumulated; any pointer may be NULL = skipped): plain
+ * tensors for the feature layers and the LSTM, the grad_* pointers of the PPNoisyLayer for the three noisy layers (their
+ * weight / bias / epsilon pointers are ignored here; shared.grad_weight_mu is required). */
+typedef struct PPQNetRNNGrads {
+    float *f0_w, *f0_b, *f2_w, *f2_b, *w_ih, *w_hh, *b_ih, *b_hh;
+    PPNoisyLayer shared, v, a;
+} PPQNetRNNGrads;
+
 int pp_version(void);
 const char *pp_last_error(void);
 
@@ -342,6 +360,30 @@ int64_t pp_per_sample_scratch_floats(int64_t capacity);
  *   step += 1;  m = lerp(m, g, 1 - beta1);  v = beta2 v + (1 - beta2) g^2;
  *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps) */
 int pp_adam_step(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, void *stream);
+
+/* ---- DRQN training mode (scripts/train_rnn_iterative.py)
+ *
+ * train_step_rnn() of scripts/train_rnn_iterative.py:400-531 up to the gradients, for `batch` sampled windows of `trace`
+ * consecutive transitions: rows[batch][trace] are replay-ring slots in time order (SequenceReplayBuffer.sample, :126-165).
+ *   q      = Q_online(obs window, zero initial (h, c))[last step][action of the last step]                    :470-478
+ *   a*     = argmax Q_online(next_obs window)[last step];   target = r + gamma Q_target(next_obs window)[a*] (1 - done)  :489-505
+ *   loss   = smooth_l1(q, target)  (mean over the batch)                                                      :509
+ * and d loss / d every parameter of the online net (BPTT through the LSTM over the whole window).  noisy_online /
+ * noisy_target select the train- (mu + sigma * epsilon) or eval-mode (mu) forward of the NoisyLinear layers (the
+ * reference: online train mode :729, target eval mode :337-338).  batch: a multiple of 16, <= 256; trace <= 16.
+ * td_out[batch], loss_out[1] may be NULL.  workspace: pp_drqn_workspace_floats(batch, trace) floats. */
+int pp_drqn_grads(const PPReplayRing *ring, const int64_t *rows, int32_t batch, int32_t trace,
+                  const PPQNetRNNParams *online, const PPQNetRNNParams *target, int32_t noisy_online, int32_t noisy_target,
+                  float gamma, const PPQNetRNNGrads *grads, float *loss_out, float *td_out, float *workspace, void *stream);
+int64_t pp_drqn_workspace_floats(int32_t batch, int32_t trace);
+
+/* torch.nn.utils.clip_grad_norm_(parameters, max_norm) (:516) on ONE flat gradient buffer (the .grad tensors are views of
+ * it): norm_out[0] = total L2 norm, norm_out[1] = the clip coefficient min(1, max_norm / (norm + 1e-6)) the buffer was
+ * scaled by.  scratch: 257 floats, ZERO before the first use (left ready for the next call). */
+int pp_clip_grad_norm(float *flat_grads, int64_t numel, float max_norm, float *norm_out, float *scratch, void *stream);
+
+/* pp_adam_step for up to 32 tensors of any size, spread over the whole GPU (optimizerB.step(), :517). */
+int pp_adam_step_multi(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, void *stream);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,16 @@ class PPAdamParam(C.Structure):
     _fields_ = [("param", c_vp), ("grad", c_vp), ("exp_avg", c_vp), ("exp_avg_sq", c_vp), ("step", c_vp), ("numel", c_i64)]
 
 
+class PPQNetRNNParams(C.Structure):
+    _fields_ = [(n, c_vp) for n in ("f0_w", "f0_b", "f2_w", "f2_b", "w_ih", "w_hh", "b_ih", "b_hh")] + [
+        ("shared", PPNoisyLayer), ("v", PPNoisyLayer), ("a", PPNoisyLayer)]
+
+
+class PPQNetRNNGrads(C.Structure):
+    _fields_ = [(n, c_vp) for n in ("f0_w", "f0_b", "f2_w", "f2_b", "w_ih", "w_hh", "b_ih", "b_hh")] + [
+        ("shared", PPNoisyLayer), ("v", PPNoisyLayer), ("a", PPNoisyLayer)]
+
+
 P = C.POINTER
 _PROTOTYPES = {
     "pp_version": (C.c_int, []),
@@ -101,6 +111,11 @@ _PROTOTYPES = {
     "pp_host_selfplay_eval": (C.c_int, [C.c_int, C.c_int, c_i64, c_i32, P(PPParams), c_vp, c_vp, c_vp, c_u64, c_i64,
                                         c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_i64]),
     "pp_host_release": (C.c_int, [C.c_int]),
+    "pp_drqn_grads": (C.c_int, [P(PPReplayRing), c_vp, c_i32, c_i32, P(PPQNetRNNParams), P(PPQNetRNNParams), c_i32, c_i32,
+                                c_f32, P(PPQNetRNNGrads), c_vp, c_vp, c_vp, c_vp]),
+    "pp_drqn_workspace_floats": (c_i64, [c_i32, c_i32]),
+    "pp_clip_grad_norm": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    "pp_adam_step_multi": (C.c_int, [P(PPAdamParam), c_i32, c_f64, c_f64, c_f64, c_f64, c_vp]),
 }
 
 EXPORTS = tuple(_PROTOTYPES)

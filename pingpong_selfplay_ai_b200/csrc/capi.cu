@@ -287,6 +287,55 @@ int pp_adam_step(const PPAdamParam *params, int32_t count, double lr, double bet
 }
 
 // ---------------------------------------------------------------------------------------------
+// DRQN training mode.
+namespace {
+bool rnn_params_ok(const PPQNetRNNParams *p) {
+    return p && p->f0_w && p->f0_b && p->f2_w && p->f2_b && p->w_ih && p->w_hh && p->b_ih && p->b_hh &&
+           noisy_ok(&p->shared, 128, 128) && noisy_ok(&p->v, 128, 1) && noisy_ok(&p->a, 128, 3);
+}
+}  // namespace
+
+int pp_drqn_grads(const PPReplayRing *ring, const int64_t *rows, int32_t batch, int32_t trace, const PPQNetRNNParams *online,
+                  const PPQNetRNNParams *target, int32_t noisy_online, int32_t noisy_target, float gamma,
+                  const PPQNetRNNGrads *grads, float *loss_out, float *td_out, float *workspace, void *stream) {
+    const char *fn = "pp_drqn_grads";
+    if (batch <= 0 || batch > 256 || batch % 16 != 0 || trace <= 0 || trace > 16) return fail(PP_E_SIZE, fn);
+    if (!ring || !ring->obs || !ring->act || !ring->rew || !ring->next_obs || !ring->done || ring->capacity <= 0 || !rows ||
+        !grads || !workspace)
+        return fail(PP_E_NULL, fn);
+    if (!rnn_params_ok(online) || !rnn_params_ok(target)) return fail(PP_E_PARAM, fn);
+    if (!grads->shared.grad_weight_mu) return fail(PP_E_NULL, fn);
+    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return fail(PP_E_ALIGN, fn);
+    return ok_or(pp::drqn_grads_launch(*ring, rows, batch, trace, *online, *target, noisy_online, noisy_target, gamma, *grads,
+                                       loss_out, td_out, workspace, (cudaStream_t)stream), fn);
+}
+
+int64_t pp_drqn_workspace_floats(int32_t batch, int32_t trace) {
+    return (batch > 0 && trace > 0) ? pp::drqn_workspace_floats(batch, trace) : 0;
+}
+
+int pp_clip_grad_norm(float *flat_grads, int64_t numel, float max_norm, float *norm_out, float *scratch, void *stream) {
+    if (numel < 0) return fail(PP_E_SIZE, "pp_clip_grad_norm");
+    if (!flat_grads || !norm_out || !scratch) return fail(PP_E_NULL, "pp_clip_grad_norm");
+    if (!(max_norm > 0.f)) return fail(PP_E_PARAM, "pp_clip_grad_norm");
+    if (numel == 0) return 0;
+    return ok_or(pp::clip_grad_norm_launch(flat_grads, numel, max_norm, norm_out, scratch, (cudaStream_t)stream), "pp_clip_grad_norm");
+}
+
+int pp_adam_step_multi(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, void *stream) {
+    if (count < 0 || count > 32) return fail(PP_E_SIZE, "pp_adam_step_multi");
+    if (count > 0 && !params) return fail(PP_E_NULL, "pp_adam_step_multi");
+    for (int i = 0; i < count; ++i) {
+        const PPAdamParam &a = params[i];
+        if (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq || !a.step) return fail(PP_E_NULL, "pp_adam_step_multi");
+        if (a.numel < 0) return fail(PP_E_SIZE, "pp_adam_step_multi");
+    }
+    if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0)) return fail(PP_E_PARAM, "pp_adam_step_multi");
+    if (count == 0) return 0;
+    return ok_or(pp::adam_multi_launch(params, count, lr, beta1, beta2, eps, (cudaStream_t)stream), "pp_adam_step_multi");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host-buffer evaluation.  One context per device ordinal (stream + device staging + pinned staging, grown on demand,
 // released by pp_host_release): calls for different devices run concurrently from different host threads, calls for
 // the same device are serialised by the context's mutex.  Nothing is bound to "the current device" of the process.

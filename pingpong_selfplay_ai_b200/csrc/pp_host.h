@@ -58,4 +58,11 @@ int noisy_reset_launch(const PPNoisyLayer *layers, int32_t count, uint64_t seed,
 int pack_qnet_launch(const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &v,
                      const PPNoisyLayer &a, int noisy, float *blob, cudaStream_t stream);
 
+int drqn_grads_launch(const PPReplayRing &ring, const int64_t *rows, int32_t batch, int32_t trace, const PPQNetRNNParams &on,
+                      const PPQNetRNNParams &tg, int noisy_on, int noisy_tg, float gamma, const PPQNetRNNGrads &gr,
+                      float *loss_out, float *td_out, float *ws, cudaStream_t stream);
+int64_t drqn_workspace_floats(int32_t batch, int32_t trace);
+int clip_grad_norm_launch(float *flat, int64_t numel, float max_norm, float *norm_out, float *scratch, cudaStream_t stream);
+int adam_multi_launch(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, cudaStream_t stream);
+
 }  // namespace pp

@@ -294,32 +294,35 @@ __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles
     heads_epilogue(g.r0 + TM_R1 + g.lane_addr, p.w + W3H_OFF, q);
 }
 
-// BOTH players (the self-play hot path).  A group owns two 64-column TMEM regions R0, R1 and one shared-memory A tile:
-//   both first layers at once   L1_A -> R0, L1_B -> R1                                        (one round trip)
-//   epilogues                   H_A written IN PLACE over R0;  H_B to the shared-memory tile, which frees R1
-//   L2_A (A = R0 in TMEM) -> R1
-//   as soon as L2_A has completed (R0 is dead):  L2_B (A = shared-memory tile) -> R0, issued BEFORE heads_A, so that its
-//   flight is covered by the 260 instructions of heads_A (reads R1)
-//   heads_B (reads R0)
-// Two exposed MMA round trips and two group barriers per lock-step step (the serial A-then-B chain had four and four).
+// BOTH players (the self-play hot path), two 64-column TMEM regions R0, R1 per group:
+//   L1_A -> R0;  H_A IN PLACE over R0;  L2_A (A = R0) -> R1
+//   as soon as L2_A has completed R0 is dead:  L1_B -> R0 is issued BEFORE heads_A (reads R1), whose ~260 instructions
+//   cover its flight;  H_B in place over R0;  L2_B (A = R0) -> R1;  heads_B
+// Three exposed MMA round trips and three group barriers per lock-step step (the serial chain with separate operand
+// regions had four and four).  [A variant that also freed R1 early by sending H_B through a SHARED-MEMORY A tile, so
+// that L2_B could follow L2_A without a drain, was 7 % SLOWER: 12 SS-mode MMAs read 48 KB of A operand per group-step
+// from shared memory and the 32 KB of epilogue stores compete with the head table's LDS traffic.]
 __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
-    group_issue(g, [&] { issue_l1(g.r0, g.pa); issue_l1(g.r0 + TM_R1, g.pb); });
+    group_issue(g, [&] { issue_l1(g.r0, g.pa); });
     group_wait(g);
-    hidden_epilogue_smem(g.r0 + TM_R1 + g.lane_addr, g.h_tile, g.row);
     hidden_epilogue_inplace(g.r0 + g.lane_addr);
-    tc::fence_proxy_async();
     tc::tc_fence_before();
     tc::bar_sync(g.bar_id, G_ROWS);
     group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, g.pa); });
     group_wait(g);
-    group_issue(g, [&] { issue_l2<true>(g.r0, 0u, g.h_tile, g.pb); });
+    group_issue(g, [&] { issue_l1(g.r0, g.pb); });
     heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pa.w + W3H_OFF, q_a);
     group_wait(g);
-    heads_epilogue(g.r0 + g.lane_addr, g.pb.w + W3H_OFF, q_b);
+    hidden_epilogue_inplace(g.r0 + g.lane_addr);
+    tc::tc_fence_before();
+    tc::bar_sync(g.bar_id, G_ROWS);                 // also: every thread has read its heads_A row of R1
+    group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, g.pb); });
+    group_wait(g);
+    heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pb.w + W3H_OFF, q_b);
 }
 
 __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
-    if (g.qa && g.qb && g.h_tile != nullptr) group_forward_both(g, q_a, q_b);
+    if (g.qa && g.qb) group_forward_both(g, q_a, q_b);
     else {
         if (g.qa) group_forward_one(g, g.pa, q_a);
         if (g.qa && g.qb) {                    // R0 / R1 still hold the first player's operands until everyone has read them
@@ -396,16 +399,14 @@ qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol,
 constexpr int TC_FUSED_THREADS = G_ROWS * CTA_GROUPS;
 struct FusedMap {
     static constexpr uint32_t W = 0, GROUPS_OFF = 2 * PLAYER_W_BYTES;
-    static constexpr uint32_t GROUP_STRIDE = GROUP_BYTES + H_BYTES;                    // X rows of both players + player B's H tile
+    static constexpr uint32_t GROUP_STRIDE = GROUP_BYTES;                              // X rows of both players
     static constexpr uint32_t SERVE_OFF = GROUPS_OFF + CTA_GROUPS * GROUP_STRIDE;      // next serve per thread: 3 doubles
     static constexpr uint32_t CTRL = SERVE_OFF + TC_FUSED_THREADS * 24;                // mbarriers + TMEM base
-    static constexpr uint32_t TOTAL = CTRL + 64;
-    // replay-row staging (896 B per warp) aliases the group's H tile: rows are staged after heads_B, when the tile is dead
-    // until the next step's epilogue, and that comes after the group barrier every warp reaches after its staging
+    static constexpr uint32_t STAGE_OFF = (CTRL + 64 + 127) / 128 * 128;               // replay-row staging: 896 B per warp
+    static constexpr uint32_t TOTAL = STAGE_OFF + (TC_FUSED_THREADS / 32) * 896;
 };
 static_assert(FusedMap::TOTAL <= 232448, "shared memory of the fused tensor-core kernel exceeds 227 KB");
-static_assert(2 * BLOB_BYTES <= CTA_GROUPS * FusedMap::GROUP_STRIDE, "weight staging aliases the group tiles");
-static_assert(4 * 896 <= H_BYTES, "replay-row staging of a group's four warps aliases its H tile");
+static_assert(2 * BLOB_BYTES <= CTA_GROUPS * GROUP_BYTES + TC_FUSED_THREADS * 24, "weight staging aliases the X rows and serve slots");
 
 template <typename R>
 __global__ void __launch_bounds__(TC_FUSED_THREADS, 1)
@@ -418,9 +419,9 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
     const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler too
     const int grp = warp_id >> 2, gw = warp_id & 3, row = threadIdx.x & 127, lane = threadIdx.x & 31;
     const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
-    GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, grp, row, qa, qb, M::GROUP_STRIDE, true);
+    GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, grp, row, qa, qb);
     double *serve_slot = reinterpret_cast<double *>(smem + M::SERVE_OFF) + threadIdx.x * 3;
-    float *row_stage = reinterpret_cast<float *>(g.h_tile) + gw * 224;
+    float *row_stage = reinterpret_cast<float *>(smem + M::STAGE_OFF) + warp_id * 224;
     const EnvConsts<R> c(params);
     const StatePtrs<R> s(st);
     const int64_t total_warps = (n + 31) / 32;

@@ -8,10 +8,12 @@ scripts/train_rnn_iterative.py around the fused recurrent rollout kernel.
                                                            target from the next-obs sequence, Huber loss, grad-clip 1.0)
     rollout + train loop                       :728-800    train_rnn_generation
 
-The rollout (env + both players + replay rows, QNetRNN on the tensor cores or CUDA cores) runs in libpong_b200.so.  The
-update itself is PyTorch on the device: the 175 k-parameter net through `nn.LSTM` (cuDNN) forward and backward over
-[batch, trace_length, 7] windows — library code around the hot path, like cuBLAS — captured in a CUDA graph; gradients
-are averaged over env slabs with one NCCL all-reduce.
+The rollout (env + both players + replay rows, QNetRNN on the tensor cores or CUDA cores) runs in libpong_b200.so, and so
+does the update: pp_drqn_grads (csrc/drqn_kernels.cu) is the forward of the three streams, the last-step Double-DQN
+Huber loss and the whole backward pass — heads, BPTT through the LSTM on thread-block clusters, feature layers — in
+~15 hand-written launches; pp_clip_grad_norm and pp_adam_step_multi finish train_step_rnn.  All of it is captured in a
+CUDA graph; gradients are averaged over env slabs with one NCCL all-reduce of the flat gradient buffer.  The PyTorch
+formulation (`loss_on`, autograd through nn.LSTM) is kept as `fused=False`: it is what the kernels are tested against.
 
 Sequence replay on a lock-step ring.  The kernel writes the row of env i at lock-step step t to slot
 (t % T) * n + i (T = capacity / n), so each env's transitions are in time order and an episode is a run of rows that
@@ -35,9 +37,12 @@ import copy
 import torch
 import torch.nn.functional as F
 
+import ctypes as C
+
+from . import _lib
 from . import dist as ppd
 from .policy import Policy, QNetRNN, pack_qnetrnn, pack_qnetrnn_tc
-from .selfplay import ReplayRing, SelfPlayEngine
+from .selfplay import ReplayRing, SelfPlayEngine, _ptr, _stream_ptr
 from .train import DQNTrainer
 
 
@@ -119,7 +124,9 @@ class DRQNTrainer(DQNTrainer):
 
     def __init__(self, model_b: QNetRNN, gamma: float = 0.99, lr: float = 1e-4, batch_size: int = 64,
                  target_update_interval: int = 2000, grad_clip_norm: float = 1.0, min_episodes_factor: int = 1,
-                 device="cuda", use_graph: bool = True):
+                 device="cuda", use_graph: bool = True, fused: bool | None = None):
+        """fused (default: on CUDA): forward, loss and backward in the hand-written kernels of csrc/drqn_kernels.cu,
+        gradient clipping and Adam in two more; fused=False is the PyTorch / autograd formulation they are tested against."""
         self.device = torch.device(device)
         self.model = model_b.to(self.device)
         ppd.broadcast_module_(self.model)                # several ranks: every replica starts from rank 0's weights
@@ -132,14 +139,83 @@ class DRQNTrainer(DQNTrainer):
         self.head_params = self.params                     # what DQNTrainer's helpers call the trainable set
         self.use_graph = use_graph
         on_cuda = self.device.type == "cuda"
-        # fused: ONE multi-tensor kernel for the 20 parameter tensors (the capturable foreach form is ~100 tiny kernels)
-        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=use_graph and on_cuda, fused=True if on_cuda else None)  # :335
+        want_fused = on_cuda if fused is None else bool(fused)
+        # torch's own fused multi-tensor Adam serves the fused=False formulation (the capturable foreach form is ~100 kernels)
+        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=(use_graph or want_fused) and on_cuda,
+                                    fused=True if on_cuda else None)                     # :335
         self._graph, self._eager_runs = None, 0
         self.gamma, self.batch_size, self.target_update_interval = gamma, batch_size, target_update_interval
         self.grad_clip_norm, self.min_episodes = float(grad_clip_norm), int(batch_size * min_episodes_factor)
         self.frame_idx = self.train_steps = 0
-        self.fused = False                               # the update is PyTorch (cuDNN LSTM backward)
         self._flat_grad = ppd.flatten_grads_(self.params)     # .grad tensors are views of one buffer: one collective
+        self.fused = want_fused
+        if self.fused:
+            self._init_fused_rnn()
+
+    # ---- the hand-written update path (csrc/drqn_kernels.cu)
+    @staticmethod
+    def _noisy(mod, grads: bool):
+        g = (lambda p: _ptr(p.grad)) if grads else (lambda p: None)
+        return _lib.PPNoisyLayer(mod.in_features, mod.out_features, _ptr(mod.weight_mu), _ptr(mod.weight_sigma),
+                                 _ptr(mod.weight_epsilon), _ptr(mod.bias_mu), _ptr(mod.bias_sigma), _ptr(mod.bias_epsilon),
+                                 g(mod.weight_mu), g(mod.weight_sigma), g(mod.bias_mu), g(mod.bias_sigma))
+
+    @classmethod
+    def _net_struct(cls, m: QNetRNN, grads: bool = False):
+        if (m.feature_dim, m.lstm_hidden_dim, m.lstm_layers, m.head_hidden_dim, m.input_dim) != (128, 128, 1, 128, 7):
+            raise ValueError("the device DRQN update is built for the reference default 7-64-128 / 1-layer LSTM 128 / head 128")
+        f, l = m.features_extractor, m.lstm
+        plain = [f[0].weight, f[0].bias, f[2].weight, f[2].bias, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0]
+        ptrs = [_ptr(t.grad) if grads else _ptr(t) for t in plain]
+        layers = [cls._noisy(mod, grads) for mod in (m.fc_shared_head[0], m.fc_V, m.fc_A)]
+        return (_lib.PPQNetRNNGrads if grads else _lib.PPQNetRNNParams)(*ptrs, *layers)
+
+    def _init_fused_rnn(self):
+        self._lib = _lib.load()
+        dev = self.device
+        self._on, self._tg = self._net_struct(self.model), self._net_struct(self.target)
+        self._gr = self._net_struct(self.model, grads=True)
+        self._ws = {}                                            # (batch, trace) -> workspace
+        self._loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._td_buf = torch.zeros(self.batch_size, dtype=torch.float32, device=dev)
+        self._norm_out = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._norm_scratch = torch.zeros(257, dtype=torch.float32, device=dev)
+        for p in self.params:                                    # the optimiser's own state, as a capturable Adam creates it
+            st = self.opt.state[p]
+            if not st:
+                st["step"] = torch.zeros((), dtype=torch.float32, device=dev)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        self._adam = (_lib.PPAdamParam * len(self.params))(*[
+            _lib.PPAdamParam(_ptr(p), _ptr(p.grad), _ptr(self.opt.state[p]["exp_avg"]), _ptr(self.opt.state[p]["exp_avg_sq"]),
+                             _ptr(self.opt.state[p]["step"]), p.numel()) for p in self.params])
+
+    def grads_on_rows(self, ring: ReplayRing, rows: torch.Tensor):
+        """train_step_rnn up to loss.backward() for given windows (ring slots int64 [batch, trace], time ascending): the
+        gradients land in the .grad tensors.  Returns the loss (0-d device tensor)."""
+        b, l = int(rows.shape[0]), int(rows.shape[1])
+        rows = rows.to(torch.int64).contiguous()
+        if (b, l) not in self._ws:
+            self._ws[(b, l)] = torch.zeros(int(self._lib.pp_drqn_workspace_floats(b, l)), dtype=torch.float32, device=self.device)
+        if self._td_buf.numel() < b:
+            self._td_buf = torch.zeros(b, dtype=torch.float32, device=self.device)
+        rs = ring.struct()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pp_drqn_grads(C.byref(rs), _ptr(rows), b, l, C.byref(self._on), C.byref(self._tg),
+                                               int(self.model.training), int(self.target.training), float(self.gamma),
+                                               C.byref(self._gr), _ptr(self._loss_buf), _ptr(self._td_buf), _ptr(self._ws[(b, l)]),
+                                               _stream_ptr(self.device)), "pp_drqn_grads")
+        return self._loss_buf[0]
+
+    def clip_and_step(self):
+        """clip_grad_norm_ (:516) + optimizerB.step() (:517) on the flat gradient buffer: four launches."""
+        g = self.opt.param_groups[0]
+        st = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pp_clip_grad_norm(_ptr(self._flat_grad), self._flat_grad.numel(), self.grad_clip_norm,
+                                                   _ptr(self._norm_out), _ptr(self._norm_scratch), st), "pp_clip_grad_norm")
+            _lib.check(self._lib.pp_adam_step_multi(self._adam, len(self.params), float(g["lr"]), float(g["betas"][0]),
+                                                    float(g["betas"][1]), float(g["eps"]), st), "pp_adam_step_multi")
 
     def loss_on(self, obs, act, rew, next_obs, done):
         """The loss of train_step_rnn for given windows (:468-507)."""
@@ -156,12 +232,16 @@ class DRQNTrainer(DQNTrainer):
         return F.smooth_l1_loss(q, targets)                                              # :509
 
     def _pre(self, sampler: SequenceSampler, beta=None, generator=None):
+        if self.fused:
+            return self.grads_on_rows(sampler.ring, sampler.sample_rows(self.batch_size, generator))
         loss = self.loss_on(*sampler.sample(self.batch_size, generator))
         self.opt.zero_grad(set_to_none=False)
         loss.backward()
         return loss.detach()
 
     def _post(self, sampler: SequenceSampler):
+        if self.fused:
+            return self.clip_and_step()
         torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip_norm)        # :516
         self.opt.step()
 

@@ -1,0 +1,128 @@
+"""The hand-written DRQN update (csrc/drqn_kernels.cu: pp_drqn_grads, pp_clip_grad_norm, pp_adam_step_multi) against
+torch autograd on the CPU (`-m gpu`): train_step_rnn of scripts/train_rnn_iterative.py:400-531 restated in
+oracle/train_port.py, run on the reference's own module (torch port, state_dict-compatible) in fp32."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pingpong_selfplay_ai_b200 as pp
+from pingpong_selfplay_ai_b200.train_rnn import DRQNTrainer, SequenceSampler
+from oracle.policy_torch import QNetRNNPort
+from oracle.train_port import drqn_loss
+import pp_testutil as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(which):
+    if which == "ckpt":                                  # the reference's trained checkpoint (large head weights, saturated gates)
+        g = dict(np.load(os.path.join(gu.GOLDEN, "qnetrnn_ckpt_golden.npz")))
+        net = pp.QNetRNN()
+        net.load_state_dict({k: torch.as_tensor(v) for k, v in gu.golden_sd(g, "rnn_agent_4_B").items()})
+    else:
+        torch.manual_seed(7)
+        net = pp.QNetRNN()
+    net.reset_noise()
+    return net
+
+
+def _filled_ring(n, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    ring = pp.ReplayRing(n * T, lockstep_envs=n)
+    ring.obs.copy_(torch.rand(n * T, 7, generator=g) * 2 - 1)
+    ring.next_obs.copy_(torch.rand(n * T, 7, generator=g) * 2 - 1)
+    ring.act.copy_(torch.randint(0, 3, (n * T,), generator=g).to(torch.uint8))
+    ring.rew.copy_(torch.randint(-1, 2, (n * T,), generator=g).float())
+    ring.done.copy_((torch.rand(n * T, generator=g) < 0.3).to(torch.uint8))
+    return ring
+
+
+def _reference(net, target, ring, rows, gamma, noisy):
+    """Loss and gradients of train_step_rnn through torch autograd on the CPU."""
+    ref, tgt = QNetRNNPort(), QNetRNNPort()
+    ref.load_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()})
+    tgt.load_state_dict({k: v.detach().cpu() for k, v in target.state_dict().items()})
+    ref.train(noisy); tgt.eval()
+    r = rows.cpu()
+    take = lambda t: t.detach().cpu()[r]
+    loss = drqn_loss(ref, tgt, take(ring.obs), take(ring.act).long(), take(ring.rew), take(ring.next_obs), take(ring.done) != 0, gamma)
+    ref.zero_grad()
+    loss.backward()
+    return float(loss.detach()), {k: p.grad.clone() for k, p in ref.named_parameters()}, ref
+
+
+@pytest.mark.parametrize("which,batch,trace", [("seed", 64, 8), ("ckpt", 64, 8), ("seed", 16, 5), ("ckpt", 128, 12)])
+def test_drqn_grads_equal_torch_autograd(which, batch, trace):
+    net = _net(which)
+    n, T = 64, 32
+    ring = _filled_ring(n, T, seed=batch + trace)
+    g = torch.Generator().manual_seed(3)
+    t_end = torch.randint(trace - 1, T, (batch,), generator=g)
+    env = torch.randint(0, n, (batch,), generator=g)
+    rows = ((t_end.unsqueeze(1) + torch.arange(-(trace - 1), 1).unsqueeze(0)) * n + env.unsqueeze(1)).cuda()
+    tr = DRQNTrainer(copy.deepcopy(net), gamma=0.97, batch_size=batch, use_graph=False)
+    with torch.no_grad():                                # a target that differs from the online net
+        for p in tr.target.parameters():
+            p.mul_(0.9)
+    assert tr.fused
+    loss = float(tr.grads_on_rows(ring, rows))
+    want_loss, want, _ = _reference(tr.model, tr.target, ring, rows, 0.97, noisy=True)
+    assert loss == pytest.approx(want_loss, rel=2e-5, abs=1e-7)
+    worst = 0.0
+    for name, p in tr.model.named_parameters():
+        got, w = p.grad.detach().cpu(), want[name]
+        scale = max(float(w.abs().max()), 1e-8)
+        err = float((got - w).abs().max()) / scale
+        worst = max(worst, err)
+        assert err < 1e-4, (name, err, scale)
+    print(f"{which} batch {batch} trace {trace}: loss {loss:.6f}, worst relative gradient error {worst:.2e}")
+
+
+def test_drqn_clip_and_adam_equal_torch():
+    """clip_grad_norm_(1.0) + Adam on the flat gradient buffer == torch's, over several steps (large and small norms)."""
+    net = _net("seed")
+    tr = DRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=64, use_graph=False)
+    ref = copy.deepcopy(tr.model).cpu()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    for step in range(4):
+        scale = [30.0, 1e-3, 3.0, 0.2][step]
+        for p, q in zip(tr.model.parameters(), ref.parameters()):
+            gr = torch.randn(p.shape, generator=g) * scale / 400
+            p.grad.copy_(gr)
+            q.grad = gr.clone()
+        norm = torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm=1.0)
+        opt.step()
+        tr.clip_and_step()
+        assert float(tr._norm_out[0]) == pytest.approx(float(norm), rel=1e-5)
+        assert float(tr._norm_out[1]) == pytest.approx(min(1.0, 1.0 / (float(norm) + 1e-6)), rel=1e-5)
+        for (name, p), q in zip(tr.model.named_parameters(), ref.parameters()):
+            assert torch.allclose(p.detach().cpu(), q.detach(), rtol=2e-5, atol=2e-7), (step, name)
+    assert all(float(tr.opt.state[p]["step"]) == 4.0 for p in tr.params)
+
+
+def test_drqn_fused_update_tracks_the_autograd_update_in_a_generation():
+    """Same windows, same noise: the fused trainer and the fused=False (autograd / cuDNN) trainer stay together over a few
+    updates, the graph-captured path included."""
+    torch.manual_seed(5)
+    net = pp.QNetRNN()
+    n, T = 256, 32
+    ring = _filled_ring(n, T, seed=9)
+    ring.steps_written = T
+    ring.head.fill_(n * T)
+    sampler = SequenceSampler(ring, trace_length=8)
+    assert sampler.refresh() > 64
+    a = DRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=64, use_graph=True)
+    b = DRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=64, use_graph=False, fused=False)
+    b.model.load_state_dict(a.model.state_dict())        # the same epsilon buffers
+    torch.backends.cudnn.allow_tf32 = False
+    for step in range(6):                                # 3 eager updates, then the captured graph
+        torch.manual_seed(100 + step); la = a.update(sampler)
+        torch.manual_seed(100 + step); lb = b.update(sampler)
+        assert float(la) == pytest.approx(float(lb), rel=1e-3, abs=1e-6), step
+    for (name, p), q in zip(a.model.named_parameters(), b.model.parameters()):
+        assert torch.allclose(p, q, rtol=1e-2, atol=2e-4), name
+    assert a.train_steps == b.train_steps == 6 and a._graph is not None
