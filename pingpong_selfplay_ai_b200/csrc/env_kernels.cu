@@ -226,7 +226,7 @@ rollout_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_
         s.ep_idx[i] = ep_idx;
         s.ep_len[i] = ep_len;
     }
-    if (out.counters) tally.flush(out.counters);
+    tally.flush(out.counters, out.ep_log ? nullptr : out.ep_log_count);
 }
 
 // collide_sphere_with_moving_plane for n independent impacts (envs/physics.py:3-23): the arithmetic of paddle_event,

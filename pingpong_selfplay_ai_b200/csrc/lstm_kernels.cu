@@ -305,7 +305,7 @@ selfplay_rnn_kernel(const PPParams params, const PPEnvState st, int64_t n, int64
         s.ep_idx[i] = L.ep_idx;
         s.ep_len[i] = L.ep_len;
     }
-    if (out.counters && env_thread) L.tally.flush(out.counters);
+    if (env_thread) L.tally.flush(out.counters, out.ep_log ? nullptr : out.ep_log_count);
 }
 
 constexpr size_t L_SMEM = (size_t)(256 * L_TILE + 2 * L_CHUNK + L_F1 * L_TILE + 7 * L_TILE) * sizeof(float) + L_TILE;

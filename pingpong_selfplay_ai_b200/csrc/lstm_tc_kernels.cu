@@ -577,7 +577,7 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
             }
             if (half == 0) total.add(L.tally);
         }
-        if (out.counters) total.flush(out.counters);
+        total.flush(out.counters, out.ep_log ? nullptr : out.ep_log_count);
     }
     tc::tc_fence_before();
     __syncthreads();

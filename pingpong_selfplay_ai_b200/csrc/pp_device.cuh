@@ -94,7 +94,7 @@ __device__ __forceinline__ void impact(const EnvConsts<R> &c, R vn, R vt, R u, R
         const R vrel = X::sub(X::sub(vt, u), X::mul(c.radius, om));
         jt = X::mul(-cap, X::sign1(vrel));
     }
-    vt_post = X::add(vt, X::div(jt, c.mass));
+    vt_post = X::add(vt, c.mass == (R)1 ? jt : X::div(jt, c.mass));              // jt / 1.0 is jt, bit for bit (uniform branch)
     om_post = X::sub(om, X::div(X::mul(c.radius, jt), c.inertia));
 }
 
@@ -131,13 +131,14 @@ template <typename R> __device__ __forceinline__ int env_step(const EnvConsts<R>
     e.y = X::add(e.y, e.vy);
     if (e.x < (R)0) { e.x = -e.x; e.vx = -e.vx; }
     else if (e.x > (R)1) { e.x = X::sub((R)2, e.x); e.vx = -e.vx; }
+    // ONE copy of the paddle event for both lines (:151-186 top, :189-223 bottom): a warp in which some env is beyond the
+    // top line and another beyond the bottom line walks the ~150-instruction impact code once, not twice.
     int flags = 0;
-    if (e.y < (R)0) {
-        if (paddle_event<R>(c, e, e.top, aA, false)) flags = F_HIT;
+    const bool top = e.y < (R)0, bottom = !top && e.y > (R)1;
+    if (top || bottom) {
+        if (paddle_event<R>(c, e, bottom ? e.bot : e.top, bottom ? aB : aA, bottom)) flags = F_HIT;
+        else if (bottom) { e.sa += 1; flags = F_POINT_A | (e.sa >= c.max_score ? F_DONE : 0); }
         else { e.sb += 1; flags = F_POINT_B | (e.sb >= c.max_score ? F_DONE : 0); }
-    } else if (e.y > (R)1) {
-        if (paddle_event<R>(c, e, e.bot, aB, true)) flags = F_HIT;
-        else { e.sa += 1; flags = F_POINT_A | (e.sa >= c.max_score ? F_DONE : 0); }
     }
     return flags;
 }
@@ -238,13 +239,18 @@ struct Tally {
         steps += o.steps; episodes += o.episodes; wins_a += o.wins_a; wins_b += o.wins_b;
         pts_a += o.pts_a; pts_b += o.pts_b; hits += o.hits; len_sum += o.len_sum;
     }
-    __device__ __forceinline__ void flush(unsigned long long *counters) {
+    // `unlogged_episodes`: the episode cursor of a launch WITHOUT a log buffer (log_episode then skips its per-step atomic)
+    __device__ __forceinline__ void flush(unsigned long long *counters, unsigned long long *unlogged_episodes = nullptr) {
         unsigned v[7] = {steps, episodes, wins_a, wins_b, pts_a, pts_b, hits};
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             unsigned s = __reduce_add_sync(0xffffffffu, v[k]);
-            if ((threadIdx.x & 31) == 0 && s) atomicAdd(counters + k, (unsigned long long)s);
+            if ((threadIdx.x & 31) == 0 && s) {
+                if (counters) atomicAdd(counters + k, (unsigned long long)s);
+                if (k == 1 && unlogged_episodes) atomicAdd(unlogged_episodes, (unsigned long long)s);
+            }
         }
+        if (!counters) return;
         unsigned long long l = len_sum;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
@@ -255,7 +261,9 @@ struct Tally {
 // Called by ALL lanes of a warp (done = this lane finished an episode this step, m = ballot of done).
 __device__ __forceinline__ void log_episode(bool done, unsigned m, const PPRolloutOut &out, int env_id, int ep_idx, int sa,
                                             int sb, int ep_len) {
-    if (m == 0 || out.ep_log_count == nullptr) return;
+    // without a log buffer there is nothing to rank: the cursor is advanced once per launch by Tally::flush instead of by a
+    // returning global atomic (a ~500-cycle round trip) on every warp-step in which some episode ends
+    if (m == 0 || out.ep_log_count == nullptr || out.ep_log == nullptr) return;
     const int lane = threadIdx.x & 31;
     unsigned long long base = 0;
     if (lane == (__ffs(m) - 1)) base = atomicAdd(out.ep_log_count, (unsigned long long)__popc(m));

@@ -108,7 +108,7 @@ selfplay_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k
         s.ep_idx[i] = L.ep_idx;
         s.ep_len[i] = L.ep_len;
     }
-    if (out.counters) L.tally.flush(out.counters);
+    L.tally.flush(out.counters, out.ep_log ? nullptr : out.ep_log_count);
 }
 
 int qnet_act_launch(int64_t n, const float *obs, const PPPolicy &pol, uint64_t seed, int64_t step_index,

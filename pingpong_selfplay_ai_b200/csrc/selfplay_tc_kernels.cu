@@ -26,6 +26,9 @@
 // Env state, observations and bookkeeping never leave registers (same step_and_book as the CUDA-core kernel).
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "pp_host.h"
 #include "pp_rollout.cuh"
 #include "tc_tiles.cuh"
@@ -162,7 +165,9 @@ __device__ __forceinline__ void hidden_epilogue_smem(uint32_t acc, uint8_t *tile
 // 45-cycle instruction floor, one more accumulator round trip and group barrier per player) and keeps the heads exact.
 __device__ __forceinline__ void heads_epilogue(uint32_t src, const uint8_t *table, float (&q)[3]) {
     const float4 *ht = reinterpret_cast<const float4 *>(table);
-    float2 v = make_float2(0.f, 0.f), a0 = v, a1 = v, a2 = v;                   // (even-k, odd-k) partial sums per output
+    // (even-k, odd-k) partial sums per output, in TWO independent sets (pairs j even / j odd): eight FFMA2 chains in
+    // flight instead of four — the epilogue is bound by the latency of its dependent FMAs, not by their number
+    float2 v[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, a0[2] = {v[0], v[0]}, a1[2] = {v[0], v[0]}, a2[2] = {v[0], v[0]};
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t r0[16], r1[16];
@@ -174,15 +179,17 @@ __device__ __forceinline__ void heads_epilogue(uint32_t src, const uint8_t *tabl
             const uint32_t *r = j < 8 ? r0 + 2 * j : r1 + 2 * (j - 8);
             const float2 h = make_float2(fmaxf(__uint_as_float(r[0]), 0.0f), fmaxf(__uint_as_float(r[1]), 0.0f));
             const float4 w01 = ht[(half * 16 + j) * 2], w23 = ht[(half * 16 + j) * 2 + 1];
-            v = __ffma2_rn(make_float2(w01.x, w01.y), h, v);
-            a0 = __ffma2_rn(make_float2(w01.z, w01.w), h, a0);
-            a1 = __ffma2_rn(make_float2(w23.x, w23.y), h, a1);
-            a2 = __ffma2_rn(make_float2(w23.z, w23.w), h, a2);
+            const int s = j & 1;
+            v[s] = __ffma2_rn(make_float2(w01.x, w01.y), h, v[s]);
+            a0[s] = __ffma2_rn(make_float2(w01.z, w01.w), h, a0[s]);
+            a1[s] = __ffma2_rn(make_float2(w23.x, w23.y), h, a1[s]);
+            a2[s] = __ffma2_rn(make_float2(w23.z, w23.w), h, a2[s]);
         }
     }
     const float4 bias = ht[64];
-    const float V = __fadd_rn(__fadd_rn(v.x, v.y), bias.x), A0 = __fadd_rn(__fadd_rn(a0.x, a0.y), bias.y);
-    const float A1 = __fadd_rn(__fadd_rn(a1.x, a1.y), bias.z), A2 = __fadd_rn(__fadd_rn(a2.x, a2.y), bias.w);
+    const float2 vs = __fadd2_rn(v[0], v[1]), a0s = __fadd2_rn(a0[0], a0[1]), a1s = __fadd2_rn(a1[0], a1[1]), a2s = __fadd2_rn(a2[0], a2[1]);
+    const float V = __fadd_rn(__fadd_rn(vs.x, vs.y), bias.x), A0 = __fadd_rn(__fadd_rn(a0s.x, a0s.y), bias.y);
+    const float A1 = __fadd_rn(__fadd_rn(a1s.x, a1s.y), bias.z), A2 = __fadd_rn(__fadd_rn(a2s.x, a2s.y), bias.w);
     const float mean = __fdiv_rn(__fadd_rn(__fadd_rn(A0, A1), A2), 3.0f);               // V + (A - mean(A))  models/qnet.py:75
     q[0] = __fadd_rn(V, __fsub_rn(A0, mean));
     q[1] = __fadd_rn(V, __fsub_rn(A1, mean));
@@ -254,8 +261,24 @@ template <int GROUPS> __device__ __forceinline__ void tc_epilogue(uint32_t tmem)
     if (threadIdx.x < 32) tc::tmem_dealloc<GROUPS * 128>(tmem);
 }
 
+// Phase timers of a -DPP_TC_TIMING build (diagnostics only): cycles per phase of a lock-step step, accumulated by every
+// thread and printed for lane 0 of the first two warps of group 0 of CTA 0.
+#ifdef PP_TC_TIMING
+struct PhaseTimer {
+    long long t[10] = {}, last = 0;
+    __device__ __forceinline__ void start() { last = clock64(); }
+    __device__ __forceinline__ void tick(int i) { const long long now = clock64(); t[i] += now - last; last = now; }
+};
+#define PP_TICK(i) g.timer.tick(i)
+#else
+#define PP_TICK(i) do {} while (0)
+#endif
+
 // One policy evaluation round for a group: X rows are already written and published by a group barrier.
 struct GroupCtx {
+#ifdef PP_TC_TIMING
+    PhaseTimer timer;
+#endif
     PlayerTiles pa, pb;
     uint8_t *h_tile;                             // shared-memory A tile of player B's hidden activations (fused kernel only)
     uint64_t *bar;
@@ -304,21 +327,35 @@ __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles
 // from shared memory and the 32 KB of epilogue stores compete with the head table's LDS traffic.]
 __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
     group_issue(g, [&] { issue_l1(g.r0, g.pa); });
+    PP_TICK(1);
     group_wait(g);
+    PP_TICK(2);
     hidden_epilogue_inplace(g.r0 + g.lane_addr);
     tc::tc_fence_before();
+    PP_TICK(3);
     tc::bar_sync(g.bar_id, G_ROWS);
+    PP_TICK(4);
     group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, g.pa); });
+    PP_TICK(5);
     group_wait(g);
+    PP_TICK(6);
     group_issue(g, [&] { issue_l1(g.r0, g.pb); });
+    PP_TICK(1);
     heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pa.w + W3H_OFF, q_a);
+    PP_TICK(7);
     group_wait(g);
+    PP_TICK(2);
     hidden_epilogue_inplace(g.r0 + g.lane_addr);
     tc::tc_fence_before();
+    PP_TICK(3);
     tc::bar_sync(g.bar_id, G_ROWS);                 // also: every thread has read its heads_A row of R1
+    PP_TICK(4);
     group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, g.pb); });
+    PP_TICK(5);
     group_wait(g);
+    PP_TICK(6);
     heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pb.w + W3H_OFF, q_b);
+    PP_TICK(7);
 }
 
 __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
@@ -397,6 +434,7 @@ qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol,
 // Work is split in units of warps (32 envs): `n_chunks` chunks of at most 16 warps, balanced to within one warp, so
 // every SM issues the same number of warp-steps whatever n is.  A CTA walks chunks blockIdx.x, + gridDim.x, ...
 constexpr int TC_FUSED_THREADS = G_ROWS * CTA_GROUPS;
+constexpr int TC_STAGGER_CYCLES = 0;           // one-off phase offset between the groups of a CTA (PP_TC_STAGGER overrides)
 struct FusedMap {
     static constexpr uint32_t W = 0, GROUPS_OFF = 2 * PLAYER_W_BYTES;
     static constexpr uint32_t GROUP_STRIDE = GROUP_BYTES;                              // X rows of both players
@@ -412,7 +450,7 @@ template <typename R>
 __global__ void __launch_bounds__(TC_FUSED_THREADS, 1)
 selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_steps, const PPPolicy pol_a,
                    const PPPolicy pol_b, uint64_t seed, int64_t step_base, const PPServeSource src, int32_t quota,
-                   int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks) {
+                   int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks, int stagger) {
     extern __shared__ __align__(128) uint8_t smem[];
     using M = FusedMap;
     const uint32_t tmem = __shfl_sync(0xffffffffu, tc_prologue<CTA_GROUPS, M>(smem, pol_a, pol_b), 0);
@@ -443,6 +481,13 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
         L.ep_idx = s.ep_idx[ic]; L.ep_len = s.ep_len[ic];
         const uint32_t gid = (uint32_t)(env_id_base + ic);
         bool have_next = false;
+        // The four groups of a CTA run identical phases; started together they stay in step with each other: all four wait
+        // for their MMAs at the same time and then compete for the issue slots at the same time.  A one-off offset of
+        // grp * stagger cycles spreads their phases over the step.
+        if (stagger > 0 && grp > 0) {
+            const long long until = clock64() + (long long)grp * stagger;
+            while (clock64() < until) {}
+        }
 
 #pragma unroll 1
         for (int64_t t = 0; t < k_steps; ++t) {
@@ -455,6 +500,9 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
                 philox_serve(params, src.seed, gid, (uint32_t)(L.ep_idx + 1), serve_slot[0], serve_slot[1], serve_slot[2]);
                 have_next = true;
             }
+#ifdef PP_TC_TIMING
+            if (t == 0) g.timer.start();
+#endif
             float oa[7], ob[7];
             observe<R>(L.e, oa, ob);
             if (qa) write_x_row(g.pa.x, row, oa);
@@ -462,6 +510,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
             tc::fence_proxy_async();
             tc::tc_fence_before();
             if (!tc::bar_red_or(g.bar_id, G_ROWS, active)) break;             // whole group frozen by the quota: for good
+            PP_TICK(0);
             float q_a[3] = {0.f, 0.f, 0.f}, q_b[3] = {0.f, 0.f, 0.f};
             if (qa || qb) group_forward(g, q_a, q_b);
             int act_a, act_b;
@@ -477,7 +526,19 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
                 step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
                                  ring.head != nullptr && t >= ring_t0, src, serve, row_stage);
             }
+            PP_TICK(8);
         }
+#ifdef PP_TC_TIMING
+        if (blockIdx.x == 0 && grp == 0 && gw < 2 && lane == 0) {
+            const char *names[9] = {"obs + X rows + barrier", "MMA issue L1", "wait L1", "hidden epilogue", "group barrier",
+                                    "MMA issue L2", "wait L2", "heads epilogue", "actions + env step + bookkeeping"};
+            long long tot = 0;
+            for (int q = 0; q < 9; ++q) tot += g.timer.t[q];
+            for (int q = 0; q < 9; ++q)
+                printf("warp %d  %-34s %8.0f cycles / step\n", gw, names[q], (double)g.timer.t[q] / (double)k_steps);
+            printf("warp %d  %-34s %8.0f cycles / step\n", gw, "STEP TOTAL", (double)tot / (double)k_steps);
+        }
+#endif
         if (valid) {
             store_env<R>(s, i, L.e);
             s.ep_idx[i] = L.ep_idx;
@@ -485,7 +546,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
         }
         total.add(L.tally);
     }
-    if (out.counters) total.flush(out.counters);
+    total.flush(out.counters, out.ep_log ? nullptr : out.ep_log_count);
     tc_epilogue<CTA_GROUPS>(tmem);
 }
 
@@ -528,15 +589,16 @@ int selfplay_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const 
         n_chunks = rounds * slots;
     }
     const unsigned blocks = (unsigned)(n_chunks < slots ? n_chunks : slots);
+    static const int stagger = [] { const char *e = getenv("PP_TC_STAGGER"); return e ? atoi(e) : TC_STAGGER_CYCLES; }();
     cudaError_t err;
     if (mode == PP_MODE_F64) {
         if ((err = cudaFuncSetAttribute(selfplay_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)err;
         selfplay_tc_kernel<double><<<blocks, TC_FUSED_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
-                                                                        env_id_base, out, r, n_chunks);
+                                                                        env_id_base, out, r, n_chunks, stagger);
     } else {
         if ((err = cudaFuncSetAttribute(selfplay_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)err;
         selfplay_tc_kernel<float><<<blocks, TC_FUSED_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
-                                                                       env_id_base, out, r, n_chunks);
+                                                                       env_id_base, out, r, n_chunks, stagger);
     }
     return (int)cudaGetLastError();
 }

@@ -105,12 +105,13 @@ def test_drqn_clip_and_adam_equal_torch():
 
 
 def test_drqn_fused_update_tracks_the_autograd_update_in_a_generation():
-    """Same windows, same noise: the fused trainer and the fused=False (autograd / cuDNN) trainer stay together over a few
-    updates, the graph-captured path included."""
+    """Same windows, same noise: the fused trainer and the fused=False (autograd / cuDNN) trainer stay together over the
+    eager updates; then the fused update runs from its captured CUDA graph."""
     torch.manual_seed(5)
     net = pp.QNetRNN()
     n, T = 256, 32
     ring = _filled_ring(n, T, seed=9)
+    ring.done.copy_((torch.rand(n * T, generator=torch.Generator().manual_seed(2)) < 0.06).to(torch.uint8))
     ring.steps_written = T
     ring.head.fill_(n * T)
     sampler = SequenceSampler(ring, trace_length=8)
@@ -119,10 +120,14 @@ def test_drqn_fused_update_tracks_the_autograd_update_in_a_generation():
     b = DRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=64, use_graph=False, fused=False)
     b.model.load_state_dict(a.model.state_dict())        # the same epsilon buffers
     torch.backends.cudnn.allow_tf32 = False
-    for step in range(6):                                # 3 eager updates, then the captured graph
+    for step in range(3):                                # the eager updates: same RNG stream -> the same windows
         torch.manual_seed(100 + step); la = a.update(sampler)
         torch.manual_seed(100 + step); lb = b.update(sampler)
         assert float(la) == pytest.approx(float(lb), rel=1e-3, abs=1e-6), step
     for (name, p), q in zip(a.model.named_parameters(), b.model.parameters()):
         assert torch.allclose(p, q, rtol=1e-2, atol=2e-4), name
-    assert a.train_steps == b.train_steps == 6 and a._graph is not None
+    before = {k: v.clone() for k, v in a.model.state_dict().items()}
+    losses = [float(a.update(sampler)) for _ in range(5)]         # captured at the 4th update, replayed afterwards
+    assert a._graph is not None and a.train_steps == 8 and all(np.isfinite(l) and l > 0 for l in losses)
+    assert len(set(losses)) == 5                                    # every replay draws fresh windows
+    assert not torch.equal(before["lstm.weight_hh_l0"], a.model.state_dict()["lstm.weight_hh_l0"])
