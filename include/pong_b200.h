@@ -377,6 +377,11 @@ int pp_drqn_grads(const PPReplayRing *ring, const int64_t *rows, int32_t batch, 
                   float gamma, const PPQNetRNNGrads *grads, float *loss_out, float *td_out, float *workspace, void *stream);
 int64_t pp_drqn_workspace_floats(int32_t batch, int32_t trace);
 
+/* QNetRNN in torch's layout -> the fp16 stage image PP_RNNTC_* (PP_RNNTC_BLOB_BYTES bytes, 16-byte aligned) the tensor-core
+ * kernels take as PPPolicy.weights with PP_PREC_F16; noisy != 0: the train-mode weights mu + sigma * epsilon of the three
+ * NoisyLinear layers (models/qnet_rnn.py:44-46).  One launch; the host-side equivalent is policy.pack_qnetrnn_tc. */
+int pp_pack_qnetrnn_tc(const PPQNetRNNParams *net, int32_t noisy, void *image, void *stream);
+
 /* torch.nn.utils.clip_grad_norm_(parameters, max_norm) (:516) on ONE flat gradient buffer (the .grad tensors are views of
  * it): norm_out[0] = total L2 norm, norm_out[1] = the clip coefficient min(1, max_norm / (norm + 1e-6)) the buffer was
  * scaled by.  scratch: 257 floats, ZERO before the first use (left ready for the next call). */

@@ -310,6 +310,13 @@ int pp_drqn_grads(const PPReplayRing *ring, const int64_t *rows, int32_t batch, 
                                        loss_out, td_out, workspace, (cudaStream_t)stream), fn);
 }
 
+int pp_pack_qnetrnn_tc(const PPQNetRNNParams *net, int32_t noisy, void *image, void *stream) {
+    if (!rnn_params_ok(net)) return fail(PP_E_PARAM, "pp_pack_qnetrnn_tc");
+    if (!image) return fail(PP_E_NULL, "pp_pack_qnetrnn_tc");
+    if (reinterpret_cast<uintptr_t>(image) & 15u) return fail(PP_E_ALIGN, "pp_pack_qnetrnn_tc");
+    return ok_or(pp::pack_qnetrnn_tc_launch(*net, noisy, image, (cudaStream_t)stream), "pp_pack_qnetrnn_tc");
+}
+
 int64_t pp_drqn_workspace_floats(int32_t batch, int32_t trace) {
     return (batch > 0 && trace > 0) ? pp::drqn_workspace_floats(batch, trace) : 0;
 }

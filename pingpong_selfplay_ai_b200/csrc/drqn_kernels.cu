@@ -21,6 +21,7 @@
 //   grad_sqnorm_kernel + grad_scale_kernel   torch.nn.utils.clip_grad_norm_ on the flat gradient buffer
 //   adam_multi_kernel + adam_bump_kernel     torch.optim.Adam on the optimiser's own state tensors
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include "pp_host.h"
 
@@ -141,38 +142,62 @@ struct Gemm {
     int relu;
 };
 struct GemmBatch { Gemm g[3]; };
-constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GM = 64, GN = 64, GK = 32, GLD = GM * GK / 256;     // 8 elements of A and of B per thread and K step
 
+// The K loop is software-pipelined: the next K step's operands are fetched from global memory into registers while the
+// current one is multiplied out of shared memory (two shared-memory buffers, one barrier per step).  The weight-gradient
+// products reduce over all 512 window-steps with only a handful of output tiles: without the prefetch every step paid a
+// full global-memory round trip and those three launches were 60 % of the update.
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const GemmBatch batch) {
-    const Gemm &g = batch.g[blockIdx.z];
+    const Gemm g = batch.g[blockIdx.z];
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
     if (m0 >= g.m || n0 >= g.n) return;
-    __shared__ float as[GK][GM + 4], bs[GK][GN + 4];
+    __shared__ __align__(16) float as[2][GK][GM + 4], bs[2][GK][GN + 4];
     const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
     float acc[4][4] = {};
     const bool a_k_fast = g.sak == 1, b_n_fast = g.sbn == 1;
-    for (int k0 = 0; k0 < g.k; k0 += GK) {
+    float ra[GLD], rb[GLD];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < GLD; ++i) {
             const int idx = tid + i * 256;
             const int am = a_k_fast ? idx / GK : idx % GM, ak = a_k_fast ? idx % GK : idx / GM;
-            as[ak][am] = (m0 + am < g.m && k0 + ak < g.k) ? g.a[(int64_t)(m0 + am) * g.sam + (int64_t)(k0 + ak) * g.sak] : 0.0f;
+            ra[i] = (m0 + am < g.m && k0 + ak < g.k) ? g.a[(int64_t)(m0 + am) * g.sam + (int64_t)(k0 + ak) * g.sak] : 0.0f;
             const int bn = b_n_fast ? idx % GN : idx / GK, bk = b_n_fast ? idx / GN : idx % GK;
-            bs[bk][bn] = (n0 + bn < g.n && k0 + bk < g.k) ? g.b[(int64_t)(k0 + bk) * g.sbk + (int64_t)(n0 + bn) * g.sbn] : 0.0f;
+            rb[i] = (n0 + bn < g.n && k0 + bk < g.k) ? g.b[(int64_t)(k0 + bk) * g.sbk + (int64_t)(n0 + bn) * g.sbn] : 0.0f;
         }
-        __syncthreads();
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < GLD; ++i) {
+            const int idx = tid + i * 256;
+            const int am = a_k_fast ? idx / GK : idx % GM, ak = a_k_fast ? idx % GK : idx / GM;
+            as[buf][ak][am] = ra[i];
+            const int bn = b_n_fast ? idx % GN : idx / GK, bk = b_n_fast ? idx / GN : idx % GK;
+            bs[buf][bk][bn] = rb[i];
+        }
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < g.k; k0 += GK) {
+        const bool more = k0 + GK < g.k;
+        if (more) fetch(k0 + GK);
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
-            const float4 av = *reinterpret_cast<const float4 *>(&as[kk][ty * 4]);
-            const float4 bv = *reinterpret_cast<const float4 *>(&bs[kk][tx * 4]);
+            const float4 av = *reinterpret_cast<const float4 *>(&as[buf][kk][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4 *>(&bs[buf][kk][tx * 4]);
             const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
         }
+        if (more) stash(buf ^ 1);
         __syncthreads();
+        buf ^= 1;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -429,27 +454,34 @@ drqn_finalize_kernel(int B, int L, const float *__restrict__ ws_dgx, const float
     const int64_t R = (int64_t)B * L;
     const int tiles = B / BT;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-    // column sums: b_ih = b_hh (512), features.2 bias (128), features.0 bias (64), shared-head bias (128)
-    for (int64_t i = gtid; i < GATES + FEAT + F1D + SH; i += stride) {
+    // column sums: b_ih = b_hh (512), features.2 bias (128), features.0 bias (64), shared-head bias (128).  A CTA takes 32
+    // columns at a time: 8 row lanes per column walk the rows, then add up in a fixed order through shared memory.
+    __shared__ float colpart[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    for (int c0 = blockIdx.x * 32; c0 < GATES + FEAT + F1D + SH; c0 += gridDim.x * 32) {
+        const int i = c0 + cl;                                       // all four segments are multiples of 32 columns wide
+        const float *src; int64_t ld; int64_t nrows; int j;
+        if (i < GATES) { src = ws_dgx; ld = GATES; nrows = R; j = i; }
+        else if (i < GATES + FEAT) { src = ws_df2; ld = FEAT; nrows = R; j = i - GATES; }
+        else if (i < GATES + FEAT + F1D) { src = ws_df1; ld = F1D; nrows = R; j = i - GATES - FEAT; }
+        else { src = ws_ds; ld = SH; nrows = B; j = i - GATES - FEAT - F1D; }
         float acc = 0.0f;
-        if (i < GATES) {
-            for (int64_t rr = 0; rr < R; ++rr) acc += ws_dgx[rr * GATES + i];
-            if (gr.b_ih) gr.b_ih[i] = acc;
-            if (gr.b_hh) gr.b_hh[i] = acc;
-        } else if (i < GATES + FEAT) {
-            const int j = (int)(i - GATES);
-            for (int64_t rr = 0; rr < R; ++rr) acc += ws_df2[rr * FEAT + j];
-            if (gr.f2_b) gr.f2_b[j] = acc;
-        } else if (i < GATES + FEAT + F1D) {
-            const int j = (int)(i - GATES - FEAT);
-            for (int64_t rr = 0; rr < R; ++rr) acc += ws_df1[rr * F1D + j];
-            if (gr.f0_b) gr.f0_b[j] = acc;
-        } else {
-            const int j = (int)(i - GATES - FEAT - F1D);
-            for (int bb = 0; bb < B; ++bb) acc += ws_ds[(int64_t)bb * SH + j];
-            if (gr.shared.grad_bias_mu) gr.shared.grad_bias_mu[j] = acc;
-            if (gr.shared.grad_bias_sigma) gr.shared.grad_bias_sigma[j] = noisy_on ? acc * on.shared.bias_epsilon[j] : 0.0f;
+        for (int64_t rr = rl; rr < nrows; rr += 8) acc += src[rr * ld + j];
+        colpart[rl][cl] = acc;
+        __syncthreads();
+        if (rl == 0) {
+            float t = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += colpart[q][cl];
+            if (i < GATES) { if (gr.b_ih) gr.b_ih[j] = t; if (gr.b_hh) gr.b_hh[j] = t; }
+            else if (i < GATES + FEAT) { if (gr.f2_b) gr.f2_b[j] = t; }
+            else if (i < GATES + FEAT + F1D) { if (gr.f0_b) gr.f0_b[j] = t; }
+            else {
+                if (gr.shared.grad_bias_mu) gr.shared.grad_bias_mu[j] = t;
+                if (gr.shared.grad_bias_sigma) gr.shared.grad_bias_sigma[j] = noisy_on ? t * on.shared.bias_epsilon[j] : 0.0f;
+            }
         }
+        __syncthreads();
     }
     for (int64_t i = gtid; i < (int64_t)GATES * HID; i += stride) {              // dW_hh: the window tiles in order
         float acc = 0.0f;
@@ -638,6 +670,108 @@ int adam_multi_launch(const PPAdamParam *params, int32_t count, double lr, doubl
     blocks = blocks < 1 ? 1 : (blocks > 296 ? 296 : blocks);
     adam_multi_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pack, count, lr, beta1, beta2, eps);
     adam_bump_kernel<<<1, 32, 0, stream>>>(pack, count);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pp
+
+// ------------------------------------------------------------------------------------------ weight image for the tensor-core rollout
+// QNetRNN in torch's layout -> the fp16 stage image PP_RNNTC_* (include/pong_b200.h) that selfplay_rnn_tc_kernel streams
+// with TMA: what policy.pack_qnetrnn_tc builds with ~100 framework kernels (2.6 ms per training chunk), in one launch.
+// Every tile is K-major, no swizzle: element (k, n) of a [K][N] tile sits at half index ((k / 8) * N + n) * 8 + k % 8.
+namespace pp {
+namespace {
+
+__device__ __forceinline__ float noisy_w(const PPNoisyLayer &l, int64_t i, int noisy) {
+    return noisy ? l.weight_mu[i] + l.weight_sigma[i] * l.weight_epsilon[i] : l.weight_mu[i];
+}
+__device__ __forceinline__ float noisy_b(const PPNoisyLayer &l, int64_t i, int noisy) {
+    return noisy ? l.bias_mu[i] + l.bias_sigma[i] * l.bias_epsilon[i] : l.bias_mu[i];
+}
+__device__ __forceinline__ __half hi_of(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ __half lo_of(float v) { return __float2half_rn(v - __half2float(__float2half_rn(v))); }
+
+// value of logical matrix `mat` at (k, n):  0 features.0^T (7 x 64)  1 features.2^T (64 x 128)  2 [W_ih | W_hh]^T (256 x 512, torch
+// gate-major columns)  3 shared head^T (128 x 128)  4 heads^T (128 x 4: V, A0, A1, A2)
+__device__ __forceinline__ float mat_at(const PPQNetRNNParams &p, int noisy, int mat, int k, int n) {
+    switch (mat) {
+        case 0: return p.f0_w[n * OBS + k];
+        case 1: return p.f2_w[n * F1D + k];
+        case 2: return k < FEAT ? p.w_ih[(int64_t)n * FEAT + k] : p.w_hh[(int64_t)n * HID + (k - FEAT)];
+        case 3: return noisy_w(p.shared, (int64_t)n * HID + k, noisy);
+        default: return n == 0 ? noisy_w(p.v, k, noisy) : noisy_w(p.a, (int64_t)(n - 1) * SH + k, noisy);
+    }
+}
+__device__ __forceinline__ float bias_at(const PPQNetRNNParams &p, int noisy, int mat, int n) {
+    switch (mat) {
+        case 0: return p.f0_b[n];
+        case 1: return p.f2_b[n];
+        case 2: return p.b_ih[n] + p.b_hh[n];
+        case 3: return noisy_b(p.shared, n, noisy);
+        default: return n == 0 ? noisy_b(p.v, 0, noisy) : noisy_b(p.a, n - 1, noisy);
+    }
+}
+
+// One tile of the image: `rows` K-rows x `cols` columns at byte offset `off`.  kind 0 = hi(w), 1 = lo(w), 2 = bias tile
+// (16 x cols: bias hi in row 7, lo in row 15), 3 / 4 = the K = 16 first-layer tiles W1h' / W1l'.  Logical element (k, n) of
+// the tile is matrix element (k0 + k, column map(n)); for the gate matrix column n of quarter q is gate n / 32, unit
+// 32 q + n % 32, i.e. torch column (n / 32) * 128 + 32 q + n % 32.
+struct PackTile { int32_t off, kind, mat, rows, cols, k0, quarter; };
+struct PackPlan { PackTile t[96]; int count; };
+
+__global__ void __launch_bounds__(256)
+pack_qnetrnn_tc_kernel(const PPQNetRNNParams p, int noisy, const PackPlan plan, __half *__restrict__ img) {
+    for (int ti = blockIdx.y; ti < plan.count; ti += gridDim.y) {
+        const PackTile &t = plan.t[ti];
+        __half *out = img + t.off / 2;
+        const int total = t.rows * t.cols;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+            const int kk = e & 7, n = (e >> 3) % t.cols, kc = e / (8 * t.cols), k = kc * 8 + kk;     // e is the half index in the tile
+            const int col = t.mat == 2 ? (n / 32) * HID + 32 * t.quarter + (n % 32) : n;
+            __half v = __float2half_rn(0.0f);
+            if (t.kind == 0) v = hi_of(mat_at(p, noisy, t.mat, t.k0 + k, col));
+            else if (t.kind == 1) v = lo_of(mat_at(p, noisy, t.mat, t.k0 + k, col));
+            else if (t.kind == 2) {
+                const bool real = t.mat != 4 || n < 4;
+                if (k == 7 && real) v = hi_of(bias_at(p, noisy, t.mat, col));
+                else if (k == 15 && real) v = lo_of(bias_at(p, noisy, t.mat, col));
+            } else if (t.kind == 3) {                          // rows 0..6 and 8..14: hi(W1^T); row 7: hi(b1); row 15: lo(b1)
+                if ((k & 7) < 7) v = hi_of(mat_at(p, noisy, 0, k & 7, n));
+                else v = k == 7 ? hi_of(bias_at(p, noisy, 0, n)) : lo_of(bias_at(p, noisy, 0, n));
+            } else {                                           // rows 0..6: lo(W1^T)
+                if (k < 7) v = lo_of(mat_at(p, noisy, 0, k, n));
+            }
+            if (t.mat == 4 && t.kind < 2 && n >= 4) v = __float2half_rn(0.0f);        // heads: columns 4..15 are padding
+            out[e] = v;
+        }
+    }
+}
+
+}  // namespace
+
+int pack_qnetrnn_tc_launch(const PPQNetRNNParams &p, int noisy, void *image, cudaStream_t stream) {
+    static PackPlan plan = [] {
+        PackPlan pl{};
+        int off = 0;
+        auto add = [&](int kind, int mat, int rows, int cols, int k0, int quarter) {
+            pl.t[pl.count++] = PackTile{off, kind, mat, rows, cols, k0, quarter};
+            off += rows * cols * 2;
+        };
+        add(3, 0, 16, 64, 0, 0); add(4, 0, 16, 64, 0, 0);                                     // S0
+        add(0, 1, 64, 128, 0, 0); add(2, 1, 16, 128, 0, 0); add(1, 1, 64, 128, 0, 0);         // S1, S2
+        for (int q = 0; q < 4; ++q) {
+            for (int c = 0; c < 4; ++c) {
+                add(0, 2, 64, 128, 64 * c, q);
+                if (c == 0) add(2, 2, 16, 128, 0, q);
+            }
+            for (int c = 0; c < 4; ++c) add(1, 2, 64, 128, 64 * c, q);
+        }
+        add(0, 3, 64, 128, 0, 0); add(2, 3, 16, 128, 0, 0); add(0, 3, 64, 128, 64, 0);        // shared head
+        add(1, 3, 64, 128, 0, 0); add(1, 3, 64, 128, 64, 0);
+        add(0, 4, 128, 16, 0, 0); add(1, 4, 128, 16, 0, 0); add(2, 4, 16, 16, 0, 0);          // dueling heads
+        return pl;
+    }();
+    pack_qnetrnn_tc_kernel<<<dim3(4, plan.count), 256, 0, stream>>>(p, noisy, plan, reinterpret_cast<__half *>(image));
     return (int)cudaGetLastError();
 }
 

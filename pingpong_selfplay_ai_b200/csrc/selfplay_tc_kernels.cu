@@ -2,27 +2,29 @@
 // built on it.
 //
 // A *group* is 128 threads = 128 envs = the 128 rows (TMEM lanes) of one UMMA tile; a CTA holds four groups that
-// run independently (named barriers, one mbarrier each), so one group's epilogue overlaps the others' MMA round
-// trips, and there is one CTA per SM.  The QNet (models/qnet.py:71-75) of one player is three tcgen05.mma batches
-// with fp16 operands and fp32 accumulation in TMEM.  Activations AND weights are split x = x_hi + x_lo into two
-// fp16 numbers (22 significant bits) and every product is taken as hi*hi + lo*hi + hi*lo, so Q-values carry
-// ~fp32 accuracy (measured ~1e-6 relative) instead of fp16's 2^-12 — trained heads have |W| > 20, where a
-// single fp16 pass is off by 3e-2:
+// run independently (named barriers, two mbarriers each), so one group's epilogue overlaps the others' MMA round
+// trips, and there is one CTA per SM.  The QNet (models/qnet.py:71-75) of one player is two tcgen05.mma batches
+// with fp16 operands and fp32 accumulation in TMEM, and the dueling heads in fp32 on the CUDA cores.  Activations AND
+// weights are split x = x_hi + x_lo into two fp16 numbers (22 significant bits) and every product is taken as
+// hi*hi + lo*hi + hi*lo, so Q-values carry ~fp32 accuracy (measured ~1e-6 relative) instead of fp16's 2^-12 — trained
+// heads have |W| > 20, where a single fp16 pass is off by 3e-2:
 //     L1  D[128x64] = X * W1h'^T + X * W1l'^T      X = [obs_hi(7) 1 | obs_lo(7) 1]   (2 MMAs, K = 16)
 //                                                  W1h' = [W1_hi ; b1_hi | W1_hi ; b1_lo], W1l' = [W1_lo ; 0 | 0]
 //     L2  D[128x64] = H1h*W2h^T + H1l*W2h^T + H1h*W2l^T (3 x 4 MMAs, K = 16 each) + X * B2'^T (bias via X's ones)
-//     L3  D[128x16] = same with the dueling heads, N = 16 (columns 0..3 = V, A0, A1, A2)
-// Between layers each thread reads ITS row of the accumulator (tcgen05.ld 32x32b), applies ReLU, splits and writes
-// the row back to TENSOR MEMORY (tcgen05.st) as the next A operand: hidden activations never touch shared memory,
-// the MMAs read A from TMEM (two fp16 per 32-bit column) and only the small weight tiles from shared memory.  A
-// group owns 128 TMEM columns, used as two 64-column regions that ping-pong between accumulator and A operand:
-//     L1 -> R0;  epilogue R0 -> H1 in R1;  L2 (A = R1) -> R0;  epilogue R0 -> H2 in R1;  L3 (A = R1) -> R0[0..15]
+//     heads: (V, A0, A1, A2) = ReLU(D) . Wh + bh as packed fp32 FFMA2 per thread, then V + (A - mean A)
+// Between the layers each thread reads ITS row of the accumulator (tcgen05.ld 32x32b), applies ReLU, splits and writes
+// the row back to TENSOR MEMORY IN PLACE (tcgen05.st over the accumulator's own columns) as the next A operand: hidden
+// activations never touch shared memory, the MMAs read A from TMEM (two fp16 per 32-bit column) and only the small
+// weight tiles from shared memory.  A group owns 128 TMEM columns = two 64-column regions:
+//     L1 -> R0;  epilogue: H1 in place over R0;  L2 (A = R0) -> R1;  heads read R1
+// and the second player's L1 goes to R0 as soon as the first player's L2 has completed, under the first player's head
+// epilogue (group_forward_both).
 // The shared-memory operands (X rows, weight tiles) use the no-swizzle K-major canonical layout stored as
 // [K/8][rows][8 halves]: a thread's 16-byte chunk stores are contiguous across the warp (conflict-free) and the
 // descriptor strides are LBO = rows*16 B (next K chunk), SBO = 128 B (next 8-row core matrix).
-// The two players' chains run one after the other in the same two regions.
-// Both players' fp32 weight blobs arrive by one TMA bulk copy each (cp.async.bulk + mbarrier) into a staging
-// area and are converted once per launch into fp16 B-operand tiles that stay in shared memory for all k steps.
+// Both players' fp32 weight blobs arrive by one TMA bulk copy each (cp.async.bulk + mbarrier: the 1-D bulk form, no
+// tensor map — the blobs are contiguous) into a staging area and are converted once per launch into fp16 B-operand
+// tiles that stay in shared memory for all k steps.
 // Env state, observations and bookkeeping never leave registers (same step_and_book as the CUDA-core kernel).
 #include <cuda_fp16.h>
 
@@ -48,25 +50,28 @@ constexpr uint32_t W1H_OFF = 0, W1L_OFF = W1H_OFF + W1_BYTES, W2H_OFF = W1L_OFF 
                    B3_OFF = W3L_OFF + W3_BYTES, PLAYER_W_BYTES = B3_OFF + B3_BYTES;              // 27136
 constexpr uint32_t X_BYTES = 2 * G_ROWS * 16;                                                    // 4096
 constexpr uint32_t GROUP_BYTES = 2 * X_BYTES;                                                    // X rows of both players
-constexpr uint32_t H_BYTES = 16 * G_ROWS * 16;  // one hidden-activation A tile in shared memory: [16 chunks][128 rows][8 halves],
-                                                // chunks 0..7 = hi (K = 64), 8..15 = lo                                  32768
 constexpr uint32_t TM_R1 = 64;                  // TMEM columns of a group: region R0 at +0, R1 at +64 (64 columns each)
 // A hidden-activation operand written IN PLACE over the accumulator it was computed from: accumulator columns
 // [32 h, 32 h + 32) become packed hi pairs [32 h, +16) and packed lo pairs [32 h + 16, +16).  K step j (16 units) of the
 // hi part therefore starts at column tm_hi(j), of the lo part at tm_hi(j) + 16.
 __device__ __forceinline__ constexpr uint32_t tm_hi(int j) { return (uint32_t)((j >> 1) * 32 + (j & 1) * 8); }
 constexpr uint32_t BLOB_BYTES = PP_QNET_BLOB_FLOATS * 4;                                         // 19728
+constexpr uint32_t CTRL_BYTES = 128;
 
 template <int GROUPS> struct SmemMap {
     static constexpr uint32_t W = 0;                                        // [2 players][PLAYER_W_BYTES]
     static constexpr uint32_t GROUPS_OFF = 2 * PLAYER_W_BYTES;              // [GROUPS][GROUP_BYTES]; start: blob staging
     static constexpr uint32_t CTRL = GROUPS_OFF + (GROUPS * GROUP_BYTES > 2 * BLOB_BYTES ? GROUPS * GROUP_BYTES : 2 * BLOB_BYTES);
-    static constexpr uint32_t TOTAL = CTRL + 64;                            // mbarriers + TMEM base
+    static constexpr uint32_t TOTAL = CTRL + CTRL_BYTES;                    // mbarriers + TMEM base
 };
-// control block (64 B): mbarriers [0] weights, [1 + g] group g at CTRL + 8 * b; the TMEM base slot follows them
+// control block (CTRL_BYTES): mbarriers [0] weights, [1 + 2 g + w] = barrier w of group g; the TMEM base slot follows them.
+// A group alternates between TWO completion barriers: consecutive MMA batches of a group are not always separated by a
+// group barrier (L1_B is committed right after L2_A has been observed), and a parity wait on ONE barrier cannot tell
+// "phase k not yet complete" from "phases k and k + 1 both complete".  With two barriers a barrier's next phase is only
+// committed after a group barrier that every thread reaches after having observed its previous phase.
 template <int GROUPS> struct CtrlMap {
-    static constexpr uint32_t TMEM_SLOT = (8 * (1 + GROUPS) + 15) / 16 * 16;
-    static_assert(8 * (1 + GROUPS) <= TMEM_SLOT && TMEM_SLOT + 4 <= 64, "TMEM base slot must not overlap the mbarriers");
+    static constexpr uint32_t TMEM_SLOT = (8 * (1 + 2 * GROUPS) + 15) / 16 * 16;
+    static_assert(8 * (1 + 2 * GROUPS) <= TMEM_SLOT && TMEM_SLOT + 4 <= CTRL_BYTES, "TMEM base slot must not overlap the mbarriers");
 };
 
 struct PlayerTiles {     // shared-memory (generic) pointers of one player's operands
@@ -142,24 +147,6 @@ __device__ __forceinline__ void hidden_epilogue_inplace(uint32_t acc) {
     tc::tmem_st_wait();
 }
 
-// The same, but the operand goes to a shared-memory A tile (H_BYTES, K-major, no swizzle): it frees the accumulator
-// region at once, which is what lets the two players' second layers follow each other without a drain in between.
-__device__ __forceinline__ void hidden_epilogue_smem(uint32_t acc, uint8_t *tile, int row) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t r0[16], r1[16], hi[16], lo[16];
-        tc::tmem_ld16(acc + half * 32, r0);
-        tc::tmem_ld16(acc + half * 32 + 16, r1);
-        tc::tmem_ld_wait();
-        split32(r0, r1, hi, lo);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {                                         // chunk = 8 hidden units = 4 packed words
-            *reinterpret_cast<uint4 *>(tile + (half * 4 + q) * A_LBO + row * 16) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            *reinterpret_cast<uint4 *>(tile + (8 + half * 4 + q) * A_LBO + row * 16) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-        }
-    }
-}
-
 // Second hidden layer's accumulator row (64 fp32 columns at `src`) -> ReLU -> the four head outputs in fp32 on the CUDA
 // cores (256 FMAs against a broadcast float4 table) -> dueling Q.  This replaces a third MMA batch (13 small MMAs at the
 // 45-cycle instruction floor, one more accumulator round trip and group barrier per player) and keeps the heads exact.
@@ -202,24 +189,17 @@ __device__ __forceinline__ void issue_l1(uint32_t d, const PlayerTiles &p) {
     tc::umma_f16(d, x, tc::smem_desc(tc::smem_u32(p.w + W1H_OFF), 64 * 16, SBO), tc::idesc_f16(128, 64), false);
     tc::umma_f16(d, x, tc::smem_desc(tc::smem_u32(p.w + W1L_OFF), 64 * 16, SBO), tc::idesc_f16(128, 64), true);
 }
-// D = Hh*Wh + Hl*Wh + Hh*Wl + X*B'  (second layer, N = 64): H = the in-place operand in TMEM at a_tm (A_SMEM = false)
-// or the shared-memory tile `h_tile` (A_SMEM = true)
-template <bool A_SMEM>
-__device__ __forceinline__ void issue_l2(uint32_t d, uint32_t a_tm, const uint8_t *h_tile, const PlayerTiles &p) {
+// D = Hh*Wh + Hl*Wh + Hh*Wl + X*B'  (second layer, N = 64): H = the in-place operand in TMEM at a_tm
+__device__ __forceinline__ void issue_l2(uint32_t d, uint32_t a_tm, const PlayerTiles &p) {
     const uint32_t wh = tc::smem_u32(p.w + W2H_OFF), wl = tc::smem_u32(p.w + W2L_OFF);
     constexpr uint32_t B_LBO = 64 * 16;
-    const uint32_t ht = A_SMEM ? tc::smem_u32(h_tile) : 0u;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
         const uint32_t b = pass == 2 ? wl : wh;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {       // K = 16 per MMA = 8 TMEM columns / 2 shared-memory chunks of A, 2 chunks of B
-            const uint64_t bd = tc::smem_desc(b + j * 2 * B_LBO, B_LBO, SBO);
-            if (A_SMEM)
-                tc::umma_f16(d, tc::smem_desc(ht + ((pass == 1 ? 8 : 0) + 2 * j) * A_LBO, A_LBO, SBO), bd, tc::idesc_f16(128, 64), (pass | j) != 0);
-            else
-                tc::umma_f16_ts(d, a_tm + tm_hi(j) + (pass == 1 ? 16u : 0u), bd, tc::idesc_f16(128, 64), (pass | j) != 0);
-        }
+        for (int j = 0; j < 4; ++j)         // K = 16 per MMA = 8 TMEM columns of A, 2 shared-memory chunks of B
+            tc::umma_f16_ts(d, a_tm + tm_hi(j) + (pass == 1 ? 16u : 0u), tc::smem_desc(b + j * 2 * B_LBO, B_LBO, SBO),
+                            tc::idesc_f16(128, 64), (pass | j) != 0);
     }
     tc::umma_f16(d, tc::smem_desc(tc::smem_u32(p.x), A_LBO, SBO), tc::smem_desc(tc::smem_u32(p.w + B2_OFF), B_LBO, SBO),
                  tc::idesc_f16(128, 64), true);
@@ -228,12 +208,12 @@ __device__ __forceinline__ void issue_l2(uint32_t d, uint32_t a_tm, const uint8_
 // Shared prologue: barriers, TMEM, weights.  Returns the TMEM base of the CTA.
 template <int GROUPS, typename M>
 __device__ __forceinline__ uint32_t tc_prologue(uint8_t *smem, const PPPolicy &pol_a, const PPPolicy &pol_b) {
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + M::CTRL);           // [0] weights, [1 + g] group g
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + M::CTRL);           // [0] weights, [1 + 2 g + w] group g
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + M::CTRL + CtrlMap<GROUPS>::TMEM_SLOT);
     const int tid = threadIdx.x;
     const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
     if (tid == 0) {
-        for (int b = 0; b < 1 + GROUPS; ++b) tc::mbar_init(bars + b, 1);
+        for (int b = 0; b < 1 + 2 * GROUPS; ++b) tc::mbar_init(bars + b, 1);
         tc::fence_mbar_init();
     }
     if (tid < 32) tc::tmem_alloc<GROUPS * 128>(tmem_slot);
@@ -265,7 +245,7 @@ template <int GROUPS> __device__ __forceinline__ void tc_epilogue(uint32_t tmem)
 // thread and printed for lane 0 of the first two warps of group 0 of CTA 0.
 #ifdef PP_TC_TIMING
 struct PhaseTimer {
-    long long t[10] = {}, last = 0;
+    long long t[12] = {}, last = 0;
     __device__ __forceinline__ void start() { last = clock64(); }
     __device__ __forceinline__ void tick(int i) { const long long now = clock64(); t[i] += now - last; last = now; }
 };
@@ -280,26 +260,25 @@ struct GroupCtx {
     PhaseTimer timer;
 #endif
     PlayerTiles pa, pb;
-    uint8_t *h_tile;                             // shared-memory A tile of player B's hidden activations (fused kernel only)
-    uint64_t *bar;
-    uint32_t parity, r0, bar_id, lane_addr;      // r0: the group's first TMEM column (lane 0); R1 = r0 + TM_R1
+    uint64_t *bar;                               // two completion barriers, used alternately: bar[0] = L1 batches, bar[1] = L2
+    uint32_t parity[2], r0, bar_id, lane_addr;   // r0: the group's first TMEM column (lane 0); R1 = r0 + TM_R1
     int row;
     bool qa, qb, issuer_warp;
 };
 
-__device__ __forceinline__ void group_wait(GroupCtx &g) {
-    tc::mbar_wait(g.bar, g.parity);
-    g.parity ^= 1u;
+template <int W> __device__ __forceinline__ void group_wait(GroupCtx &g) {
+    tc::mbar_wait(g.bar + W, g.parity[W]);
+    g.parity[W] ^= 1u;
     tc::tc_fence_after();
 }
 
-// an elected lane of the group's first warp runs `issue` and commits to the group's mbarrier
-template <typename F> __device__ __forceinline__ void group_issue(GroupCtx &g, F &&issue) {
+// an elected lane of the group's first warp runs `issue` and commits to completion barrier W of the group
+template <int W, typename F> __device__ __forceinline__ void group_issue(GroupCtx &g, F &&issue) {
     if (g.issuer_warp) {                      // warp-uniform branch
         if (tc::elect_one()) {
             tc::tc_fence_after();
             issue();
-            tc::umma_commit(g.bar);
+            tc::umma_commit(g.bar + W);
         }
         __syncwarp();
     }
@@ -307,13 +286,13 @@ template <typename F> __device__ __forceinline__ void group_issue(GroupCtx &g, F
 
 // ONE QNet player p: L1 -> R0; H in place; L2 -> R1; (ReLU, fp32 heads on the CUDA cores) -> Q
 __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles &p, float (&q)[3]) {
-    group_issue(g, [&] { issue_l1(g.r0, p); });
-    group_wait(g);
+    group_issue<0>(g, [&] { issue_l1(g.r0, p); });
+    group_wait<0>(g);
     hidden_epilogue_inplace(g.r0 + g.lane_addr);
     tc::tc_fence_before();
     tc::bar_sync(g.bar_id, G_ROWS);
-    group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, p); });
-    group_wait(g);
+    group_issue<1>(g, [&] { issue_l2(g.r0 + TM_R1, g.r0, p); });
+    group_wait<1>(g);
     heads_epilogue(g.r0 + TM_R1 + g.lane_addr, p.w + W3H_OFF, q);
 }
 
@@ -326,33 +305,33 @@ __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles
 // that L2_B could follow L2_A without a drain, was 7 % SLOWER: 12 SS-mode MMAs read 48 KB of A operand per group-step
 // from shared memory and the 32 KB of epilogue stores compete with the head table's LDS traffic.]
 __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
-    group_issue(g, [&] { issue_l1(g.r0, g.pa); });
+    group_issue<0>(g, [&] { issue_l1(g.r0, g.pa); });
     PP_TICK(1);
-    group_wait(g);
+    group_wait<0>(g);
     PP_TICK(2);
     hidden_epilogue_inplace(g.r0 + g.lane_addr);
     tc::tc_fence_before();
     PP_TICK(3);
     tc::bar_sync(g.bar_id, G_ROWS);
     PP_TICK(4);
-    group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, g.pa); });
+    group_issue<1>(g, [&] { issue_l2(g.r0 + TM_R1, g.r0, g.pa); });
     PP_TICK(5);
-    group_wait(g);
+    group_wait<1>(g);
     PP_TICK(6);
-    group_issue(g, [&] { issue_l1(g.r0, g.pb); });
+    group_issue<0>(g, [&] { issue_l1(g.r0, g.pb); });     // no group barrier since the last commit: the OTHER completion barrier
     PP_TICK(1);
     heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pa.w + W3H_OFF, q_a);
     PP_TICK(7);
-    group_wait(g);
+    group_wait<0>(g);
     PP_TICK(2);
     hidden_epilogue_inplace(g.r0 + g.lane_addr);
     tc::tc_fence_before();
     PP_TICK(3);
     tc::bar_sync(g.bar_id, G_ROWS);                 // also: every thread has read its heads_A row of R1
     PP_TICK(4);
-    group_issue(g, [&] { issue_l2<false>(g.r0 + TM_R1, g.r0, nullptr, g.pb); });
+    group_issue<1>(g, [&] { issue_l2(g.r0 + TM_R1, g.r0, g.pb); });
     PP_TICK(5);
-    group_wait(g);
+    group_wait<1>(g);
     PP_TICK(6);
     heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pb.w + W3H_OFF, q_b);
     PP_TICK(7);
@@ -373,15 +352,14 @@ __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], floa
 // `grp` and `tmem` must be warp-uniform VALUES THE COMPILER CAN SEE as uniform (shfl broadcasts), so that the UMMA
 // descriptors derived from them live in uniform registers instead of being re-broadcast before every MMA.
 __device__ __forceinline__ GroupCtx make_group(uint8_t *smem, uint32_t groups_off, uint32_t ctrl_off, uint32_t tmem, int grp,
-                                               int row, bool qa, bool qb, uint32_t group_stride = GROUP_BYTES, bool with_h_tile = false) {
+                                               int row, bool qa, bool qb) {
     GroupCtx g;
-    uint8_t *gb = smem + groups_off + grp * group_stride;
+    uint8_t *gb = smem + groups_off + grp * GROUP_BYTES;
     g.pa = PlayerTiles{smem, gb};
     g.pb = PlayerTiles{smem + PLAYER_W_BYTES, gb + X_BYTES};
-    g.h_tile = with_h_tile ? gb + GROUP_BYTES : nullptr;
     g.row = row;
-    g.bar = reinterpret_cast<uint64_t *>(smem + ctrl_off) + 1 + grp;
-    g.parity = 0;
+    g.bar = reinterpret_cast<uint64_t *>(smem + ctrl_off) + 1 + 2 * grp;
+    g.parity[0] = g.parity[1] = 0;
     g.r0 = tmem + grp * 128;
     g.bar_id = 1 + grp;
     g.lane_addr = (uint32_t)((row >> 5) * 32) << 16;
@@ -437,10 +415,9 @@ constexpr int TC_FUSED_THREADS = G_ROWS * CTA_GROUPS;
 constexpr int TC_STAGGER_CYCLES = 0;           // one-off phase offset between the groups of a CTA (PP_TC_STAGGER overrides)
 struct FusedMap {
     static constexpr uint32_t W = 0, GROUPS_OFF = 2 * PLAYER_W_BYTES;
-    static constexpr uint32_t GROUP_STRIDE = GROUP_BYTES;                              // X rows of both players
-    static constexpr uint32_t SERVE_OFF = GROUPS_OFF + CTA_GROUPS * GROUP_STRIDE;      // next serve per thread: 3 doubles
+    static constexpr uint32_t SERVE_OFF = GROUPS_OFF + CTA_GROUPS * GROUP_BYTES;      // next serve per thread: 3 doubles
     static constexpr uint32_t CTRL = SERVE_OFF + TC_FUSED_THREADS * 24;                // mbarriers + TMEM base
-    static constexpr uint32_t STAGE_OFF = (CTRL + 64 + 127) / 128 * 128;               // replay-row staging: 896 B per warp
+    static constexpr uint32_t STAGE_OFF = (CTRL + CTRL_BYTES + 127) / 128 * 128;       // replay-row staging: 896 B per warp
     static constexpr uint32_t TOTAL = STAGE_OFF + (TC_FUSED_THREADS / 32) * 896;
 };
 static_assert(FusedMap::TOTAL <= 232448, "shared memory of the fused tensor-core kernel exceeds 227 KB");
@@ -509,8 +486,9 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
             if (qb) write_x_row(g.pb.x, row, ob);
             tc::fence_proxy_async();
             tc::tc_fence_before();
-            if (!tc::bar_red_or(g.bar_id, G_ROWS, active)) break;             // whole group frozen by the quota: for good
             PP_TICK(0);
+            if (!tc::bar_red_or(g.bar_id, G_ROWS, active)) break;             // whole group frozen by the quota: for good
+            PP_TICK(10);
             float q_a[3] = {0.f, 0.f, 0.f}, q_b[3] = {0.f, 0.f, 0.f};
             if (qa || qb) group_forward(g, q_a, q_b);
             int act_a, act_b;
@@ -518,6 +496,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
             else act_a = explore(qa ? argmax3(q_a) : follower_action(oa, pol_a.follower_tol), pol_a.eps_threshold, seed, gid, step, STREAM_ACT_A);
             if (pol_b.kind == PP_POLICY_RANDOM) act_b = random_action(seed, gid, step, STREAM_ACT_B);
             else act_b = explore(qb ? argmax3(q_b) : follower_action(ob, pol_b.follower_tol), pol_b.eps_threshold, seed, gid, step, STREAM_ACT_B);
+            PP_TICK(8);
             if (gw < my_warps) {      // warp-uniform: warps without envs skip the bookkeeping collectives entirely
                 auto serve = [&](int ep, R &vx, R &vy, R &sp) {
                     if (have_next) { vx = (R)serve_slot[0]; vy = (R)serve_slot[1]; sp = (R)serve_slot[2]; have_next = false; }
@@ -526,15 +505,16 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
                 step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
                                  ring.head != nullptr && t >= ring_t0, src, serve, row_stage);
             }
-            PP_TICK(8);
+            PP_TICK(9);
         }
 #ifdef PP_TC_TIMING
         if (blockIdx.x == 0 && grp == 0 && gw < 2 && lane == 0) {
-            const char *names[9] = {"obs + X rows + barrier", "MMA issue L1", "wait L1", "hidden epilogue", "group barrier",
-                                    "MMA issue L2", "wait L2", "heads epilogue", "actions + env step + bookkeeping"};
+            const char *names[11] = {"serve prefetch + obs + X rows", "MMA issue L1", "wait L1", "hidden epilogue", "group barrier",
+                                     "MMA issue L2", "wait L2", "heads epilogue", "argmax / explore", "env step + bookkeeping",
+                                     "step barrier (skew of the group)"};
             long long tot = 0;
-            for (int q = 0; q < 9; ++q) tot += g.timer.t[q];
-            for (int q = 0; q < 9; ++q)
+            for (int q = 0; q < 11; ++q) tot += g.timer.t[q];
+            for (int q = 0; q < 11; ++q)
                 printf("warp %d  %-34s %8.0f cycles / step\n", gw, names[q], (double)g.timer.t[q] / (double)k_steps);
             printf("warp %d  %-34s %8.0f cycles / step\n", gw, "STEP TOTAL", (double)tot / (double)k_steps);
         }

@@ -190,6 +190,19 @@ class DRQNTrainer(DQNTrainer):
             _lib.PPAdamParam(_ptr(p), _ptr(p.grad), _ptr(self.opt.state[p]["exp_avg"]), _ptr(self.opt.state[p]["exp_avg_sq"]),
                              _ptr(self.opt.state[p]["step"]), p.numel()) for p in self.params])
 
+    def reset_noise_and_pack_tc(self, image: torch.Tensor, seed: int = 0):
+        """model.reset_noise() + pack_qnetrnn_tc(model, noisy=True) into `image` (a tensor-core player's weights) on the
+        device: two launches (pp_noisy_reset, pp_pack_qnetrnn_tc) instead of ~100 framework kernels and a host round trip."""
+        if not hasattr(self, "_noise_layers"):
+            m = self.model
+            self._noise_layers = (_lib.PPNoisyLayer * 3)(*[self._noisy(mod, False) for mod in (m.fc_shared_head[0], m.fc_V, m.fc_A)])
+            self._noise_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        st = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pp_noisy_reset(self._noise_layers, 3, int(seed) & (2 ** 64 - 1), _ptr(self._noise_counter), st),
+                       "pp_noisy_reset")
+            _lib.check(self._lib.pp_pack_qnetrnn_tc(C.byref(self._on), 1, _ptr(image), st), "pp_pack_qnetrnn_tc")
+
     def grads_on_rows(self, ring: ReplayRing, rows: torch.Tensor):
         """train_step_rnn up to loss.backward() for given windows (ring slots int64 [batch, trace], time ascending): the
         gradients land in the .grad tensors.  Returns the loss (0-d device tensor)."""
@@ -285,9 +298,12 @@ def train_rnn_generation(engine: SelfPlayEngine, trainer: DRQNTrainer, ring: Rep
         engine.pb = Policy.qnetrnn(trainer.model, num_envs=env.n, noisy=True, eps=epsilon, precision=precision, device=dev)
     while done_steps < lockstep_steps:
         k = min(chunk, lockstep_steps - done_steps)
-        trainer.model.reset_noise()                                                      # B's noise: one draw per chunk
-        blob = pack(trainer.model, noisy=True).to(dev)
-        engine.pb.weights.copy_(blob, non_blocking=True)
+        if trainer.fused and precision == "f16":                                         # B's noise: one draw per chunk
+            trainer.reset_noise_and_pack_tc(engine.pb.weights)
+        else:
+            trainer.model.reset_noise()
+            blob = pack(trainer.model, noisy=True).to(dev)
+            engine.pb.weights.copy_(blob, non_blocking=True)
         engine.pb.eps = epsilon
         engine.run(k, ring=ring)
         done_steps += k

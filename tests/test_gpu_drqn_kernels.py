@@ -131,3 +131,22 @@ def test_drqn_fused_update_tracks_the_autograd_update_in_a_generation():
     assert a._graph is not None and a.train_steps == 8 and all(np.isfinite(l) and l > 0 for l in losses)
     assert len(set(losses)) == 5                                    # every replay draws fresh windows
     assert not torch.equal(before["lstm.weight_hh_l0"], a.model.state_dict()["lstm.weight_hh_l0"])
+
+
+@pytest.mark.parametrize("noisy", [False, True])
+def test_device_pack_of_the_tensor_core_weight_image_equals_the_host_pack(noisy):
+    """pp_pack_qnetrnn_tc (one launch) == policy.pack_qnetrnn_tc (the torch formulation), byte for byte, for a random-init
+    net and the reference's trained checkpoint."""
+    import ctypes as C
+    from pingpong_selfplay_ai_b200 import _lib
+    from pingpong_selfplay_ai_b200.policy import pack_qnetrnn_tc
+    from pingpong_selfplay_ai_b200.selfplay import _ptr, _stream_ptr
+    for which in ("seed", "ckpt"):
+        net = _net(which).cuda()
+        want = pack_qnetrnn_tc(net, noisy=noisy).cpu().numpy()
+        st = DRQNTrainer._net_struct(net)
+        img = torch.zeros(_lib.RNNTC_BLOB_BYTES, dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.load().pp_pack_qnetrnn_tc(C.byref(st), int(noisy), _ptr(img), _stream_ptr(torch.device("cuda", 0))))
+        got = img.cpu().numpy()
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, (which, bad[:8], bad.size)

@@ -43,7 +43,8 @@ for _ in range(2):
     pack(); eng.run(k, ring=ring); sampler.refresh()
     for _ in range(4):
         trainer.update(sampler)
-phase("reset_noise + pack_qnetrnn_tc", pack)
+phase("reset_noise + pack_qnetrnn_tc (host)", pack)
+phase("reset_noise + pack (device kernels)", lambda: trainer.reset_noise_and_pack_tc(eng.pb.weights))
 phase(f"rollout {k} steps x {n} envs + ring", lambda: eng.run(k, ring=ring))
 phase("sampler.refresh", sampler.refresh)
 phase("trainer.update (graph replay)", lambda: trainer.update(sampler), reps=20)
