@@ -332,7 +332,8 @@ int pp_pack_qnet(const float *features0_weight, const float *features0_bias, con
  * accumulated) to the grad_* pointers of online_v / online_a; the feature layers (features.0 [64][7], features.2
  * [64][64], torch layout) are frozen (:97) and shared by the online and the target net.  idx[batch] are ring slots,
  * iw[batch] the importance weights.  td_out[batch], loss_out[1] and prios (the PER priority array indexed by ring
- * slot, receives |td| + 1e-6, :74-76,163-164) may be NULL.  noisy_online / noisy_target select the train- or
+ * slot, receives |td| + 1e-6, :74-76,163-164) may be NULL; *max_prio (may be NULL) is raised to the largest priority written
+ * (a running maximum: what new rows get at :57,62 without an O(capacity) pass per push).  noisy_online / noisy_target select the train- or
  * eval-mode forward of each net (the reference: online train mode, target eval mode :100).  batch <= 4096.
  * `workspace`: pp_dqn_workspace_floats(batch) floats of device memory, ZERO before the first launch that uses it (the
  * kernel leaves it ready for the next one): per-tile partial sums + the ticket of the CTA that finishes last. */
@@ -340,7 +341,7 @@ int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float 
                       const float *features0_weight, const float *features0_bias, const float *features2_weight,
                       const float *features2_bias, const PPNoisyLayer *online_v, const PPNoisyLayer *online_a,
                       const PPNoisyLayer *target_v, const PPNoisyLayer *target_a, int32_t noisy_online,
-                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios,
+                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios, float *max_prio,
                       float *workspace, void *stream);
 int64_t pp_dqn_workspace_floats(int32_t batch);
 

@@ -141,3 +141,73 @@ def drqn_loss(model, target, obs, act, rew, next_obs, done, gamma):
         nq = q_next_target.gather(1, best).squeeze(1)
         targets = rew[:, -1] + gamma * nq * (~done[:, -1])
     return F.smooth_l1_loss(q, targets)
+
+
+# ------------------------------------------------------------------------------------------ PyTorch formulations of the updates
+# The product trainers (pingpong_selfplay_ai_b200.train / .train_rnn) run hand-written CUDA kernels only.  These
+# subclasses keep their host logic (batch gating, target sync, CUDA-graph capture, gradient all-reduce) and replace the
+# kernels by plain PyTorch / autograd, on any device: the second opinion the kernels are tested against, and what the
+# CPU tests compare with the line-by-line restatements above.
+def per_sample_torch(sampler, batch_size: int, beta, generator=None):
+    """PrioritizedReplay.sample (:64-73) with torch ops on the sampler's device -> (idx int64[bs], weights f32[bs])."""
+    if sampler.seen == 0:
+        raise RuntimeError("sampling from an empty replay ring")
+    pa = sampler.prios.pow(sampler.alpha)
+    cdf = pa.cumsum(0)                                   # np.random.choice(p=probs) is inverse-CDF sampling
+    total = cdf[-1]
+    u = torch.rand(batch_size, device=pa.device, generator=generator) * total
+    idx = torch.searchsorted(cdf, u, right=True).clamp_(max=sampler.ring.capacity - 1)
+    w = (sampler.size_t * (pa[idx] / total)).pow(-beta)
+    return idx, w / w.max()
+
+
+def _torch_trainers():
+    from pingpong_selfplay_ai_b200.train import DQNTrainer
+    from pingpong_selfplay_ai_b200.train_rnn import DRQNTrainer
+
+    class TorchDQNTrainer(DQNTrainer):
+        FUSED = False
+
+        def _check_device(self, device):
+            return torch.device(device)
+
+        def _pre(self, sampler, beta, generator=None):
+            ring = sampler.ring
+            idx, iw = (sampler.sample(self.batch_size, beta, generator) if "sample" in vars(sampler)
+                       else per_sample_torch(sampler, self.batch_size, beta, generator))
+            self.model.reset_noise()                                                       # :142-143
+            self.target.reset_noise()
+            loss, td = dqn_loss(self.model, self.target, ring.obs[idx], ring.act[idx].to(torch.int64), ring.rew[idx],
+                                ring.next_obs[idx], ring.done[idx] != 0, iw, self.gamma)
+            self.opt.zero_grad(set_to_none=False)
+            loss.backward()
+            self._idx, self._td = idx, td.detach()
+            return loss.detach()
+
+        def _post(self, sampler):
+            self.opt.step()
+            sampler.update_priorities(self._idx, self._td)                                 # :163-164
+
+    class TorchDRQNTrainer(DRQNTrainer):
+        FUSED = False
+
+        def _check_device(self, device):
+            return torch.device(device)
+
+        def loss_on(self, obs, act, rew, next_obs, done):
+            return drqn_loss(self.model, self.target, obs, act, rew, next_obs, done, self.gamma)
+
+        def _pre(self, sampler, beta=None, generator=None):
+            loss = self.loss_on(*sampler.sample(self.batch_size, generator))
+            self.opt.zero_grad(set_to_none=False)
+            loss.backward()
+            return loss.detach()
+
+        def _post(self, sampler):
+            torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip_norm)      # :516
+            self.opt.step()
+
+    return TorchDQNTrainer, TorchDRQNTrainer
+
+
+TorchDQNTrainer, TorchDRQNTrainer = _torch_trainers()

@@ -103,7 +103,7 @@ _PROTOTYPES = {
     "pp_noisy_reset": (C.c_int, [P(PPNoisyLayer), c_i32, c_u64, c_vp, c_vp]),
     "pp_pack_qnet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_vp, c_vp]),
     "pp_dqn_head_grads": (C.c_int, [P(PPReplayRing), c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, P(PPNoisyLayer), P(PPNoisyLayer),
-                                    P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                    P(PPNoisyLayer), P(PPNoisyLayer), c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pp_dqn_workspace_floats": (c_i64, [c_i32]),
     "pp_per_sample": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_u64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "pp_per_sample_scratch_floats": (c_i64, [c_i64]),

@@ -241,8 +241,8 @@ int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float 
                       const float *features0_weight, const float *features0_bias, const float *features2_weight,
                       const float *features2_bias, const PPNoisyLayer *online_v, const PPNoisyLayer *online_a,
                       const PPNoisyLayer *target_v, const PPNoisyLayer *target_a, int32_t noisy_online,
-                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios, float *workspace,
-                      void *stream) {
+                      int32_t noisy_target, float gamma, float *td_out, float *loss_out, float *prios, float *max_prio,
+                      float *workspace, void *stream) {
     const char *fn = "pp_dqn_head_grads";
     if (batch <= 0 || batch > 4096) return fail(PP_E_SIZE, fn);
     if (!workspace) return fail(PP_E_NULL, fn);
@@ -252,7 +252,7 @@ int pp_dqn_head_grads(const PPReplayRing *ring, const int64_t *idx, const float 
         return fail(PP_E_PARAM, fn);
     return ok_or(pp::dqn_head_grads_launch(*ring, idx, iw, batch, features0_weight, features0_bias, features2_weight,
                                            features2_bias, *online_v, *online_a, *target_v, *target_a,
-                                           noisy_online, noisy_target, gamma, td_out, loss_out, prios, workspace, (cudaStream_t)stream), fn);
+                                           noisy_online, noisy_target, gamma, td_out, loss_out, prios, max_prio, workspace, (cudaStream_t)stream), fn);
 }
 
 int64_t pp_dqn_workspace_floats(int32_t batch) { return batch > 0 ? pp::dqn_workspace_floats(batch) : 0; }

@@ -110,7 +110,8 @@ dqn_head_grads_kernel(const PPReplayRing ring, const int64_t *__restrict__ idx, 
                       const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
                       const float *__restrict__ b2, const PPNoisyLayer on_v, const PPNoisyLayer on_a,
                       const PPNoisyLayer tg_v, const PPNoisyLayer tg_a, int noisy_online, int noisy_target, float gamma,
-                      float *__restrict__ td_out, float *__restrict__ loss_out, float *__restrict__ prios, float *ws) {
+                      float *__restrict__ td_out, float *__restrict__ loss_out, float *__restrict__ prios,
+                      float *__restrict__ max_prio, float *ws) {
     extern __shared__ __align__(16) float smem[];
     float *sw = smem;                                                          // feature weights
     float4 *head_on = reinterpret_cast<float4 *>(smem + D_FEAT_FLOATS);        // [65]
@@ -231,7 +232,13 @@ dqn_head_grads_kernel(const PPReplayRing ring, const int64_t *__restrict__ idx, 
             const long long slot = slots[rr];
             bool last = true;
             for (int q = rr + 1; q < batch; ++q) last = last && slots[q] != slot;
-            if (last) prios[slot] = fabsf(__ldcg(ws_td + rr)) + 1e-6f;
+            if (last) {
+                const float pnew = fabsf(__ldcg(ws_td + rr)) + 1e-6f;
+                prios[slot] = pnew;
+                // running maximum of every priority ever assigned (positive floats order like their bit patterns): what
+                // new rows get (:57,62) without a pass over the whole priority array per push
+                if (max_prio) atomicMax(reinterpret_cast<int *>(max_prio), __float_as_int(pnew));
+            }
         }
     }
     if (tid == 0) *ticket = 0u;                                                // ready for the next launch
@@ -509,8 +516,8 @@ int64_t dqn_workspace_floats(int32_t batch) { return (int64_t)((batch + D_ROWS -
 int dqn_head_grads_launch(const PPReplayRing &ring, const int64_t *idx, const float *iw, int32_t batch,
                           const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &on_v,
                           const PPNoisyLayer &on_a, const PPNoisyLayer &tg_v, const PPNoisyLayer &tg_a, int noisy_online,
-                          int noisy_target, float gamma, float *td_out, float *loss_out, float *prios, float *workspace,
-                          cudaStream_t stream) {
+                          int noisy_target, float gamma, float *td_out, float *loss_out, float *prios, float *max_prio,
+                          float *workspace, cudaStream_t stream) {
     static bool attr_set = false;                      // set once, before any stream capture replays the launch
     if (!attr_set) {
         cudaError_t err = cudaFuncSetAttribute(dqn_head_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM);
@@ -520,7 +527,7 @@ int dqn_head_grads_launch(const PPReplayRing &ring, const int64_t *idx, const fl
     const unsigned tiles = (unsigned)((batch + D_ROWS - 1) / D_ROWS);
     dqn_head_grads_kernel<<<tiles, D_THREADS, D_SMEM, stream>>>(ring, idx, iw, batch, w1, b1, w2, b2, on_v, on_a, tg_v, tg_a,
                                                                 noisy_online, noisy_target, gamma, td_out, loss_out, prios,
-                                                                workspace);
+                                                                max_prio, workspace);
     return (int)cudaGetLastError();
 }
 

@@ -47,7 +47,7 @@ int replay_scatter_launch(int64_t n, const PPReplayRing &ring, const float *obs,
 int dqn_head_grads_launch(const PPReplayRing &ring, const int64_t *idx, const float *iw, int32_t batch,
                           const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &on_v, const PPNoisyLayer &on_a,
                           const PPNoisyLayer &tg_v, const PPNoisyLayer &tg_a, int noisy_online, int noisy_target, float gamma,
-                          float *td_out, float *loss_out, float *prios, float *workspace, cudaStream_t stream);
+                          float *td_out, float *loss_out, float *prios, float *max_prio, float *workspace, cudaStream_t stream);
 int64_t dqn_workspace_floats(int32_t batch);
 int64_t per_chunk(int64_t capacity);
 int per_sample_launch(const float *prios, int64_t capacity, float alpha, const float *beta, const float *size, uint64_t seed,

@@ -7,8 +7,11 @@ update of scripts/train_iterative.py, with gradients averaged over env slabs (ra
     train_step  :132-168                                   DQNTrainer.update
     rollout + train loop  :233-261                         train_generation
 
-The rollout (env step + both players' actions + replay rows) runs in libpong_b200.so; what is here is PyTorch
-on the device for the 520 trainable head parameters, plus the NCCL all-reduce of their gradients.
+The rollout (env step + both players' actions + replay rows) runs in libpong_b200.so, and so does the update
+(csrc/dqn_kernels.cu: prioritised sampling, NoisyNet noise, forward + TD error + head gradients + new priorities, Adam);
+what is here sequences those launches, captures them in a CUDA graph and all-reduces the gradients over ranks (NCCL).
+There is no CPU path: the trainers refuse non-CUDA devices.  The PyTorch / autograd formulation of the same update,
+which the kernels are tested against, lives with the test infrastructure (oracle/train_port.py: TorchDQNTrainer).
 
 How the reference's sequential schedule maps to n lock-step envs ("training semantics do not batch 1:1"):
   * the reference does one gradient step per env step; here `updates_per_chunk` gradient steps follow every chunk
@@ -30,19 +33,25 @@ import ctypes as C
 
 from . import _lib
 from . import dist as ppd
+from .env import _require_cuda
 from .policy import NoisyLinear, Policy, QNet, pack_qnet
 from .selfplay import ReplayRing, SelfPlayEngine, _ptr, _stream_ptr
 
 
 class PrioritizedSampler:
-    """Proportional prioritised replay over a ReplayRing (alpha 0.6; new rows get the current maximum priority;
-    priorities become |TD| + 1e-6 after a sample is trained on) — scripts/train_iterative.py:49-76 on the device."""
+    """Proportional prioritised replay over a ReplayRing (alpha 0.6; new rows get the maximum priority; priorities become
+    |TD| + 1e-6 after a sample is trained on) — scripts/train_iterative.py:49-76 on the device.
+    `max_prio` is a RUNNING maximum kept on the device (raised by pp_dqn_head_grads whenever it writes a larger
+    priority, never lowered): the reference recomputes `prios.max()` over the whole buffer at every push (:57, O(capacity)
+    per transition); the running maximum is an upper bound of it that costs nothing per push."""
 
     def __init__(self, ring: ReplayRing, alpha: float = 0.6):
         self.ring, self.alpha = ring, float(alpha)
-        self.prios = torch.zeros(ring.capacity, dtype=torch.float32, device=ring.obs.device)
+        dev = ring.obs.device
+        self.prios = torch.zeros(ring.capacity, dtype=torch.float32, device=dev)
+        self.max_prio = torch.ones(1, dtype=torch.float32, device=dev)         # 1.0 while nothing has been trained on (:57)
         self.seen = 0                                   # ring.head at the last note_new_rows()
-        self.size_t = torch.zeros((), dtype=torch.float32, device=ring.obs.device)     # len(self) on the device
+        self.size_t = torch.zeros((), dtype=torch.float32, device=dev)         # len(self) on the device
 
     def __len__(self):
         return min(self.seen, self.ring.capacity)
@@ -56,46 +65,27 @@ class PrioritizedSampler:
         if new <= 0:
             return 0
         cap = self.ring.capacity
-        if self.seen > 0:                                # stays on the device: no host round trip
-            max_p = self.prios.max()
-            max_p = torch.where(max_p > 0, max_p, torch.ones_like(max_p))
-        else:
-            max_p = torch.ones((), dtype=torch.float32, device=self.prios.device)
         if new >= cap:
-            self.prios.copy_(max_p.expand_as(self.prios))
+            self.prios.copy_(self.max_prio.expand_as(self.prios))
         else:
             lo, hi = self.seen % cap, head % cap
             if lo < hi:
-                self.prios[lo:hi] = max_p
+                self.prios[lo:hi] = self.max_prio
             else:
-                self.prios[lo:] = max_p
-                self.prios[:hi] = max_p
+                self.prios[lo:] = self.max_prio
+                self.prios[:hi] = self.max_prio
         self.seen = head
         self.size_t.fill_(float(len(self)))
         return new
 
-    def sample(self, batch_size: int, beta, generator=None):
-        """-> (idx int64[bs], importance weights f32[bs]) — :64-73.  Shapes and control flow do not depend on how full
-        the ring is (unfilled slots have priority 0, hence probability 0; `beta` may be a 0-d device tensor), so the
-        whole update can be captured in a CUDA graph."""
+    def sample(self, batch_size: int, beta, seed: int = 0):
+        """-> (idx int64[bs], importance weights f32[bs]) — :64-73: `np.random.choice(p = prios^alpha / sum)` as a two-level
+        inverse-CDF draw in three hand-written launches (pp_per_sample: chunk sums, one warp per sample, normalisation),
+        deterministic for a given seed and call count.  Unfilled slots have priority 0, hence probability 0.  `beta`: float
+        or 0-d device tensor.  Returns static buffers (valid until the next call): what a CUDA graph wants."""
         if self.seen == 0:
             raise RuntimeError("sampling from an empty replay ring")
-        pa = self.prios.pow(self.alpha)                  # probs = pa / pa.sum() (:66-67), never materialised: two passes
-        # np.random.choice(p=probs) is inverse-CDF sampling; the same here (torch.multinomial costs 1 ms at 2 M rows)
-        cdf = pa.cumsum(0)                               # over the ring instead of four
-        total = cdf[-1]
-        u = torch.rand(batch_size, device=pa.device, generator=generator) * total
-        idx = torch.searchsorted(cdf, u, right=True).clamp_(max=self.ring.capacity - 1)
-        w = (self.size_t * (pa[idx] / total)).pow(-beta)
-        return idx, w / w.max()
-
-    def sample_fused(self, batch_size: int, beta, seed: int = 0):
-        """The same draw in three hand-written launches (pp_per_sample: chunk sums, warp-per-sample two-level inverse CDF,
-        normalisation) instead of ~14 framework kernels; deterministic for a given seed and call count.  `beta`: float or
-        0-d device tensor.  Returns static buffers (valid until the next call): what a CUDA graph wants."""
-        if self.seen == 0:
-            raise RuntimeError("sampling from an empty replay ring")
-        dev = self.prios.device
+        dev = _require_cuda(self.prios.device)
         if getattr(self, "_f_batch", None) != batch_size:
             self._f_lib = _lib.load()
             self._f_batch = batch_size
@@ -115,8 +105,13 @@ class PrioritizedSampler:
                                                  _ptr(self._f_idx), _ptr(self._f_w), _stream_ptr(dev)), "pp_per_sample")
         return self._f_idx, self._f_w
 
+    sample_fused = sample
+
     def update_priorities(self, idx, td_abs):
-        self.prios[idx] = td_abs.detach().abs().to(torch.float32) + 1e-6           # :74-76
+        """:74-76 for callers that computed TD errors themselves (the fused update writes priorities in its own kernel)."""
+        p = td_abs.detach().abs().to(torch.float32) + 1e-6
+        self.prios[idx] = p
+        self.max_prio.copy_(torch.maximum(self.max_prio, p.max().reshape(1)))
 
 
 class DQNTrainer:
@@ -125,10 +120,13 @@ class DQNTrainer:
     def __init__(self, model_b: QNet, gamma: float = 0.99, lr: float = 2.5e-4, batch_size: int = 256,
                  target_update_interval: int = 1000, beta_start: float = 0.4, beta_frames: int = 100000, device="cuda",
                  use_graph: bool = True, fused: bool | None = None, seed: int = 0):
-        """fused (default: on CUDA): forward, TD error, loss and head gradients run in ONE hand-written kernel
-        (pp_dqn_head_grads), NoisyNet noise in another (pp_noisy_reset); the PyTorch formulation below is what they
-        are tested against and what runs on the CPU."""
-        self.device = torch.device(device)
+        """Forward, TD error, loss and head gradients run in ONE hand-written kernel (pp_dqn_head_grads), NoisyNet noise
+        in another (pp_noisy_reset), sampling and Adam likewise.  `fused` exists for call-site compatibility: False is
+        refused here (the PyTorch formulation is oracle/train_port.TorchDQNTrainer, test infrastructure)."""
+        if fused is False and self.FUSED:
+            raise ValueError("the product trainer runs the hand-written update only; the PyTorch formulation it is tested "
+                             "against is oracle/train_port.TorchDQNTrainer")
+        self.device = self._check_device(device)
         self.model = model_b.to(self.device)
         ppd.broadcast_module_(self.model)                # several ranks: every replica starts from rank 0's weights
         for p in self.model.features.parameters():                                   # :97
@@ -137,7 +135,7 @@ class DQNTrainer:
         self.target.eval()                                                             # :100
         self.head_params = list(self.model.fc_V.parameters()) + list(self.model.fc_A.parameters())
         self.use_graph = use_graph
-        self.fused = (self.device.type == "cuda") if fused is None else bool(fused)
+        self.fused = self.FUSED
         capturable = (use_graph or self.fused) and self.device.type == "cuda"          # device-side step counters
         self.opt = torch.optim.Adam(self.head_params, lr=lr, capturable=capturable)    # :101-104
         self._graph, self._eager_runs = None, 0
@@ -146,6 +144,11 @@ class DQNTrainer:
         self.frame_idx = self.train_steps = 0
         if self.fused:
             self._init_fused(seed)
+
+    FUSED = True                                         # oracle/train_port.TorchDQNTrainer overrides (test infrastructure)
+
+    def _check_device(self, device) -> torch.device:
+        return _require_cuda(device)                     # no CPU path: raises without a CUDA device
 
     # ---- the hand-written update path (csrc/dqn_kernels.cu)
     @staticmethod
@@ -199,12 +202,15 @@ class DQNTrainer:
             _lib.check(self._lib.pp_pack_qnet(*self._feature_ptrs(), C.byref(self._on_v), C.byref(self._on_a), 1,
                                               _ptr(blob), st), "pp_pack_qnet")
 
-    def _pre_fused(self, sampler: "PrioritizedSampler", beta, generator=None):
-        if generator is None and hasattr(sampler, "sample_fused") and "sample" not in vars(sampler):
-            idx, iw = sampler.sample_fused(self.batch_size, beta, self._noise_seed)
-        else:                                            # an explicit torch generator (or a patched sampler): framework path
+    def _pre(self, sampler: "PrioritizedSampler", beta, generator=None):
+        """train_step() up to loss.backward(): local gradients are in p.grad afterwards.  `beta` is a float or a 0-d
+        device tensor.  No host synchronisation.  (A `sample` attribute set on the sampler INSTANCE overrides the draw:
+        the tests inject fixed batches that way.)"""
+        if "sample" in vars(sampler):
             idx, iw = sampler.sample(self.batch_size, beta, generator)
             idx, iw = idx.contiguous(), iw.to(torch.float32).contiguous()
+        else:
+            idx, iw = sampler.sample(self.batch_size, beta, self._noise_seed)
         ring = sampler.ring.struct()
         st = _stream_ptr(self.device)
         with torch.cuda.device(self.device):
@@ -212,42 +218,16 @@ class DQNTrainer:
             _lib.check(self._lib.pp_dqn_head_grads(C.byref(ring), _ptr(idx), _ptr(iw), self.batch_size, *self._feature_ptrs(),
                                                    C.byref(self._on_v), C.byref(self._on_a), C.byref(self._tg_v), C.byref(self._tg_a),
                                                    int(self.model.training), int(self.target.training), float(self.gamma),
-                                                   _ptr(self._td_buf), _ptr(self._loss_buf), _ptr(sampler.prios), _ptr(self._workspace), st),
+                                                   _ptr(self._td_buf), _ptr(self._loss_buf), _ptr(sampler.prios), _ptr(sampler.max_prio),
+                                                   _ptr(self._workspace), st),
                        "pp_dqn_head_grads")
         self._idx, self._td = idx, self._td_buf
         return self._loss_buf[0]
 
-    def _pre(self, sampler: PrioritizedSampler, beta, generator=None):
-        """train_step() up to loss.backward(): local gradients are in p.grad afterwards.  `beta` is a float or a 0-d
-        device tensor.  No host synchronisation."""
-        if self.fused:
-            return self._pre_fused(sampler, beta, generator)
-        ring = sampler.ring
-        idx, iw = sampler.sample(self.batch_size, beta, generator)
-        self.model.reset_noise()                                                       # :142-143
-        self.target.reset_noise()
-        s, ns = ring.obs[idx], ring.next_obs[idx]
-        a = ring.act[idx].to(torch.int64)
-        r, d = ring.rew[idx], ring.done[idx] != 0
-        q = self.model(s).gather(1, a.unsqueeze(1)).squeeze(1)                         # :152
-        with torch.no_grad():
-            na = self.model(ns).argmax(1, keepdim=True)                                # :154
-            nq = self.target(ns).gather(1, na).squeeze(1)                              # :155
-        targets = r + self.gamma * nq * (~d)                                           # :156
-        td = q - targets
-        loss = (iw * td.pow(2)).mean()                                                 # :158
-        self.opt.zero_grad(set_to_none=False)
-        loss.backward()
-        self._idx, self._td = idx, td.detach()
-        return loss.detach()
-
     def _post(self, sampler: PrioritizedSampler):
-        """The rest of train_step(): optimiser step on the (rank-averaged) gradients, new priorities."""
-        if self.fused:                                   # one launch; the priorities were written by pp_dqn_head_grads
-            self._adam_step()
-        else:
-            self.opt.step()
-            sampler.update_priorities(self._idx, self._td)                             # :163-164
+        """The rest of train_step(): optimiser step on the (rank-averaged) gradients (one launch; the new priorities were
+        written by pp_dqn_head_grads)."""
+        self._adam_step()
 
     def _body(self, sampler, beta, generator=None):
         loss = self._pre(sampler, beta, generator)
@@ -285,9 +265,12 @@ class DQNTrainer:
         return loss
 
     def _graphed(self, sampler, beta: float):
-        """Replay of the captured update.  One graph on a single GPU.  With several ranks the gradient all-reduce stays
-        OUT of the graphs (NCCL's watchdog thread and stream capture do not mix): graph 1 = sample + forward + backward,
-        eager NCCL all-reduce of the static gradient tensors, graph 2 = optimiser step + priorities."""
+        """Replay of the captured update: ONE CUDA graph — sampling, forward / backward, the NCCL all-reduce of the flat
+        gradient buffer (several ranks) and the optimiser step.  The collective is captured like any other node: the
+        communicator exists by then (the first three updates run eagerly and ARE its warm-up) and the capture uses
+        capture_error_mode="thread_local", so that the CUDA calls of NCCL's watchdog thread do not invalidate it.
+        PP_SPLIT_UPDATE_GRAPH=1 selects the older form (two graphs around an eager all-reduce: a host round trip per
+        update, which cost 8 GPUs half their update rate)."""
         if self._graph is None:
             if self._eager_runs < 3:                      # the first updates run eagerly: they ARE the warm-up
                 self._eager_runs += 1
@@ -295,15 +278,15 @@ class DQNTrainer:
             self._beta_t = torch.zeros((), dtype=torch.float32, device=self.device)
             self._beta_t.fill_(beta)
             self._graph_sampler = sampler
-            self._split = ppd.is_parallel() or os.environ.get("PP_SPLIT_UPDATE_GRAPH") == "1"      # the env var: tests
+            self._split = os.environ.get("PP_SPLIT_UPDATE_GRAPH") == "1"
             torch.cuda.synchronize(self.device)
             pool = torch.cuda.graph_pool_handle()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, pool=pool):
+            with torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local"):
                 self._loss_t = self._pre(sampler, self._beta_t) if self._split else self._body(sampler, self._beta_t)
             if self._split:
                 self._graph_post = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph_post, pool=pool):
+                with torch.cuda.graph(self._graph_post, pool=pool, capture_error_mode="thread_local"):
                     self._post(sampler)
             self._graph = graph                           # capture records without running: replay below IS this update
         if sampler is not self._graph_sampler:
@@ -337,11 +320,7 @@ def train_generation(engine: SelfPlayEngine, trainer: DQNTrainer, ring: ReplayRi
     all_ready = False                                    # once every rank's ring holds a batch it stays that way
     while done_steps < lockstep_steps:
         k = min(chunk, lockstep_steps - done_steps)
-        if trainer.fused:                                                              # B's noise: one draw per chunk
-            trainer.reset_noise_and_pack(engine.pb.weights)
-        else:
-            trainer.model.reset_noise()
-            engine.pb.set_weights(pack_qnet(trainer.model, noisy=True))
+        trainer.reset_noise_and_pack(engine.pb.weights)                                # B's noise: one draw per chunk
         engine.pb.eps = epsilon
         engine.run(k, ring=ring)
         done_steps += k

@@ -12,8 +12,9 @@ The rollout (env + both players + replay rows, QNetRNN on the tensor cores or CU
 does the update: pp_drqn_grads (csrc/drqn_kernels.cu) is the forward of the three streams, the last-step Double-DQN
 Huber loss and the whole backward pass — heads, BPTT through the LSTM on thread-block clusters, feature layers — in
 ~15 hand-written launches; pp_clip_grad_norm and pp_adam_step_multi finish train_step_rnn.  All of it is captured in a
-CUDA graph; gradients are averaged over env slabs with one NCCL all-reduce of the flat gradient buffer.  The PyTorch
-formulation (`loss_on`, autograd through nn.LSTM) is kept as `fused=False`: it is what the kernels are tested against.
+CUDA graph; gradients are averaged over env slabs with one NCCL all-reduce of the flat gradient buffer.  There is no CPU
+path; the PyTorch formulation (autograd through nn.LSTM) the kernels are tested against is
+oracle/train_port.TorchDRQNTrainer (test infrastructure).
 
 Sequence replay on a lock-step ring.  The kernel writes the row of env i at lock-step step t to slot
 (t % T) * n + i (T = capacity / n), so each env's transitions are in time order and an episode is a run of rows that
@@ -35,13 +36,12 @@ from __future__ import annotations
 import copy
 
 import torch
-import torch.nn.functional as F
 
 import ctypes as C
 
 from . import _lib
 from . import dist as ppd
-from .policy import Policy, QNetRNN, pack_qnetrnn, pack_qnetrnn_tc
+from .policy import Policy, QNetRNN, pack_qnetrnn
 from .selfplay import ReplayRing, SelfPlayEngine, _ptr, _stream_ptr
 from .train import DQNTrainer
 
@@ -122,12 +122,18 @@ class SequenceSampler:
 class DRQNTrainer(DQNTrainer):
     """Last-step Double-DQN on QNetRNN, all parameters trained — scripts/train_rnn_iterative.py:335-338,400-531."""
 
+    FUSED = True                                         # oracle/train_port.TorchDRQNTrainer overrides (test infrastructure)
+
     def __init__(self, model_b: QNetRNN, gamma: float = 0.99, lr: float = 1e-4, batch_size: int = 64,
                  target_update_interval: int = 2000, grad_clip_norm: float = 1.0, min_episodes_factor: int = 1,
                  device="cuda", use_graph: bool = True, fused: bool | None = None):
-        """fused (default: on CUDA): forward, loss and backward in the hand-written kernels of csrc/drqn_kernels.cu,
-        gradient clipping and Adam in two more; fused=False is the PyTorch / autograd formulation they are tested against."""
-        self.device = torch.device(device)
+        """Forward, loss and backward run in the hand-written kernels of csrc/drqn_kernels.cu, gradient clipping and Adam in
+        two more.  `fused` exists for call-site compatibility: False is refused here (the PyTorch / autograd formulation is
+        oracle/train_port.TorchDRQNTrainer, test infrastructure)."""
+        if fused is False and self.FUSED:
+            raise ValueError("the product trainer runs the hand-written update only; the PyTorch formulation it is tested "
+                             "against is oracle/train_port.TorchDRQNTrainer")
+        self.device = self._check_device(device)
         self.model = model_b.to(self.device)
         ppd.broadcast_module_(self.model)                # several ranks: every replica starts from rank 0's weights
         self.model.train()                                                               # :729
@@ -139,7 +145,7 @@ class DRQNTrainer(DQNTrainer):
         self.head_params = self.params                     # what DQNTrainer's helpers call the trainable set
         self.use_graph = use_graph
         on_cuda = self.device.type == "cuda"
-        want_fused = on_cuda if fused is None else bool(fused)
+        want_fused = self.FUSED
         # torch's own fused multi-tensor Adam serves the fused=False formulation (the capturable foreach form is ~100 kernels)
         self.opt = torch.optim.Adam(self.params, lr=lr, capturable=(use_graph or want_fused) and on_cuda,
                                     fused=True if on_cuda else None)                     # :335
@@ -230,33 +236,11 @@ class DRQNTrainer(DQNTrainer):
             _lib.check(self._lib.pp_adam_step_multi(self._adam, len(self.params), float(g["lr"]), float(g["betas"][0]),
                                                     float(g["betas"][1]), float(g["eps"]), st), "pp_adam_step_multi")
 
-    def loss_on(self, obs, act, rew, next_obs, done):
-        """The loss of train_step_rnn for given windows (:468-507)."""
-        b = obs.shape[0]
-        h0 = self.model.init_hidden(b, obs.device)
-        q_last, _ = self.model(obs, h0)                                                  # :470
-        q = q_last.gather(1, act[:, -1].unsqueeze(1)).squeeze(1)                         # :475-478
-        with torch.no_grad():
-            q_next_online, _ = self.model(next_obs, self.model.init_hidden(b, obs.device))    # :489
-            best = q_next_online.argmax(dim=1, keepdim=True)                             # :490
-            q_next_target, _ = self.target(next_obs, self.target.init_hidden(b, obs.device))  # :494
-            nq = q_next_target.gather(1, best).squeeze(1)                                # :497
-            targets = rew[:, -1] + self.gamma * nq * (~done[:, -1])                      # :505
-        return F.smooth_l1_loss(q, targets)                                              # :509
-
     def _pre(self, sampler: SequenceSampler, beta=None, generator=None):
-        if self.fused:
-            return self.grads_on_rows(sampler.ring, sampler.sample_rows(self.batch_size, generator))
-        loss = self.loss_on(*sampler.sample(self.batch_size, generator))
-        self.opt.zero_grad(set_to_none=False)
-        loss.backward()
-        return loss.detach()
+        return self.grads_on_rows(sampler.ring, sampler.sample_rows(self.batch_size, generator))
 
     def _post(self, sampler: SequenceSampler):
-        if self.fused:
-            return self.clip_and_step()
-        torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip_norm)        # :516
-        self.opt.step()
+        self.clip_and_step()
 
     def _body(self, sampler, beta=None, generator=None):
         loss = self._pre(sampler, beta, generator)
@@ -292,18 +276,16 @@ def train_rnn_generation(engine: SelfPlayEngine, trainer: DRQNTrainer, ring: Rep
     env = engine.env
     env.counters.zero_()
     dev = env.device
-    pack = pack_qnetrnn_tc if precision == "f16" else pack_qnetrnn
     eps0, losses, done_steps = float(epsilon), [], 0
     if engine.pb.weights is None or engine.pb.h is None:
         engine.pb = Policy.qnetrnn(trainer.model, num_envs=env.n, noisy=True, eps=epsilon, precision=precision, device=dev)
     while done_steps < lockstep_steps:
         k = min(chunk, lockstep_steps - done_steps)
-        if trainer.fused and precision == "f16":                                         # B's noise: one draw per chunk
+        if precision == "f16":                                                           # B's noise: one draw per chunk
             trainer.reset_noise_and_pack_tc(engine.pb.weights)
-        else:
+        else:                                            # fp32 rollout kernel: the k-major blob, packed with device-side torch ops
             trainer.model.reset_noise()
-            blob = pack(trainer.model, noisy=True).to(dev)
-            engine.pb.weights.copy_(blob, non_blocking=True)
+            engine.pb.weights.copy_(pack_qnetrnn(trainer.model, noisy=True).to(dev), non_blocking=True)
         engine.pb.eps = epsilon
         engine.run(k, ring=ring)
         done_steps += k

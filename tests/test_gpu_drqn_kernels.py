@@ -11,7 +11,7 @@ import torch
 import pingpong_selfplay_ai_b200 as pp
 from pingpong_selfplay_ai_b200.train_rnn import DRQNTrainer, SequenceSampler
 from oracle.policy_torch import QNetRNNPort
-from oracle.train_port import drqn_loss
+from oracle.train_port import TorchDRQNTrainer, drqn_loss
 import pp_testutil as gu
 
 pytestmark = pytest.mark.gpu
@@ -105,7 +105,7 @@ def test_drqn_clip_and_adam_equal_torch():
 
 
 def test_drqn_fused_update_tracks_the_autograd_update_in_a_generation():
-    """Same windows, same noise: the fused trainer and the fused=False (autograd / cuDNN) trainer stay together over the
+    """Same windows, same noise: the product trainer and the autograd / cuDNN formulation (oracle TorchDRQNTrainer) stay together over the
     eager updates; then the fused update runs from its captured CUDA graph."""
     torch.manual_seed(5)
     net = pp.QNetRNN()
@@ -117,7 +117,7 @@ def test_drqn_fused_update_tracks_the_autograd_update_in_a_generation():
     sampler = SequenceSampler(ring, trace_length=8)
     assert sampler.refresh() > 64
     a = DRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=64, use_graph=True)
-    b = DRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=64, use_graph=False, fused=False)
+    b = TorchDRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=64, use_graph=False, device="cuda")
     b.model.load_state_dict(a.model.state_dict())        # the same epsilon buffers
     torch.backends.cudnn.allow_tf32 = False
     for step in range(3):                                # the eager updates: same RNG stream -> the same windows

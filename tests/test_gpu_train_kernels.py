@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 pp = gu.pp
 from pingpong_selfplay_ai_b200 import _lib  # noqa: E402
 from pingpong_selfplay_ai_b200.selfplay import _ptr, _stream_ptr  # noqa: E402
+from oracle.train_port import TorchDQNTrainer, per_sample_torch  # noqa: E402
 
 
 def _ring(cap, seed):
@@ -63,14 +64,16 @@ def test_dqn_head_grads_kernel_matches_autograd(batch, online_train_mode):
     iw = torch.rand(batch, generator=g, device="cuda") + 0.1
     td_w, loss_w, grads_w = _torch_update(tr, ring, idx, iw)
     prios = torch.zeros(ring.capacity, device="cuda")
+    max_prio = torch.full((1,), 1e-3, device="cuda")
     td = torch.zeros(batch, device="cuda"); loss = torch.zeros(1, device="cuda")
     rs = ring.struct()
     lib = _lib.load()
     _lib.check(lib.pp_dqn_head_grads(C.byref(rs), _ptr(idx), _ptr(iw), batch, *tr._feature_ptrs(), C.byref(tr._on_v),
                                      C.byref(tr._on_a), C.byref(tr._tg_v), C.byref(tr._tg_a), int(tr.model.training),
-                                     int(tr.target.training), tr.gamma, _ptr(td), _ptr(loss), _ptr(prios), _ptr(tr._workspace),
-                                     _stream_ptr(torch.device("cuda"))), "pp_dqn_head_grads")
+                                     int(tr.target.training), tr.gamma, _ptr(td), _ptr(loss), _ptr(prios), _ptr(max_prio),
+                                     _ptr(tr._workspace), _stream_ptr(torch.device("cuda"))), "pp_dqn_head_grads")
     torch.cuda.synchronize()
+    assert float(max_prio) == pytest.approx(max(1e-3, float(td_w.abs().max()) + 1e-6), rel=1e-5)     # the running maximum
     assert int(tr._workspace.view(torch.int32)[-8:].abs().sum()) == 0          # the ticket is back to zero: relaunchable
     assert torch.allclose(td, td_w, rtol=1e-5, atol=2e-6)
     assert abs(loss.item() - loss_w.item()) <= 1e-5 * abs(loss_w.item()) + 1e-7
@@ -151,11 +154,11 @@ def test_fused_and_framework_updates_train_alike():
     ring = _ring(8192, seed=3)
 
     def run(fused, noise_from=None):
-        tr = pp.DQNTrainer(pp.QNet(), batch_size=256, fused=fused, use_graph=False, lr=1e-3)
+        tr = (pp.DQNTrainer if fused else TorchDQNTrainer)(pp.QNet(), batch_size=256, use_graph=False, lr=1e-3, device="cuda")
         tr.model.load_state_dict(net.state_dict()); tr.target.load_state_dict(net.state_dict())
         sampler = pp.PrioritizedSampler(ring); sampler.note_new_rows()
         torch.manual_seed(9)
-        idx, iw = sampler.sample(256, 0.4)
+        idx, iw = per_sample_torch(sampler, 256, 0.4)
         sampler.sample = lambda *a, **k: (idx, iw)          # the same batch for both
         if noise_from is not None:                           # replay the noise the fused update drew
             for dst, src in ((tr.model, noise_from.model), (tr.target, noise_from.target)):
@@ -205,8 +208,8 @@ def test_adam_step_kernel_matches_torch_adam_on_its_own_state():
 
 
 def test_split_update_graphs_match_the_single_graph(monkeypatch):
-    """Several ranks: the update is two CUDA graphs around an eager NCCL all-reduce.  On one GPU (all-reduce = no-op) the
-    split form must train exactly like the single graph.  The batch is pinned (torch.cumsum behind the sampler is not
+    """PP_SPLIT_UPDATE_GRAPH=1: the update as two CUDA graphs around an eager all-reduce (the fallback form).  On one GPU
+    (all-reduce = no-op) it must train exactly like the single graph.  The batch is pinned (torch.cumsum behind the sampler is not
     run-to-run deterministic in floating point, so whole trajectories through the real sampler are not comparable)."""
     ring = _ring(8192, seed=3)
     outs = []

@@ -1,11 +1,14 @@
-"""Training-mode host logic on the CPU: prioritised sampling and the Double-DQN head update, checked against a
-line-by-line restatement of the reference's train_step (scripts/train_iterative.py:132-168) on the same batch."""
+"""Training-mode host logic on the CPU: prioritised-replay bookkeeping and the PyTorch formulation of the Double-DQN head
+update (oracle/train_port.TorchDQNTrainer = the product trainer's host logic with autograd in place of the CUDA kernels),
+checked against a line-by-line restatement of the reference's train_step (scripts/train_iterative.py:132-168) on the same
+batch.  The hand-written kernels are then checked against this formulation on the GPU (tests/test_gpu_train_kernels.py)."""
 import copy
 
 import pytest
 import torch
 
 import pingpong_selfplay_ai_b200 as pp
+from oracle.train_port import TorchDQNTrainer, per_sample_torch
 
 
 def _filled_ring(cap, rows, seed=0):
@@ -34,14 +37,14 @@ def test_prioritized_sampler_new_rows_wrap_and_probabilities():
     assert torch.all(s.prios[30:] == s.prios[3]) and torch.all(s.prios[:20] == s.prios[3])   # max priority (:57,62)
     assert s.prios[25] == 1.0                                                          # untouched old row
     torch.manual_seed(0)
-    s.prios.fill_(1.0); s.prios[7] = 1000.0
-    idx, w = s.sample(4000, beta=0.5)
+    s.prios.fill_(1.0); s.update_priorities(torch.tensor([7]), torch.tensor([1000.0]))
+    idx, w = per_sample_torch(s, 4000, 0.5)
     p7 = 1000.0 ** 0.6 / (99 + 1000.0 ** 0.6)
     assert abs((idx == 7).float().mean().item() - p7) < 0.03
     assert w.max() == 1.0 and w[idx == 7][0] == pytest.approx((100 * p7) ** -0.5 / (100 * (1 - p7) / 99) ** -0.5, rel=1e-4)
     ring.head.fill_(500)                                                               # more new rows than capacity
     s.note_new_rows()
-    assert torch.all(s.prios == 1000.0)
+    assert torch.all(s.prios == s.max_prio) and float(s.max_prio) == pytest.approx(1000.0)     # the running maximum (:57)
 
 
 def test_dqn_update_equals_reference_train_step_restated():
@@ -50,7 +53,7 @@ def test_dqn_update_equals_reference_train_step_restated():
     ring = _filled_ring(4096, 3000, seed=1)
     s1 = pp.PrioritizedSampler(ring); s1.note_new_rows()
     s1.prios[:3000] = torch.rand(3000) + 0.01
-    tr = pp.DQNTrainer(copy.deepcopy(net), gamma=0.99, lr=2.5e-4, batch_size=256, target_update_interval=2, device="cpu")
+    tr = TorchDQNTrainer(copy.deepcopy(net), gamma=0.99, lr=2.5e-4, batch_size=256, target_update_interval=2, device="cpu")
     ref_model, ref_target = copy.deepcopy(tr.model), copy.deepcopy(tr.target)
     ref_prios = s1.prios.clone()
     heads = list(ref_model.fc_V.parameters()) + list(ref_model.fc_A.parameters())
@@ -92,7 +95,7 @@ def test_dqn_update_equals_reference_train_step_restated():
 
 
 def test_update_waits_for_a_full_batch():
-    tr = pp.DQNTrainer(pp.QNet(), batch_size=64, device="cpu")
+    tr = TorchDQNTrainer(pp.QNet(), batch_size=64, device="cpu")
     ring = _filled_ring(128, 10)
     s = pp.PrioritizedSampler(ring); s.note_new_rows()
     assert tr.update(s) is None and tr.train_steps == 0

@@ -9,7 +9,8 @@ import torch
 import torch.nn.functional as F
 
 import pingpong_selfplay_ai_b200 as pp
-from pingpong_selfplay_ai_b200.train_rnn import DRQNTrainer, SequenceSampler
+from pingpong_selfplay_ai_b200.train_rnn import SequenceSampler
+from oracle.train_port import TorchDRQNTrainer
 
 L = 8
 
@@ -117,7 +118,7 @@ def _unrolled_last_q(net, seq):
 def test_drqn_loss_and_update_follow_train_step_rnn():
     torch.manual_seed(4)
     net = pp.QNetRNN()
-    tr = DRQNTrainer(copy.deepcopy(net), gamma=0.99, lr=1e-3, batch_size=16, target_update_interval=2, device="cpu",
+    tr = TorchDRQNTrainer(copy.deepcopy(net), gamma=0.99, lr=1e-3, batch_size=16, target_update_interval=2, device="cpu",
                      use_graph=False)
     assert sum(p.numel() for p in tr.params) == sum(p.numel() for p in net.parameters()) and all(p.requires_grad for p in tr.params)
     with torch.no_grad():                                            # make online and target differ
@@ -155,7 +156,7 @@ def test_drqn_loss_and_update_follow_train_step_rnn():
     assert all(torch.equal(p, q) for p, q in zip(tr.model.parameters(), tr.target.parameters()))
     # gradient clipping: a huge loss scale still moves each parameter by at most ~lr per step (Adam) and the stored
     # gradients have norm <= 1
-    big = DRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=16, device="cpu", use_graph=False, grad_clip_norm=1.0)
+    big = TorchDRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=16, device="cpu", use_graph=False, grad_clip_norm=1.0)
     ring.rew.mul_(1e4)
     big.update(s, generator=g)
     total = torch.sqrt(sum((p.grad ** 2).sum() for p in big.params))

@@ -17,7 +17,7 @@ rs = ring.struct()
 def grads():
     lib.pp_dqn_head_grads(C.byref(rs), _ptr(idx), _ptr(iw), 256, *tr._feature_ptrs(), C.byref(tr._on_v), C.byref(tr._on_a),
                           C.byref(tr._tg_v), C.byref(tr._tg_a), 1, 0, 0.99, _ptr(tr._td_buf), _ptr(tr._loss_buf), _ptr(sampler.prios),
-                          _ptr(tr._workspace), st)
+                          _ptr(sampler.max_prio), _ptr(tr._workspace), st)
 def noise():
     lib.pp_noisy_reset(tr._noise_all, 4, 0, _ptr(tr._noise_counter), st)
 def timed(name, fn, reps=200):
@@ -31,7 +31,7 @@ def timed(name, fn, reps=200):
 timed("pp_dqn_head_grads (batch 256)", grads)
 timed("pp_noisy_reset (4 layers)", noise)
 timed("opt.step (torch Adam, capturable)", tr.opt.step)
-timed("sampler.sample (4 M rows)", lambda: sampler.sample(256, 0.5)); timed("sampler.sample_fused", lambda: sampler.sample_fused(256, 0.5))
+timed("sampler.sample (4 M rows, 3 launches)", lambda: sampler.sample(256, 0.5))
 if hasattr(tr, "_adam_step"):
     timed("pp_adam_step", tr._adam_step)
 g = torch.cuda.CUDAGraph()
