@@ -34,11 +34,12 @@ __device__ __forceinline__ void store_rows_staged(float *__restrict__ stage, flo
 // Called by ALL lanes of a warp.  `ob` = player B's observation the action was chosen from; `serve(ep, vx, vy, spin)`
 // yields the serve of episode `ep` of this env.  `stage`: 224 floats of shared memory private to the warp (16-byte
 // aligned) for vectorised replay rows, or nullptr.
-template <typename R, typename ServeFn>
+template <typename R, bool PRECLAIM = false, typename ServeFn>
 __device__ __forceinline__ void step_and_book(const EnvConsts<R> &c, Lane<R> &L, bool active, int act_a, int act_b,
                                               const float (&ob)[7], int64_t t, int64_t n, int64_t i, int64_t env_id_base,
                                               int32_t quota, const PPRolloutOut &out, const PPReplayRing &ring, bool ring_on,
-                                              const PPServeSource &src, ServeFn &&serve, float *stage = nullptr) {
+                                              const PPServeSource &src, ServeFn &&serve, float *stage = nullptr,
+                                              int preclaimed = -1) {
     const int lane = threadIdx.x & 31;
     int flags = 0;
     if (active) {
@@ -86,8 +87,17 @@ __device__ __forceinline__ void step_and_book(const EnvConsts<R> &c, Lane<R> &L,
     const bool queue = src.kind == PP_SERVE_QUEUE;
     if (queue) log_episode(fin, m_fin, out, (int)(env_id_base + L.ep_idx % n), (int)(L.ep_idx / n), L.e.sa, L.e.sb, L.ep_len);
     else log_episode(fin, m_fin, out, (int)(env_id_base + i), L.ep_idx, L.e.sa, L.e.sb, L.ep_len);
+    // PP_SERVE_QUEUE: a finishing env takes the serve it claimed ahead of time (`preclaimed` >= 0: its serve is already
+    // drawn), the others claim now
     int claimed = 0;
-    if (queue && m_fin) claimed = claim_serves(fin, m_fin, src);               // warp-uniform branch
+    if (PRECLAIM) {
+        claimed = preclaimed;
+        const unsigned m_claim = __ballot_sync(0xffffffffu, fin && preclaimed < 0);
+        if (queue && m_claim) {                                                // warp-uniform branch
+            const int c = claim_serves(fin && preclaimed < 0, m_claim, src);
+            if (preclaimed < 0) claimed = c;
+        }
+    } else if (queue && m_fin) claimed = claim_serves(fin, m_fin, src);        // warp-uniform branch
     if (fin) {
         L.tally.episodes += 1;
         if (L.e.sa > L.e.sb) L.tally.wins_a += 1; else L.tally.wins_b += 1;

@@ -412,7 +412,6 @@ qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol,
 // Work is split in units of warps (32 envs): `n_chunks` chunks of at most 16 warps, balanced to within one warp, so
 // every SM issues the same number of warp-steps whatever n is.  A CTA walks chunks blockIdx.x, + gridDim.x, ...
 constexpr int TC_FUSED_THREADS = G_ROWS * CTA_GROUPS;
-constexpr int TC_STAGGER_CYCLES = 0;           // one-off phase offset between the groups of a CTA (PP_TC_STAGGER overrides)
 struct FusedMap {
     static constexpr uint32_t W = 0, GROUPS_OFF = 2 * PLAYER_W_BYTES;
     static constexpr uint32_t SERVE_OFF = GROUPS_OFF + CTA_GROUPS * GROUP_BYTES;      // next serve per thread: 3 doubles
@@ -423,11 +422,11 @@ struct FusedMap {
 static_assert(FusedMap::TOTAL <= 232448, "shared memory of the fused tensor-core kernel exceeds 227 KB");
 static_assert(2 * BLOB_BYTES <= CTA_GROUPS * GROUP_BYTES + TC_FUSED_THREADS * 24, "weight staging aliases the X rows and serve slots");
 
-template <typename R>
+template <typename R, bool PRECLAIM>
 __global__ void __launch_bounds__(TC_FUSED_THREADS, 1)
 selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_steps, const PPPolicy pol_a,
                    const PPPolicy pol_b, uint64_t seed, int64_t step_base, const PPServeSource src, int32_t quota,
-                   int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks, int stagger) {
+                   int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks) {
     extern __shared__ __align__(128) uint8_t smem[];
     using M = FusedMap;
     const uint32_t tmem = __shfl_sync(0xffffffffu, tc_prologue<CTA_GROUPS, M>(smem, pol_a, pol_b), 0);
@@ -442,6 +441,12 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
     const int64_t total_warps = (n + 31) / 32;
     const int64_t ring_t0 = ring_first_step(ring, n, k_steps);
     const bool prefetch_serves = src.kind == PP_SERVE_PHILOX;
+    // a serve QUEUE drawn from Philox (the host-buffer evaluation): envs also draw their next serve ahead of time, all
+    // lanes together — but they have to CLAIM it first, and an env that holds a claimed serve will play it, so claiming
+    // ahead stops 2 n serves before the end of the queue: the last serves go to whichever envs finish first (no tail of
+    // envs that sit on a second episode while others idle)
+    constexpr bool preclaim_serves = PRECLAIM;           // its own instantiation: the main path does not carry the code
+    int next_q = -1;
     Tally total;
 
 #pragma unroll 1
@@ -458,13 +463,6 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
         L.ep_idx = s.ep_idx[ic]; L.ep_len = s.ep_len[ic];
         const uint32_t gid = (uint32_t)(env_id_base + ic);
         bool have_next = false;
-        // The four groups of a CTA run identical phases; started together they stay in step with each other: all four wait
-        // for their MMAs at the same time and then compete for the issue slots at the same time.  A one-off offset of
-        // grp * stagger cycles spreads their phases over the step.
-        if (stagger > 0 && grp > 0) {
-            const long long until = clock64() + (long long)grp * stagger;
-            while (clock64() < until) {}
-        }
 
 #pragma unroll 1
         for (int64_t t = 0; t < k_steps; ++t) {
@@ -476,6 +474,18 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
             if ((t & 7) == 0 && prefetch_serves && active && !have_next && !(quota > 0 && L.ep_idx + 1 >= quota)) {
                 philox_serve(params, src.seed, gid, (uint32_t)(L.ep_idx + 1), serve_slot[0], serve_slot[1], serve_slot[2]);
                 have_next = true;
+            }
+            if ((t & 7) == 0 && preclaim_serves) {
+                const bool want = active && !have_next && L.ep_idx != 0x7fffffff;
+                const unsigned m_want = __ballot_sync(0xffffffffu, want);
+                if (m_want && (long long)*reinterpret_cast<volatile unsigned long long *>(src.queue_head) + 2 * n < src.queue_total) {
+                    const int q = claim_serves(want, m_want, src);
+                    if (want && q != 0x7fffffff) {
+                        philox_serve(params, src.seed, (uint32_t)(env_id_base + q % n), (uint32_t)(q / n), serve_slot[0], serve_slot[1], serve_slot[2]);
+                        have_next = true;
+                        next_q = q;
+                    }
+                }
             }
 #ifdef PP_TC_TIMING
             if (t == 0) g.timer.start();
@@ -502,8 +512,9 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
                     if (have_next) { vx = (R)serve_slot[0]; vy = (R)serve_slot[1]; sp = (R)serve_slot[2]; have_next = false; }
                     else next_serve<R>(params, src, n, i, env_id_base, ep, vx, vy, sp);
                 };
-                step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
-                                 ring.head != nullptr && t >= ring_t0, src, serve, row_stage);
+                const int pre = (preclaim_serves && have_next) ? next_q : -1;
+                step_and_book<R, PRECLAIM>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
+                                           ring.head != nullptr && t >= ring_t0, src, serve, row_stage, pre);
             }
             PP_TICK(9);
         }
@@ -569,18 +580,16 @@ int selfplay_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const 
         n_chunks = rounds * slots;
     }
     const unsigned blocks = (unsigned)(n_chunks < slots ? n_chunks : slots);
-    static const int stagger = [] { const char *e = getenv("PP_TC_STAGGER"); return e ? atoi(e) : TC_STAGGER_CYCLES; }();
-    cudaError_t err;
-    if (mode == PP_MODE_F64) {
-        if ((err = cudaFuncSetAttribute(selfplay_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)err;
-        selfplay_tc_kernel<double><<<blocks, TC_FUSED_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
-                                                                        env_id_base, out, r, n_chunks, stagger);
-    } else {
-        if ((err = cudaFuncSetAttribute(selfplay_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)err;
-        selfplay_tc_kernel<float><<<blocks, TC_FUSED_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota,
-                                                                       env_id_base, out, r, n_chunks, stagger);
-    }
-    return (int)cudaGetLastError();
+    const bool preclaim = src.kind == PP_SERVE_QUEUE && src.pool_vx == nullptr;   // a Philox-drawn serve queue (host-buffer evaluation)
+    auto launch = [&](auto kernel) -> int {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return (int)err;
+        kernel<<<blocks, TC_FUSED_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota, env_id_base, out, r,
+                                                        n_chunks);
+        return (int)cudaGetLastError();
+    };
+    if (mode == PP_MODE_F64) return preclaim ? launch(selfplay_tc_kernel<double, true>) : launch(selfplay_tc_kernel<double, false>);
+    return preclaim ? launch(selfplay_tc_kernel<float, true>) : launch(selfplay_tc_kernel<float, false>);
 }
 
 }  // namespace pp
