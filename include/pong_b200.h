@@ -378,6 +378,17 @@ int pp_drqn_grads(const PPReplayRing *ring, const int64_t *rows, int32_t batch, 
                   float gamma, const PPQNetRNNGrads *grads, float *loss_out, float *td_out, float *workspace, void *stream);
 int64_t pp_drqn_workspace_floats(int32_t batch, int32_t trace);
 
+/* SequenceReplayBuffer.sample (scripts/train_rnn_iterative.py:126-141) on a lock-step ring ([T][n], PPReplayRing with
+ * lockstep_envs = n, `steps_written` steps so far): weights[T * n] (indexed by ring slot) = the probability weight of
+ * the window of `trace` steps that ENDS at that slot — 1 / (len - trace + 1) if its episode is complete inside the ring,
+ * at least `trace` long and contains the window, else 0 (every stored episode has total weight 1: episode first, window
+ * second); *episodes = number of stored episodes (len(memory), :170-171).  starts_fresh != 0: step 0 of the ring is the
+ * first step of an episode.  Draw window ends with pp_per_sample(weights, T * n, alpha = 1, ...), then
+ * pp_seq_expand_rows turns the ends into rows[batch][trace] (time ascending) for pp_drqn_grads. */
+int pp_seq_window_weights(const uint8_t *done, int64_t n, int64_t T, int64_t steps_written, int32_t trace, int32_t starts_fresh,
+                          float *weights, unsigned long long *episodes, void *stream);
+int pp_seq_expand_rows(const int64_t *end_slots, int32_t batch, int32_t trace, int64_t n, int64_t T, int64_t *rows, void *stream);
+
 /* QNetRNN in torch's layout -> the fp16 stage image PP_RNNTC_* (PP_RNNTC_BLOB_BYTES bytes, 16-byte aligned) the tensor-core
  * kernels take as PPPolicy.weights with PP_PREC_F16; noisy != 0: the train-mode weights mu + sigma * epsilon of the three
  * NoisyLinear layers (models/qnet_rnn.py:44-46).  One launch; the host-side equivalent is policy.pack_qnetrnn_tc. */

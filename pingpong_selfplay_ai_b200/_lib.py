@@ -114,6 +114,8 @@ _PROTOTYPES = {
     "pp_drqn_grads": (C.c_int, [P(PPReplayRing), c_vp, c_i32, c_i32, P(PPQNetRNNParams), P(PPQNetRNNParams), c_i32, c_i32,
                                 c_f32, P(PPQNetRNNGrads), c_vp, c_vp, c_vp, c_vp]),
     "pp_drqn_workspace_floats": (c_i64, [c_i32, c_i32]),
+    "pp_seq_window_weights": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "pp_seq_expand_rows": (C.c_int, [c_vp, c_i32, c_i32, c_i64, c_i64, c_vp, c_vp]),
     "pp_pack_qnetrnn_tc": (C.c_int, [P(PPQNetRNNParams), c_i32, c_vp, c_vp]),
     "pp_clip_grad_norm": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "pp_adam_step_multi": (C.c_int, [P(PPAdamParam), c_i32, c_f64, c_f64, c_f64, c_f64, c_vp]),

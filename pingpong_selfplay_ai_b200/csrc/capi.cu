@@ -310,6 +310,20 @@ int pp_drqn_grads(const PPReplayRing *ring, const int64_t *rows, int32_t batch, 
                                        loss_out, td_out, workspace, (cudaStream_t)stream), fn);
 }
 
+int pp_seq_window_weights(const uint8_t *done, int64_t n, int64_t T, int64_t steps_written, int32_t trace, int32_t starts_fresh,
+                          float *weights, unsigned long long *episodes, void *stream) {
+    if (n <= 0 || T <= 0 || steps_written < 0 || trace <= 0 || trace > T) return fail(PP_E_SIZE, "pp_seq_window_weights");
+    if (!done || !weights || !episodes) return fail(PP_E_NULL, "pp_seq_window_weights");
+    return ok_or(pp::seq_window_weights_launch(done, n, T, steps_written, trace, starts_fresh, weights, episodes, (cudaStream_t)stream),
+                 "pp_seq_window_weights");
+}
+
+int pp_seq_expand_rows(const int64_t *end_slots, int32_t batch, int32_t trace, int64_t n, int64_t T, int64_t *rows, void *stream) {
+    if (batch <= 0 || trace <= 0 || n <= 0 || T <= 0 || trace > T) return fail(PP_E_SIZE, "pp_seq_expand_rows");
+    if (!end_slots || !rows) return fail(PP_E_NULL, "pp_seq_expand_rows");
+    return ok_or(pp::seq_expand_rows_launch(end_slots, batch, trace, n, T, rows, (cudaStream_t)stream), "pp_seq_expand_rows");
+}
+
 int pp_pack_qnetrnn_tc(const PPQNetRNNParams *net, int32_t noisy, void *image, void *stream) {
     if (!rnn_params_ok(net)) return fail(PP_E_PARAM, "pp_pack_qnetrnn_tc");
     if (!image) return fail(PP_E_NULL, "pp_pack_qnetrnn_tc");

@@ -776,3 +776,68 @@ int pack_qnetrnn_tc_launch(const PPQNetRNNParams &p, int noisy, void *image, cud
 }
 
 }  // namespace pp
+
+// ------------------------------------------------------------------------------------------ sequence replay on a lock-step ring
+// SequenceReplayBuffer.sample (scripts/train_rnn_iterative.py:126-141) draws a stored episode uniformly, then a window of
+// `trace` consecutive steps uniformly inside it.  On the time-major ring [T][n] that is: a window ENDING at row (t, i) is
+// eligible iff its episode is complete inside the ring, has len >= trace and the window lies inside it, with weight
+// 1 / (len - trace + 1) — every stored episode carries total weight 1.  One thread per env walks its column once.
+namespace pp {
+namespace {
+
+__global__ void __launch_bounds__(256)
+seq_window_weights_kernel(const uint8_t *__restrict__ done, int64_t n, int64_t T, int64_t steps_written, int trace, int starts_fresh,
+                          float *__restrict__ weights, unsigned long long *__restrict__ episodes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool wrapped = steps_written > T;
+    const int64_t shift = wrapped ? steps_written % T : 0;           // physical row of the oldest step
+    unsigned count = 0;
+    if (i < n) {
+        auto at = [&](int64_t t) { int64_t r = t + shift; if (r >= T) r -= T; return r * n + i; };
+        int64_t begin = 0;                                           // first row of the episode being walked
+        bool cut = !(starts_fresh && !wrapped);                      // its start lies before the ring's oldest row
+        for (int64_t t = 0; t < T; ++t) {
+            if (done[at(t)]) {
+                const int64_t len = t - begin + 1;
+                const bool stored = !cut && len >= trace;
+                const float wv = stored ? 1.0f / (float)(len - trace + 1) : 0.0f;
+                for (int64_t e = begin; e <= t; ++e) weights[at(e)] = (e - begin + 1 >= trace) ? wv : 0.0f;
+                count += stored ? 1u : 0u;
+                begin = t + 1;
+                cut = false;
+            }
+        }
+        for (int64_t e = begin; e < T; ++e) weights[at(e)] = 0.0f;  // the episode still running (or rows not written yet)
+    }
+    count = __reduce_add_sync(0xffffffffu, count);
+    if ((threadIdx.x & 31) == 0 && count) atomicAdd(episodes, (unsigned long long)count);
+}
+
+// sampled window ends (ring slots) -> the `trace` slots of each window in time order
+__global__ void seq_expand_rows_kernel(const int64_t *__restrict__ end_slots, int batch, int trace, int64_t n, int64_t T,
+                                       int64_t *__restrict__ rows) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= batch * trace) return;
+    const int b = j / trace, k = j % trace;
+    const int64_t slot = end_slots[b], env = slot % n;
+    int64_t r = slot / n - (trace - 1) + k;
+    if (r < 0) r += T;
+    rows[j] = r * n + env;
+}
+
+}  // namespace
+
+int seq_window_weights_launch(const uint8_t *done, int64_t n, int64_t T, int64_t steps_written, int trace, int starts_fresh,
+                              float *weights, unsigned long long *episodes, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(episodes, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return (int)e;
+    seq_window_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(done, n, T, steps_written, trace, starts_fresh, weights, episodes);
+    return (int)cudaGetLastError();
+}
+
+int seq_expand_rows_launch(const int64_t *end_slots, int batch, int trace, int64_t n, int64_t T, int64_t *rows, cudaStream_t stream) {
+    seq_expand_rows_kernel<<<(batch * trace + 255) / 256, 256, 0, stream>>>(end_slots, batch, trace, n, T, rows);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pp

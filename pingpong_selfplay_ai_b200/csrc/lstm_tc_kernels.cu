@@ -550,7 +550,9 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
                     int a = 1;
                     if (pol.kind == PP_POLICY_QNETRNN) {
                         float q[3];
+                        RT_T0(tps_);
                         compute_player_step(w, p ? ob : oa, r_fresh, r_live, pol.h, pol.c, ic, q);
+                        if (tid == 0) { RT_ADD(12, tps_); RT_ADD(0, clock64() - 1); }
                         a = explore(argmax3(q), pol.eps_threshold, seed, gid, step, stream_id);   // (h, c) advance even when exploring
                     } else if (pol.kind == PP_POLICY_RANDOM) {
                         a = random_action(seed, gid, step, stream_id);
@@ -562,6 +564,7 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
                     }
                     if (p) act_b = a; else act_a = a;
                 }
+                RT_T0(tenv_);
                 if (half == 0 && gw < my_warps) {                              // whole warps: the bookkeeping collectives are safe
                     const int ep_before = L.ep_idx;
                     step_and_book<R>(c, L, active, act_a, act_b, ob, t, n, i, env_id_base, quota, out, ring,
@@ -569,6 +572,7 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
                                      [&](int ep, R &vx, R &vy, R &sp) { next_serve<R>(params, src, n, i, env_id_base, ep, vx, vy, sp); });
                     fresh = active ? (L.ep_idx != ep_before) : fresh;
                 }
+                if (tid == 0) RT_ADD(13, tenv_);
             }
             if (valid && half == 0) {
                 store_env<R>(s, i, L.e);

@@ -63,6 +63,9 @@ int drqn_grads_launch(const PPReplayRing &ring, const int64_t *rows, int32_t bat
                       float *loss_out, float *td_out, float *ws, cudaStream_t stream);
 int64_t drqn_workspace_floats(int32_t batch, int32_t trace);
 int clip_grad_norm_launch(float *flat, int64_t numel, float max_norm, float *norm_out, float *scratch, cudaStream_t stream);
+int seq_window_weights_launch(const uint8_t *done, int64_t n, int64_t T, int64_t steps_written, int trace, int starts_fresh,
+                              float *weights, unsigned long long *episodes, cudaStream_t stream);
+int seq_expand_rows_launch(const int64_t *end_slots, int batch, int trace, int64_t n, int64_t T, int64_t *rows, cudaStream_t stream);
 int pack_qnetrnn_tc_launch(const PPQNetRNNParams &p, int noisy, void *image, cudaStream_t stream);
 int adam_multi_launch(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, cudaStream_t stream);
 

@@ -87,22 +87,72 @@ class SequenceSampler:
         w = torch.where(ok, 1.0 / (ep_len - L + 1).clamp(min=1).to(torch.float64), torch.zeros((), dtype=torch.float64, device=dev))
         return w, d, shift
 
+    def _on_cuda(self) -> bool:
+        return self.ring.obs.device.type == "cuda"
+
     def refresh(self) -> int:
-        """Rebuild the sampling table after new rows were written (one pass over the ring on the device; no per-row
-        host work).  Returns the number of stored episodes."""
+        """Rebuild the sampling table after new rows were written.  On the device: ONE hand-written launch
+        (pp_seq_window_weights: a thread per env walks its column of done flags) writes the window weights per ring
+        slot and counts the stored episodes; `sample_rows` then draws with pp_per_sample.  The torch formulation below
+        is the host-logic mirror the CPU tests compare with SequenceReplayBuffer (it also serves an explicit generator).
+        Returns the number of stored episodes."""
         if self.ring.steps_written == 0:
             self.episodes = 0
             return 0
+        self._cdf_valid = False
+        if self._on_cuda():
+            dev = self.ring.obs.device
+            if getattr(self, "_k_w", None) is None:
+                self._k_lib = _lib.load()
+                self._k_w = torch.zeros(self.T * self.n, dtype=torch.float32, device=dev)
+                self._k_eps = torch.zeros(1, dtype=torch.int64, device=dev)
+                self._k_eps_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+            with torch.cuda.device(dev):
+                _lib.check(self._k_lib.pp_seq_window_weights(_ptr(self.ring.done), self.n, self.T, int(self.ring.steps_written),
+                                                             self.trace_length, int(self.starts_fresh), _ptr(self._k_w), _ptr(self._k_eps),
+                                                             _stream_ptr(dev)), "pp_seq_window_weights")
+            self._k_eps_host.copy_(self._k_eps, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            self.episodes = int(self._k_eps_host[0])
+            return self.episodes
+        return self._refresh_torch()
+
+    def _refresh_torch(self) -> int:
         w, d, shift = self.window_weights()
         torch.cumsum(w.flatten(), 0, out=self._cdf)
         self._shift.fill_(shift)
         self.episodes = int(((w > 0) & d).sum().item())           # every stored episode ends with exactly one such row
+        self._cdf_valid = True
         return self.episodes
 
-    def sample_rows(self, batch_size: int, generator=None):
-        """-> ring slots int64 [batch, trace_length], time ascending."""
+    def sample_rows(self, batch_size: int, generator=None, seed: int = 0):
+        """-> ring slots int64 [batch, trace_length], time ascending.  On the device (no explicit generator): window ends
+        drawn by pp_per_sample over the weight array (alpha = 1; Philox keyed by seed and a device-side draw counter, so a
+        replayed CUDA graph draws fresh windows), expanded by pp_seq_expand_rows: four launches, static buffers."""
         if self.episodes == 0:
             raise RuntimeError("no complete episode of at least trace_length steps in the ring")
+        if self._on_cuda() and generator is None:
+            dev = self.ring.obs.device
+            if getattr(self, "_k_batch", None) != batch_size:
+                cap = self.T * self.n
+                self._k_batch = batch_size
+                self._k_idx = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+                self._k_iw = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+                self._k_rows = torch.zeros(batch_size, self.trace_length, dtype=torch.int64, device=dev)
+                self._k_sums = torch.zeros(int(self._k_lib.pp_per_sample_scratch_floats(cap)), dtype=torch.float32, device=dev)
+                if getattr(self, "_k_counter", None) is None:                          # the draw counter outlives a change of batch size
+                    self._k_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+                self._k_one = torch.ones(2, dtype=torch.float32, device=dev)             # beta, size: the importance weights are unused
+            st = _stream_ptr(dev)
+            with torch.cuda.device(dev):
+                _lib.check(self._k_lib.pp_per_sample(_ptr(self._k_w), self.T * self.n, 1.0, _ptr(self._k_one[0:1]), _ptr(self._k_one[1:2]),
+                                                     int(seed) & (2 ** 64 - 1), _ptr(self._k_counter), batch_size, _ptr(self._k_sums),
+                                                     _ptr(self._k_idx), _ptr(self._k_iw), st), "pp_per_sample")
+                _lib.check(self._k_lib.pp_seq_expand_rows(_ptr(self._k_idx), batch_size, self.trace_length, self.n, self.T,
+                                                          _ptr(self._k_rows), st), "pp_seq_expand_rows")
+            return self._k_rows
+        if not getattr(self, "_cdf_valid", False):
+            self._refresh_torch()
         total = self._cdf[-1]
         u = torch.rand(batch_size, dtype=torch.float64, device=self._cdf.device, generator=generator) * total
         idx = torch.searchsorted(self._cdf, u, right=True)

@@ -120,9 +120,12 @@ def test_drqn_fused_update_tracks_the_autograd_update_in_a_generation():
     b = TorchDRQNTrainer(copy.deepcopy(net), lr=1e-3, batch_size=64, use_graph=False, device="cuda")
     b.model.load_state_dict(a.model.state_dict())        # the same epsilon buffers
     torch.backends.cudnn.allow_tf32 = False
-    for step in range(3):                                # the eager updates: same RNG stream -> the same windows
-        torch.manual_seed(100 + step); la = a.update(sampler)
-        torch.manual_seed(100 + step); lb = b.update(sampler)
+    for step in range(3):                                # the eager updates, on the same windows for both
+        rows = sampler.sample_rows(64, generator=torch.Generator(device="cuda").manual_seed(100 + step)).clone()
+        sampler.sample_rows = lambda *args, **kw: rows   # instance override: both trainers draw through it
+        la = a.update(sampler)
+        lb = b.update(sampler)
+        del sampler.sample_rows
         assert float(la) == pytest.approx(float(lb), rel=1e-3, abs=1e-6), step
     for (name, p), q in zip(a.model.named_parameters(), b.model.parameters()):
         assert torch.allclose(p, q, rtol=1e-2, atol=2e-4), name
@@ -150,3 +153,47 @@ def test_device_pack_of_the_tensor_core_weight_image_equals_the_host_pack(noisy)
         got = img.cpu().numpy()
         bad = np.flatnonzero(got != want)
         assert bad.size == 0, (which, bad[:8], bad.size)
+
+
+@pytest.mark.parametrize("steps", [25, 40, 41, 97, 200])
+def test_sequence_sampler_kernels_equal_the_reference_episode_then_window_distribution(steps):
+    """pp_seq_window_weights / pp_per_sample / pp_seq_expand_rows on the device == SequenceReplayBuffer's distribution
+    (scripts/train_rnn_iterative.py:115-141, restated in tests/test_train_rnn_logic.py): the weight of every window end,
+    the stored-episode count, and 61 440 drawn windows (contiguous, inside one stored episode, frequencies = weights)."""
+    import test_train_rnn_logic as host
+    n, T, L = 50, 40, host.L
+    ring_cpu, done = host._lockstep_ring(n, T, steps, seed=steps, p_done=0.07)
+    ring = pp.ReplayRing(n * T, lockstep_envs=n)
+    for name in ("obs", "next_obs", "act", "rew", "done"):
+        getattr(ring, name).copy_(getattr(ring_cpu, name))
+    ring.steps_written = steps
+    want, episodes = host._reference_buffer(done, n, T, steps)
+    s = SequenceSampler(ring, trace_length=L)
+    assert s.refresh() == episodes == len(s)
+    w = gu.np_of(s._k_w).reshape(T, n)
+    lo = max(0, steps - T)
+    got = {}
+    for r, i in zip(*np.nonzero(w)):
+        t = next(t for t in range(lo, steps) if t % T == r)                     # the absolute step held by ring row r
+        got[(t, int(i))] = float(w[r, i])
+    assert got.keys() == want.keys() and all(abs(got[k] - want[k]) < 1e-6 for k in want)
+    if not episodes:
+        return
+    draws = 15 * 4096
+    rows = np.concatenate([gu.np_of(s.sample_rows(4096, seed=3)).copy() for _ in range(15)])    # static buffer: copy each draw
+    assert rows.shape == (draws, L)
+    t_abs = gu.np_of(ring.obs)[rows, 0].astype(np.int64)                         # obs[.., 0] = absolute step, obs[.., 1] = env
+    env = gu.np_of(ring.obs)[rows, 1].astype(np.int64)
+    assert np.all(np.diff(t_abs, axis=1) == 1) and np.all(env == env[:, :1])
+    assert not done[t_abs[:, :-1], env[:, :-1]].any()                            # no episode end inside a window
+    ends = list(zip(t_abs[:, -1].tolist(), env[:, -1].tolist()))
+    assert set(ends) <= set(want)
+    freq = {k: 0 for k in want}
+    for e in ends:
+        freq[e] += 1
+    total = sum(want.values())
+    for k, wv in want.items():
+        p = wv / total
+        assert abs(freq[k] / draws - p) < 5 * np.sqrt(p * (1 - p) / draws) + 1e-4, (k, freq[k] / draws, p)
+    again = gu.np_of(s.sample_rows(64, seed=3))
+    assert not np.array_equal(again, rows[:64])                                  # the draw counter advances
