@@ -17,6 +17,7 @@ lib.pp_debug_rt_timing(t, 1)
 ctas, ps = 148, 148 * k * 2                       # player-steps timed by thread 0 of every CTA
 names = {1: "issuer: wait for operand rows (ready)", 3: "issuer: wait for a weight stage (full)", 4: "issuer: wait for a drained accumulator",
          8: "worker: wait for accumulators (done)", 9: "worker: h_prev staging", 10: "worker: LSTM cells (4 quarters)",
+         14: "worker:   of which tcgen05.ld + wait (8 per player-step)", 15: "worker:   of which cell arithmetic (8 batches of 8 units)",
          12: "worker: player-step total", 13: "worker: env step + bookkeeping (per lock-step step x2)"}
 for slot, name in names.items():
     print(f"{name:56s} {t[slot] / ps:10.0f} cycles / player-step")
