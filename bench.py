@@ -690,8 +690,8 @@ def measure_config5_train(pp, ppd, args, dev, rank, world, local, peaks):
     assert out["env_steps"] == CONFIG5_ENVS * k * chunks and out["updates"] == upc * chunks
     # the collective alone: the flat 520-float gradient buffer, 200 all-reduces back to back
     ar_us = None
-    if world > 1:
-        flat = trainer._flat_grad
+    if world > 1:                                       # the NCCL collective alone, for reference (the update may not use it)
+        flat = trainer._flat_grad.clone()
         for _ in range(10):
             ppd.allreduce_mean_flat_(flat)
         torch.cuda.synchronize()
@@ -707,8 +707,10 @@ def measure_config5_train(pp, ppd, args, dev, rank, world, local, peaks):
            "value": value, "unit": UNIT, "n_gpus": world, "scaling": "strong", "envs_total": CONFIG5_ENVS, "envs_per_gpu": n,
            "lockstep_steps_per_chunk": k, "updates_per_chunk": upc, "batch_per_rank": 256, "chunks": chunks, "warmup_chunks": warm,
            "ms_per_chunk": 1e3 * sec / chunks, "updates_per_s": out["updates"] / sec, "grad_allreduce_us": ar_us,
-           "grad_allreduce": ("captured inside the update's CUDA graph" if getattr(trainer, "_split", True) is False and world > 1
-                              else ("eager NCCL all-reduce between two CUDA graphs" if world > 1 else "single rank: none")),
+           "grad_allreduce": ("single rank: none" if world == 1 else
+                              (trainer._p2p_note if getattr(trainer, "_p2p", None) is not None else
+                               ("NCCL all-reduce captured inside the update's CUDA graph" if getattr(trainer, "_split", True) is False
+                                else "eager NCCL all-reduce between two CUDA graphs") + "; " + getattr(trainer, "_p2p_note", ""))),
            "mean_loss": out["mean_loss"], "epsilon": out["epsilon"], "episodes": out["episodes"], "replay_capacity": ring.capacity,
            "dtype": f"{args.mode} env state + {args.precision} QNet rollout, fp32 update", "clocks": clocks,
            "roofline": {"bound": "tensor", "kernel": "selfplay_tc_kernel (rollout with replay rows)", "achieved": tf,

@@ -362,6 +362,23 @@ int64_t pp_per_sample_scratch_floats(int64_t capacity);
  *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps) */
 int pp_adam_step(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, void *stream);
 
+/* Several ranks (one process per GPU): optimizerB.step() with the gradient all-reduce of scripts/train_iterative.py's
+ * data-parallel form FUSED in front of it, over peer-mapped memory (NVLink), in ONE launch and without NCCL.
+ * blocks[r] = rank r's block as mapped into THIS process (e.g. torch.distributed._symmetric_memory rendezvous:
+ * buffer_ptrs), each pp_peer_block_bytes(capacity_floats) bytes, zeroed before the first use on every rank:
+ * float staging[2][capacity_floats]; uint32 flags[8].  flat_grad[numel] (numel <= capacity_floats) is the flat buffer the
+ * grad pointers of `params` view; on return it holds the MEAN over ranks (summed in rank order: bit-identical on every
+ * rank) and the parameters have taken one Adam step.  *epoch (device memory, starts at 0) counts the calls; every rank
+ * must make the same calls in the same order — the kernel waits for its peers.  world <= 8, count <= 16. */
+typedef struct PPPeerBlocks {
+    void *blocks[8];
+    int32_t rank, world;
+    int64_t capacity_floats;
+} PPPeerBlocks;
+int pp_adam_step_allreduce(const PPAdamParam *params, int32_t count, float *flat_grad, int64_t numel, const PPPeerBlocks *peers,
+                           unsigned long long *epoch, double lr, double beta1, double beta2, double eps, void *stream);
+int64_t pp_peer_block_bytes(int64_t capacity_floats);
+
 /* ---- DRQN training mode (scripts/train_rnn_iterative.py)
  *
  * train_step_rnn() of scripts/train_rnn_iterative.py:400-531 up to the gradients, for `batch` sampled windows of `trace`

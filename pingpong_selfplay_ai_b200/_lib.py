@@ -83,6 +83,10 @@ class PPQNetRNNGrads(C.Structure):
         ("shared", PPNoisyLayer), ("v", PPNoisyLayer), ("a", PPNoisyLayer)]
 
 
+class PPPeerBlocks(C.Structure):
+    _fields_ = [("blocks", c_vp * 8), ("rank", c_i32), ("world", c_i32), ("capacity_floats", c_i64)]
+
+
 P = C.POINTER
 _PROTOTYPES = {
     "pp_version": (C.c_int, []),
@@ -108,6 +112,8 @@ _PROTOTYPES = {
     "pp_per_sample": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_u64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "pp_per_sample_scratch_floats": (c_i64, [c_i64]),
     "pp_adam_step": (C.c_int, [P(PPAdamParam), c_i32, c_f64, c_f64, c_f64, c_f64, c_vp]),
+    "pp_adam_step_allreduce": (C.c_int, [P(PPAdamParam), c_i32, c_vp, c_i64, P(PPPeerBlocks), c_vp, c_f64, c_f64, c_f64, c_f64, c_vp]),
+    "pp_peer_block_bytes": (c_i64, [c_i64]),
     "pp_host_selfplay_eval": (C.c_int, [C.c_int, C.c_int, c_i64, c_i32, P(PPParams), c_vp, c_vp, c_vp, c_u64, c_i64,
                                         c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_i64]),
     "pp_host_release": (C.c_int, [C.c_int]),

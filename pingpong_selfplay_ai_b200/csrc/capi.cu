@@ -286,6 +286,24 @@ int pp_adam_step(const PPAdamParam *params, int32_t count, double lr, double bet
     return ok_or(pp::adam_step_launch(params, count, lr, beta1, beta2, eps, (cudaStream_t)stream), "pp_adam_step");
 }
 
+int pp_adam_step_allreduce(const PPAdamParam *params, int32_t count, float *flat_grad, int64_t numel, const PPPeerBlocks *peers,
+                           unsigned long long *epoch, double lr, double beta1, double beta2, double eps, void *stream) {
+    const char *fn = "pp_adam_step_allreduce";
+    if (count <= 0 || count > 16 || numel <= 0) return fail(PP_E_SIZE, fn);
+    if (!params || !flat_grad || !peers || !epoch) return fail(PP_E_NULL, fn);
+    if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || numel > peers->capacity_floats)
+        return fail(PP_E_SIZE, fn);
+    for (int r = 0; r < peers->world; ++r) if (!peers->blocks[r]) return fail(PP_E_NULL, fn);
+    for (int i = 0; i < count; ++i) {
+        const PPAdamParam &a = params[i];
+        if (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq || !a.step) return fail(PP_E_NULL, fn);
+    }
+    if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0)) return fail(PP_E_PARAM, fn);
+    return ok_or(pp::adam_allreduce_launch(params, count, flat_grad, numel, *peers, epoch, lr, beta1, beta2, eps, (cudaStream_t)stream), fn);
+}
+
+int64_t pp_peer_block_bytes(int64_t capacity_floats) { return capacity_floats > 0 ? (2 * capacity_floats + 8) * 4 : 0; }
+
 // ---------------------------------------------------------------------------------------------
 // DRQN training mode.
 namespace {

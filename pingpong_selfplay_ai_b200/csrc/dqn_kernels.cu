@@ -333,6 +333,85 @@ adam_step_kernel(const AdamParams ps, int count, double lr, double beta1, double
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same Adam step with the gradient ALL-REDUCE over NVLink fused in front of it (several ranks, one process per GPU):
+// no NCCL call, no second launch.  Every rank owns one block of peer-mapped ("symmetric") memory
+//     float staging[2][capacity]   its gradients of the current / previous epoch
+//     uint32 flags[8]              flags[r] = last epoch rank r has published
+// and sees all blocks through its own address space (PPPeerBlocks.blocks[r]).  Per update (epoch e = *epoch + 1):
+//   1. copy my flat gradient buffer into my staging[e & 1], fence (system scope), then write e into flags[me] of EVERY
+//      rank's block (remote stores over NVLink: a waiting rank polls its own memory);
+//   2. wait until my flags[r] >= e for all r;
+//   3. read every rank's staging[e & 1] (peer loads), add them in rank order — the same order on every rank, so all
+//      replicas compute bit-identical averages —, write the mean back into the flat gradient buffer;
+//   4. Adam on the averaged gradients.
+// Double buffering is enough: a rank overwrites staging[e & 1] at epoch e + 2, i.e. after it has passed the wait of epoch
+// e + 1, which no rank can satisfy before it has finished its own epoch-e kernel.
+struct PeerBlocks { float *blocks[8]; int rank, world; long long capacity; };
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+adam_allreduce_kernel(const AdamParams ps, int count, float *__restrict__ flat_grad, int numel, const PeerBlocks peers,
+                      unsigned long long *epoch, double lr, double beta1, double beta2, double eps) {
+    __shared__ float s_step_size[16], s_bc2_sqrt[16], s_step[16];
+    const int tid = threadIdx.x;
+    const unsigned e = (unsigned)(*epoch + 1ull);
+    const int slot = (int)(e & 1u);
+    float *mine = peers.blocks[peers.rank] + (long long)slot * peers.capacity;
+    for (int f = tid; f < numel; f += blockDim.x) mine[f] = flat_grad[f];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < peers.world) {
+        unsigned *flags = reinterpret_cast<unsigned *>(peers.blocks[tid] + 2 * peers.capacity);
+        st_release_sys(flags + peers.rank, e);
+    }
+    if (tid < peers.world) {
+        const unsigned *my_flags = reinterpret_cast<const unsigned *>(peers.blocks[peers.rank] + 2 * peers.capacity);
+        while ((int)(ld_acquire_sys(my_flags + tid) - e) < 0) {}
+    }
+    __syncthreads();
+    const float inv = 1.0f / (float)peers.world;
+    for (int f = tid; f < numel; f += blockDim.x) {
+        float acc = 0.0f;
+        for (int r = 0; r < peers.world; ++r)
+            acc += *reinterpret_cast<const volatile float *>(peers.blocks[r] + (long long)slot * peers.capacity + f);
+        flat_grad[f] = acc * inv;
+    }
+    __syncthreads();
+    // ---- adam_step_kernel's body on the averaged gradients
+    const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), epsf = (float)eps;
+    if (tid < count) {
+        const double step = (double)*ps.p[tid].step + 1.0;
+        s_step[tid] = (float)step;
+        s_step_size[tid] = (float)(lr / (1.0 - pow(beta1, step)));
+        s_bc2_sqrt[tid] = (float)sqrt(1.0 - pow(beta2, step));
+    }
+    __syncthreads();
+    int64_t total = 0;
+    for (int t = 0; t < count; ++t) total += ps.p[t].numel;
+    for (int64_t f = tid; f < total; f += blockDim.x) {
+        int t = 0;
+        int64_t i = f;
+        while (i >= ps.p[t].numel) { i -= ps.p[t].numel; ++t; }
+        const PPAdamParam &a = ps.p[t];
+        const float g = a.grad[i];
+        const float m = a.exp_avg[i] + w1 * (g - a.exp_avg[i]);
+        const float v = a.exp_avg_sq[i] * b2 + w2 * (g * g);
+        a.exp_avg[i] = m; a.exp_avg_sq[i] = v;
+        a.param[i] = a.param[i] - s_step_size[t] * (m / (sqrtf(v) / s_bc2_sqrt[t] + epsf));
+    }
+    if (tid < count) *ps.p[tid].step = s_step[tid];
+    if (tid == 0) *epoch = (unsigned long long)e;
+}
+
+// ---------------------------------------------------------------------------------------------
 // PrioritizedReplay.sample (scripts/train_iterative.py:64-73): np.random.choice(len, batch, p = prios^alpha / sum) and
 // the importance weights (N p)^-beta / max, as a two-level inverse-CDF draw:
 //   per_chunk_sums_kernel : sum of prios^alpha over chunks of the priority array (one pass, fixed summation order)
@@ -508,6 +587,17 @@ int adam_step_launch(const PPAdamParam *params, int32_t count, double lr, double
     AdamParams pack{};
     for (int i = 0; i < count; ++i) pack.p[i] = params[i];
     adam_step_kernel<<<1, 256, 0, stream>>>(pack, count, lr, beta1, beta2, eps);
+    return (int)cudaGetLastError();
+}
+
+int adam_allreduce_launch(const PPAdamParam *params, int32_t count, float *flat_grad, int64_t numel, const PPPeerBlocks &peers,
+                          unsigned long long *epoch, double lr, double beta1, double beta2, double eps, cudaStream_t stream) {
+    AdamParams pack{};
+    for (int i = 0; i < count; ++i) pack.p[i] = params[i];
+    PeerBlocks pb{};
+    for (int r = 0; r < peers.world; ++r) pb.blocks[r] = reinterpret_cast<float *>(peers.blocks[r]);
+    pb.rank = peers.rank; pb.world = peers.world; pb.capacity = peers.capacity_floats;
+    adam_allreduce_kernel<<<1, 256, 0, stream>>>(pack, count, flat_grad, (int)numel, pb, epoch, lr, beta1, beta2, eps);
     return (int)cudaGetLastError();
 }
 

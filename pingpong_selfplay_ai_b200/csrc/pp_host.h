@@ -54,6 +54,8 @@ int per_sample_launch(const float *prios, int64_t capacity, float alpha, const f
                       unsigned long long *counter, int32_t batch, float *chunk_sums, int64_t *idx_out, float *w_out,
                       cudaStream_t stream);
 int adam_step_launch(const PPAdamParam *params, int32_t count, double lr, double beta1, double beta2, double eps, cudaStream_t stream);
+int adam_allreduce_launch(const PPAdamParam *params, int32_t count, float *flat_grad, int64_t numel, const PPPeerBlocks &peers,
+                          unsigned long long *epoch, double lr, double beta1, double beta2, double eps, cudaStream_t stream);
 int noisy_reset_launch(const PPNoisyLayer *layers, int32_t count, uint64_t seed, unsigned long long *counter, cudaStream_t stream);
 int pack_qnet_launch(const float *w1, const float *b1, const float *w2, const float *b2, const PPNoisyLayer &v,
                      const PPNoisyLayer &a, int noisy, float *blob, cudaStream_t stream);

@@ -182,6 +182,42 @@ class DQNTrainer:
             _lib.PPAdamParam(_ptr(p), _ptr(p.grad), _ptr(self.opt.state[p]["exp_avg"]), _ptr(self.opt.state[p]["exp_avg_sq"]),
                              _ptr(self.opt.state[p]["step"]), p.numel()) for p in self.head_params])
         self._workspace = torch.zeros(int(self._lib.pp_dqn_workspace_floats(self.batch_size)), dtype=torch.float32, device=self.device)
+        self._init_p2p()
+
+    def _init_p2p(self):
+        """Several ranks: peer-mapped gradient blocks for pp_adam_step_allreduce — the all-reduce of the 520 head gradients
+        over NVLink fused into the Adam launch (no NCCL node in the update).  The blocks come from
+        torch.distributed._symmetric_memory (CUDA VMM handles exchanged between the ranks' processes); every rank sees
+        every block in its own address space.  Whether the path is used is ONE decision for all ranks (all-reduce MIN of
+        `it worked here`); otherwise the update keeps the NCCL all-reduce.  PP_P2P_ALLREDUCE=0 turns it off."""
+        self._p2p, self._p2p_note = None, "single rank"
+        if not ppd.is_parallel():
+            return
+        import torch.distributed as tdist
+        ok, err = 0, "disabled by PP_P2P_ALLREDUCE=0"
+        if os.environ.get("PP_P2P_ALLREDUCE", "1") == "1" and tdist.get_world_size() <= 8:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                cap = (self._flat_grad.numel() + 63) // 64 * 64
+                nfloats = int(self._lib.pp_peer_block_bytes(cap)) // 4
+                block = symm.empty(nfloats, dtype=torch.float32, device=self.device)
+                block.zero_()
+                hdl = symm.rendezvous(block, tdist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                peers = _lib.PPPeerBlocks()
+                for r, ptr in enumerate(ptrs):
+                    peers.blocks[r] = ptr
+                peers.rank, peers.world, peers.capacity_floats = tdist.get_rank(), tdist.get_world_size(), cap
+                epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
+                torch.cuda.synchronize(self.device)
+                ok, cand = 1, (peers, epoch, block, hdl)
+            except Exception as e:                                             # noqa: BLE001 — any failure means: use NCCL
+                err = f"symmetric memory unavailable: {type(e).__name__}: {e}"
+        if ppd.all_ranks_ready(bool(ok), self.device):
+            tdist.barrier()                                                    # every block is zeroed before anyone signals
+            self._p2p, self._p2p_note = cand, "fused into the Adam kernel over peer-mapped memory (NVLink), no NCCL"
+        else:
+            self._p2p_note = f"NCCL all-reduce ({err if not ok else 'a peer could not map symmetric memory'})"
 
     def _adam_step(self):
         g = self.opt.param_groups[0]
@@ -226,7 +262,16 @@ class DQNTrainer:
 
     def _post(self, sampler: PrioritizedSampler):
         """The rest of train_step(): optimiser step on the (rank-averaged) gradients (one launch; the new priorities were
-        written by pp_dqn_head_grads)."""
+        written by pp_dqn_head_grads).  With peer-mapped gradient blocks the averaging happens in the same launch."""
+        if getattr(self, "_p2p", None) is not None:
+            peers, epoch = self._p2p[0], self._p2p[1]
+            g = self.opt.param_groups[0]
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.pp_adam_step_allreduce(self._adam, len(self.head_params), _ptr(self._flat_grad),
+                                                            self._flat_grad.numel(), C.byref(peers), _ptr(epoch), float(g["lr"]),
+                                                            float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                                            _stream_ptr(self.device)), "pp_adam_step_allreduce")
+            return
         self._adam_step()
 
     def _body(self, sampler, beta, generator=None):
@@ -236,6 +281,8 @@ class DQNTrainer:
         return loss
 
     def _allreduce_grads(self):
+        if getattr(self, "_p2p", None) is not None:       # averaged inside the Adam launch (_post)
+            return
         if getattr(self, "_flat_grad", None) is not None:
             ppd.allreduce_mean_flat_(self._flat_grad)
         else:

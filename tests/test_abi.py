@@ -39,7 +39,8 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     structs = {"PPParams": _lib.PPParams, "PPEnvState": _lib.PPEnvState, "PPServeSource": _lib.PPServeSource,
                "PPPolicy": _lib.PPPolicy, "PPRolloutOut": _lib.PPRolloutOut, "PPReplayRing": _lib.PPReplayRing,
                "PPNoisyLayer": _lib.PPNoisyLayer, "PPAdamParam": _lib.PPAdamParam,
-               "PPQNetRNNParams": _lib.PPQNetRNNParams, "PPQNetRNNGrads": _lib.PPQNetRNNGrads}
+               "PPQNetRNNParams": _lib.PPQNetRNNParams, "PPQNetRNNGrads": _lib.PPQNetRNNGrads,
+               "PPPeerBlocks": _lib.PPPeerBlocks}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for name, st in structs.items():
         lines.append(f'printf("{name} %zu\\n", sizeof({name}));')

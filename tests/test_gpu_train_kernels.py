@@ -306,3 +306,35 @@ def test_a_training_generation_learns_to_beat_the_frozen_opponent():
         deltas.append(after - before); finals.append(after)
         assert trainer.train_steps == rounds * 16 * 64 and eps < 0.2
     assert np.mean(deltas) > 0.03 and max(finals) > 0.58, (deltas, finals)
+
+
+def test_adam_step_allreduce_with_one_rank_equals_adam_step():
+    """pp_adam_step_allreduce with world = 1 (the block is this GPU's own memory): publish, self-signal, mean over one
+    rank, Adam — the parameters move exactly like pp_adam_step's, epoch after epoch (the two staging slots alternate)."""
+    torch.manual_seed(4)
+    net = pp.QNet()
+    a = pp.DQNTrainer(net, batch_size=64, use_graph=False, lr=3e-3)
+    b = pp.DQNTrainer(pp.QNet(), batch_size=64, use_graph=False, lr=3e-3)
+    b.model.load_state_dict(a.model.state_dict())
+    lib = _lib.load()
+    cap = 576
+    block = torch.zeros(int(lib.pp_peer_block_bytes(cap)) // 4, dtype=torch.float32, device="cuda")
+    peers = _lib.PPPeerBlocks()
+    peers.blocks[0] = block.data_ptr()
+    peers.rank, peers.world, peers.capacity_floats = 0, 1, cap
+    epoch = torch.zeros(1, dtype=torch.int64, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for step in range(5):
+        grads = torch.randn(a._flat_grad.numel(), generator=g, device="cuda")
+        a._flat_grad.copy_(grads); b._flat_grad.copy_(grads)
+        a._adam_step()
+        grp = b.opt.param_groups[0]
+        _lib.check(lib.pp_adam_step_allreduce(b._adam, len(b.head_params), _ptr(b._flat_grad), b._flat_grad.numel(), C.byref(peers),
+                                              _ptr(epoch), float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]),
+                                              float(grp["eps"]), _stream_ptr(torch.device("cuda"))), "pp_adam_step_allreduce")
+        torch.cuda.synchronize()
+        assert int(epoch) == step + 1 and torch.equal(b._flat_grad, grads)               # the mean over one rank
+        assert torch.equal(block[(step + 1) % 2 * cap:(step + 1) % 2 * cap + grads.numel()], grads)     # staged in slot e & 1
+        for p, q in zip(a.head_params, b.head_params):
+            assert torch.equal(p, q)
+    assert int(block[2 * cap:].view(torch.int32)[0]) == 5                                # flags[0] = the last epoch
