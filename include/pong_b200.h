@@ -115,7 +115,9 @@ typedef struct PPPolicy {
                                  * evaluates `np.float32 - 0.02` and the compares in float64, and so does the engine   */
     const float *weights;       /* packed blob, see PP_QNET_* / PP_RNN_* offsets (QNetRNN with PP_PREC_F16: the
                                  * fp16 image PP_RNNTC_*)                                                     */
-    float *h, *c;               /* QNetRNN only: [n][128] each, zeroed by the engine at episode start       */
+    float *h, *c;               /* QNetRNN only, 128 floats per env each, zeroed by the engine at episode start.  PP_PREC_F32:
+                                 * unit-major [128][n].  PP_PREC_F16: blocked by warp, [ceil(n / 32)][32][32][4] — unit u of
+                                 * env i at ((i / 32 * 32 + u / 4) * 32 + i % 32) * 4 + u % 4                            */
 } PPPolicy;
 
 /* QNet blob (floats): effective weights (eval: mu, train: mu + sigma*eps — models/qnet.py:43-50),

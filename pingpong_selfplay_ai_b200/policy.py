@@ -246,9 +246,11 @@ class Policy:
         if kind == _lib.POLICY_QNETRNN:
             if num_envs is None:
                 raise ValueError("QNetRNN players carry per-env (h, c): pass num_envs")
-            # fp32 path: unit-major [128, n] (coalesced along the env index); tensor-core path: env-major [n, 128]
-            # (a thread streams its own 512-byte row).  `hidden()` returns either as [n, 128].
-            shape = (num_envs, 128) if self.precision == _lib.PREC_F16 else (128, num_envs)
+            # fp32 path: unit-major [128, n] (coalesced along the env index); tensor-core path: blocked by warp,
+            # [ceil(n / 32)][32 unit groups][32 envs][4] (a warp's accesses are contiguous 512-byte runs).  `hidden()`
+            # returns either as [n, 128].
+            self.num_envs = int(num_envs)
+            shape = ((num_envs + 31) // 32, 32, 32, 4) if self.precision == _lib.PREC_F16 else (128, num_envs)
             self.h = torch.zeros(*shape, dtype=torch.float32, device=self.device)
             self.c = torch.zeros(*shape, dtype=torch.float32, device=self.device)
 
@@ -277,7 +279,10 @@ class Policy:
         """(h, c) as [num_envs, 128] views, whatever the storage layout of the precision path."""
         if self.h is None:
             return None, None
-        return (self.h, self.c) if self.precision == _lib.PREC_F16 else (self.h.t(), self.c.t())
+        if self.precision == _lib.PREC_F16:
+            unblock = lambda t: t.permute(0, 2, 1, 3).reshape(-1, 128)[:self.num_envs]
+            return unblock(self.h), unblock(self.c)
+        return self.h.t(), self.c.t()
 
     def set_weights(self, blob):
         self.weights.copy_(blob.to(self.weights.device, torch.float32), non_blocking=True)
