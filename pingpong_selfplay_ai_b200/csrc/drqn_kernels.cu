@@ -729,10 +729,10 @@ pack_qnetrnn_tc_kernel(const PPQNetRNNParams p, int noisy, const PackPlan plan, 
             const int kk = e & 7, n = (e >> 3) % t.cols, kc = e / (8 * t.cols), k = kc * 8 + kk;     // e is the half index in the tile
             const int col = t.mat == 2 ? (n / 32) * HID + 32 * t.quarter + (n % 32) : n;
             __half v = __float2half_rn(0.0f);
-            if (t.kind == 0) v = hi_of(mat_at(p, noisy, t.mat, t.k0 + k, col));
-            else if (t.kind == 1) v = lo_of(mat_at(p, noisy, t.mat, t.k0 + k, col));
+            const bool real = t.mat != 4 || n < 4;             // heads: columns 4..15 are padding (nothing to read there)
+            if (t.kind == 0) { if (real) v = hi_of(mat_at(p, noisy, t.mat, t.k0 + k, col)); }
+            else if (t.kind == 1) { if (real) v = lo_of(mat_at(p, noisy, t.mat, t.k0 + k, col)); }
             else if (t.kind == 2) {
-                const bool real = t.mat != 4 || n < 4;
                 if (k == 7 && real) v = hi_of(bias_at(p, noisy, t.mat, col));
                 else if (k == 15 && real) v = lo_of(bias_at(p, noisy, t.mat, col));
             } else if (t.kind == 3) {                          // rows 0..6 and 8..14: hi(W1^T); row 7: hi(b1); row 15: lo(b1)
@@ -741,7 +741,6 @@ pack_qnetrnn_tc_kernel(const PPQNetRNNParams p, int noisy, const PackPlan plan, 
             } else {                                           // rows 0..6: lo(W1^T)
                 if (k < 7) v = lo_of(mat_at(p, noisy, 0, k, n));
             }
-            if (t.mat == 4 && t.kind < 2 && n >= 4) v = __float2half_rn(0.0f);        // heads: columns 4..15 are padding
             out[e] = v;
         }
     }

@@ -19,6 +19,8 @@
 // rounded gate weights alone the reference's trained checkpoint drifts to 1.3e-3 relative after 12 carried steps).
 // The 640 KB weight image is what L2 has to deliver to every SM on every player-step.  sigmoid / tanh use ex2.approx +
 // rcp.approx (error ~1e-6, far inside the 1e-3 budget).
+#include <cstdio>
+#include <cstdlib>
 #include "pp_host.h"
 #include "pp_rollout.cuh"
 #include "tc_tiles.cuh"
@@ -74,13 +76,17 @@ struct Issuer {
     uint32_t ready_par, dfree_par;
     bool leader;                   // ALL lanes of the issuer warp run the program (uniform control flow keeps counters and
                                    // descriptors in uniform registers); only the leader lane executes the TMA / MMA / commit
+    bool pair;                     // the CTA shares its weight stream with its cluster peer: a slot is free once BOTH have read it
 
     __device__ __forceinline__ uint32_t acquire() {     // shared-memory address of the next stage, landed (Producer sent it)
         { RT_T0(t_); tc::mbar_wait(bars + B_FULL + c_slot, (uint32_t)c_round); if (leader) RT_ADD(3, t_); }
         return tc::smem_u32(smem + SM_RING + c_slot * RT_SLOT);
     }
     __device__ __forceinline__ void release() {         // the slot is free once the MMAs issued so far have read it
-        if (leader) tc::umma_commit(bars + B_EMPTY + c_slot);
+        if (leader) {
+            if (pair) tc::umma_commit_multicast(bars + B_EMPTY + c_slot, 3);
+            else tc::umma_commit(bars + B_EMPTY + c_slot);
+        }
         if (++c_slot == (int)RT_SLOTS) { c_slot = 0; c_round ^= 1; }
     }
     __device__ __forceinline__ void wait_ready() {
@@ -103,6 +109,8 @@ struct Producer {
     uint64_t *bars;
     int slot, round;
     bool leader;
+    int pair_rank;                 // < 0: alone; 0 / 1: this CTA loads that HALF of every stage and multicasts it to both CTAs of
+                                   // the cluster (each SM then pulls half the image from L2 per player-step)
     __device__ __forceinline__ void player_step(const uint8_t *img) {
 #pragma unroll 1
         for (int st = 0; st < PP_RNNTC_STAGES; ++st) {
@@ -110,8 +118,13 @@ struct Producer {
             uint32_t off, bytes;
             stage_info(st, off, bytes);
             if (leader) {
-                tc::mbar_expect_tx(bars + B_FULL + slot, bytes);
-                tc::tma_bulk_g2s(smem + SM_RING + slot * RT_SLOT, img + off, bytes, bars + B_FULL + slot);
+                tc::mbar_expect_tx(bars + B_FULL + slot, bytes);        // both halves land on this barrier
+                if (pair_rank < 0) {
+                    tc::tma_bulk_g2s(smem + SM_RING + slot * RT_SLOT, img + off, bytes, bars + B_FULL + slot);
+                } else {
+                    const uint32_t half = bytes >> 1, at = (uint32_t)pair_rank * half;
+                    tc::tma_bulk_g2s_multicast(smem + SM_RING + slot * RT_SLOT + at, img + off + at, half, bars + B_FULL + slot, 3);
+                }
             }
             if (++slot == (int)RT_SLOTS) { slot = 0; round ^= 1; }
         }
@@ -410,11 +423,11 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
     dueling_q(tm + T_D1, q);
 }
 
-__device__ __forceinline__ uint32_t rnn_tc_prologue(uint8_t *smem, int warp_id) {
+__device__ __forceinline__ uint32_t rnn_tc_prologue(uint8_t *smem, int warp_id, bool pair = false) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_CTRL);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_CTRL + CTRL_TMEM);
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < RT_SLOTS; ++s) { tc::mbar_init(bars + B_FULL + s, 1); tc::mbar_init(bars + B_EMPTY + s, 1); }
+        for (uint32_t s = 0; s < RT_SLOTS; ++s) { tc::mbar_init(bars + B_FULL + s, 1); tc::mbar_init(bars + B_EMPTY + s, pair ? 2 : 1); }
         tc::mbar_init(bars + B_READY, RT_WORKERS);
         tc::mbar_init(bars + B_DONE, 1); tc::mbar_init(bars + B_DONE + 1, 1);
         tc::mbar_init(bars + B_DFREE, RT_WORKERS); tc::mbar_init(bars + B_DFREE + 1, RT_WORKERS);
@@ -424,6 +437,7 @@ __device__ __forceinline__ uint32_t rnn_tc_prologue(uint8_t *smem, int warp_id) 
     if (warp_id == RT_ISSUER_WARP) tc::tmem_alloc<512>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
+    if (pair) tc::cluster_sync_all();                   // the peer's barriers exist before anything is multicast to them
     tc::tc_fence_after();
     return __shfl_sync(0xffffffffu, *tmem_slot, 0);
 }
@@ -443,7 +457,7 @@ qnetrnn_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy p
     int64_t my_tiles = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) ++my_tiles;
     if (warp_id == RT_ISSUER_WARP) {
-        Issuer is{smem, bars, tm, 0, 0, 0u, 0u, tc::elect_one()};
+        Issuer is{smem, bars, tm, 0, 0, 0u, 0u, tc::elect_one(), false};
         for (int64_t t = 0; t < my_tiles; ++t) {
             RT_T0(t_);
             issue_player_step(is);
@@ -451,7 +465,7 @@ qnetrnn_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy p
         }
         __syncwarp();
     } else if (warp_id == RT_PRODUCER_WARP) {
-        Producer pr{smem, bars, 0, 0, tc::elect_one()};
+        Producer pr{smem, bars, 0, 0, tc::elect_one(), -1};
         for (int64_t t = 0; t < my_tiles; ++t) pr.player_step(reinterpret_cast<const uint8_t *>(pol.weights));
         __syncwarp();
     } else {
@@ -490,14 +504,16 @@ qnetrnn_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy p
 // of scripts/train_rnn_iterative.py:732-780 on the tensor cores.  Env state lives in the registers of the row's first
 // thread; (h, c) are env-major in global memory and zeroed at every episode start.  The launch is cut into chunks of at
 // most 4 warps of envs, balanced to within one warp, a whole number of rounds over the SMs.
-template <typename R>
+// PAIR: launched as clusters of two CTAs that run the same stage sequence (no quota, equal chunk counts) and share ONE weight
+// stream: each loads half of every stage and multicasts it to both.
+template <typename R, bool PAIR>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_steps, const PPPolicy pol_a,
                        const PPPolicy pol_b, uint64_t seed, int64_t step_base, const PPServeSource src, int32_t quota,
                        int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const uint32_t tm = rnn_tc_prologue(smem, warp_id);
+    const uint32_t tm = rnn_tc_prologue(smem, warp_id, PAIR);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_CTRL);
     volatile uint32_t *stop_flag = reinterpret_cast<volatile uint32_t *>(smem + SM_CTRL + CTRL_STOP);
     volatile uint8_t *row_fresh = smem + SM_FLAGS, *row_live = smem + SM_FLAGS + RT_ROWS;
@@ -506,8 +522,8 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
 
     if (warp_id == RT_ISSUER_WARP || warp_id == RT_PRODUCER_WARP) {
         const bool producer = warp_id == RT_PRODUCER_WARP;                      // both follow the same step protocol
-        Issuer is{smem, bars, tm, 0, 0, 0u, 0u, tc::elect_one()};
-        Producer pr{smem, bars, 0, 0, is.leader};
+        Issuer is{smem, bars, tm, 0, 0, 0u, 0u, tc::elect_one(), PAIR};
+        Producer pr{smem, bars, 0, 0, is.leader, PAIR ? (int)tc::cluster_cta_rank() : -1};
         uint32_t step_par = 0;
 #pragma unroll 1
         for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
@@ -602,6 +618,7 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (PAIR) tc::cluster_sync_all();                   // no CTA leaves while its peer may still signal its barriers
     if (warp_id == RT_ISSUER_WARP) tc::tmem_dealloc<512>(tm);
 }
 
@@ -636,24 +653,67 @@ int qnetrnn_act_tc_launch(int64_t n, const float *obs, const PPPolicy &pol, cons
     return (int)cudaGetLastError();
 }
 
+// CTAs that can be co-resident as clusters of two (one CTA per SM; a GPC with an odd SM count leaves one out); 0 = no pairs
+template <typename R> static int rt_pair_slots() {
+    static int slots = -1;
+    if (slots < 0) {
+        slots = 0;
+        const char *off = getenv("PP_RNN_PAIR");
+        if (!(off && off[0] == '0') &&
+            cudaFuncSetAttribute(selfplay_rnn_tc_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL) == cudaSuccess) {
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute at{};
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            cfg.gridDim = dim3((unsigned)(rt_sm_count() & ~1)); cfg.blockDim = dim3(RT_THREADS); cfg.dynamicSmemBytes = SM_TOTAL;
+            cfg.attrs = &at; cfg.numAttrs = 1;
+            int clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&clusters, selfplay_rnn_tc_kernel<R, true>, &cfg) == cudaSuccess) slots = 2 * clusters;
+            else (void)cudaGetLastError();
+        }
+#ifdef PP_TC_TIMING
+        printf("[rnn-tc] paired slots: %d of %d SMs\n", slots, rt_sm_count());
+#endif
+    }
+    return slots;
+}
+
+template <typename R>
+static int selfplay_rnn_tc_launch_t(int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa, const PPPolicy &pb,
+                                    uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota, int64_t env_id_base,
+                                    const PPRolloutOut &out, const PPReplayRing &r, cudaStream_t stream) {
+    const int64_t total_warps = (n + 31) / 32;
+    cudaError_t err;
+    // paired form: every CTA must run the same number of full chunks (no quota freezes a tile, no ragged last round), and
+    // leaving a few SMs unpaired must cost less than the shared stream gains
+    const int64_t pslots = rt_pair_slots<R>();
+    if (quota <= 0 && pslots >= rt_sm_count() - 8 && total_warps >= pslots * 4) {
+        const int64_t n_chunks = ((total_warps + pslots * 4 - 1) / (pslots * 4)) * pslots;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)pslots); cfg.blockDim = dim3(RT_THREADS); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = stream;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, selfplay_rnn_tc_kernel<R, true>, p, st, n, k, pa, pb, seed, step_base, src, quota,
+                                       env_id_base, out, r, n_chunks);
+    }
+    const int64_t slots = rt_sm_count();
+    int64_t n_chunks = (total_warps + 3) / 4;                                   // tiles of <= 4 warps ...
+    if (n_chunks > slots) n_chunks = ((total_warps + slots * 4 - 1) / (slots * 4)) * slots;   // ... a whole number of rounds
+    const unsigned blocks = (unsigned)(n_chunks < slots ? n_chunks : slots);
+    if ((err = cudaFuncSetAttribute(selfplay_rnn_tc_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL)) != cudaSuccess) return (int)err;
+    selfplay_rnn_tc_kernel<R, false><<<blocks, RT_THREADS, SM_TOTAL, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota, env_id_base, out, r, n_chunks);
+    return (int)cudaGetLastError();
+}
+
 int selfplay_rnn_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
                            const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
                            int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream) {
     PPReplayRing r{};
     if (ring) r = *ring;
-    const int64_t total_warps = (n + 31) / 32, slots = rt_sm_count();
-    int64_t n_chunks = (total_warps + 3) / 4;                                   // tiles of <= 4 warps ...
-    if (n_chunks > slots) n_chunks = ((total_warps + slots * 4 - 1) / (slots * 4)) * slots;   // ... a whole number of rounds
-    const unsigned blocks = (unsigned)(n_chunks < slots ? n_chunks : slots);
-    cudaError_t err;
-    if (mode == PP_MODE_F64) {
-        if ((err = cudaFuncSetAttribute(selfplay_rnn_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL)) != cudaSuccess) return (int)err;
-        selfplay_rnn_tc_kernel<double><<<blocks, RT_THREADS, SM_TOTAL, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota, env_id_base, out, r, n_chunks);
-    } else {
-        if ((err = cudaFuncSetAttribute(selfplay_rnn_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL)) != cudaSuccess) return (int)err;
-        selfplay_rnn_tc_kernel<float><<<blocks, RT_THREADS, SM_TOTAL, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota, env_id_base, out, r, n_chunks);
-    }
-    return (int)cudaGetLastError();
+    return mode == PP_MODE_F64 ? selfplay_rnn_tc_launch_t<double>(n, k, p, st, pa, pb, seed, step_base, src, quota, env_id_base, out, r, stream)
+                               : selfplay_rnn_tc_launch_t<float>(n, k, p, st, pa, pb, seed, step_base, src, quota, env_id_base, out, r, stream);
 }
 
 }  // namespace pp

@@ -66,6 +66,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same copy delivered to the SAME shared-memory offset of every CTA of the cluster named in cta_mask; each destination's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_bulk_g2s_multicast(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // ---------------------------------------------------------------- TMEM
 template <uint32_t COLS> __device__ __forceinline__ void tmem_alloc(uint32_t *smem_result) {      // one full warp
@@ -133,6 +147,11 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // all MMAs issued so far by this thread arrive on `bar` when they have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ... arriving on the mbarrier at the same offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
 // two fp32 -> packed fp16x2 (lo = a, hi = b), round-to-nearest, saturating to +-65504; RELU clamps negatives to 0

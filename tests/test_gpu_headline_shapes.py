@@ -220,3 +220,43 @@ def test_recurrent_tensor_core_rollout_at_config4_shape():
     for side, pol in enumerate((pa, pb)):
         assert np.abs(gu.np_of(pol.hidden()[0])[sub][keep] - hc[side][0][keep]).max() < 1e-3
         assert np.abs(gu.np_of(pol.hidden()[1])[sub][keep] - hc[side][1][keep]).max() < 1e-3
+
+
+_PAIR_SCRIPT = r"""
+import hashlib, sys
+import numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import pingpong_selfplay_ai_b200 as pp
+cfg = eval(sys.argv[2])
+n = int(sys.argv[3])
+torch.manual_seed(0); net_a = pp.QNetRNN()
+torch.manual_seed(1); net_b = pp.QNetRNN()
+env = pp.VecPongEnv2P(n, mode="f64", serve="philox", seed=11, **cfg)
+env.reset()
+pa = pp.Policy.qnetrnn(net_a, num_envs=n, precision="f16")
+pb = pp.Policy.qnetrnn(net_b, num_envs=n, precision="f16")
+eng = pp.SelfPlayEngine(env, pa, pb, seed=5)
+h = hashlib.sha256()
+for k in (7, 18):
+    h.update(eng.run(k, want_actions=True)["actions"].cpu().numpy().tobytes())
+for t in (env._real[:, :n].contiguous(), env._int[:, :n].contiguous(), env.counters, pa.hidden()[0], pa.hidden()[1], pb.hidden()[0], pb.hidden()[1]):
+    h.update(t.cpu().numpy().tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_recurrent_rollout_with_a_shared_weight_stream_equals_the_unpaired_kernel():
+    """Above 148 x 4 warps of envs the recurrent kernel runs as clusters of two CTAs that multicast half of every weight
+    stage to each other (lstm_tc_kernels.cu, PAIR); PP_RNN_PAIR=0 selects the one-CTA form.  Same arithmetic, so the action
+    stream, the env state and both players' (h, c) are bit-identical — and a ragged n (whole rounds of unequal chunks)
+    must not deadlock the pair."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for pair in ("1", "0"):
+        env = dict(os.environ, PP_RNN_PAIR=pair)
+        r = subprocess.run([sys.executable, "-c", _PAIR_SCRIPT, root, repr(BENCH_ENV_CFG), "40001"], env=env, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[pair] = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    assert digests["1"] == digests["0"]
