@@ -1,10 +1,11 @@
 // lstm_tc_kernels.cu — K2b on the tensor cores: one QNetRNN step (models/qnet_rnn.py:107-144, seq_len 1) for a
 // 128-env tile per CTA, every layer a tcgen05.mma batch with fp32 accumulation in TMEM (PP_PREC_F16).
 //
-// Roles: 4 compute warps (thread = env = TMEM lane) + 1 issuer warp whose elected lane streams the weight image
-// PP_RNNTC_* from L2 through a 4-slot shared-memory ring with TMA bulk copies AND issues every MMA.  The two sides
-// meet only at mbarriers:  ready (128 arrivals: "my operand rows are written"), done[2] (tcgen05.commit: "accumulator
-// buffer b is complete"), dfree[2] (128 arrivals: "buffer b has been drained").
+// Roles: 8 compute warps (two threads per env = TMEM lane) + 1 issuer warp whose elected lane issues every MMA + 1 producer
+// warp that streams the weight image PP_RNNTC_* from L2 through a 4-slot shared-memory ring with TMA bulk copies (in the
+// paired form two CTAs of a cluster load half a stage each and multicast it).  The sides meet only at mbarriers:  ready
+// (256 arrivals: "my operand rows are written"), done[2] (tcgen05.commit: "accumulator buffer b is complete"), dfree[2]
+// (256 arrivals: "buffer b has been drained"), full / empty per ring slot.
 //
 // Tensor memory (all 512 columns of the SM):
 //     [  0,128) A_hi   gate operand [f2 | h_prev] (fp16 pairs), later the shared-head output s      (K = 256)
@@ -29,8 +30,10 @@ namespace pp {
 
 #ifdef PP_TC_TIMING
 // debug build: cycles per phase, summed over the launch.  issuer: 0 player-steps 1 wait_ready 2 fill(empty) 3 full wait
-// 4 wait_dfree 5 total;  worker (thread 0): 8 wait_done 9 h staging 10 cell 11 relu_split 12 total
-__device__ unsigned long long g_rt_timing[16];
+// 4 wait_dfree 5 total;  worker (thread 0): 8 wait_done 9 h staging 10 cell 12 total 13 env step 14 cell ld 15 cell math
+// 16.. wait_done by hand-off (L1, features.2, quarters 0..3, shared head, dueling heads).  Two more experiment switches
+// (wrong results, timing only): PP_RT_NOCELL drops the cell arithmetic, PP_RT_HALFBYTES fetches half of every weight stage.
+__device__ unsigned long long g_rt_timing[32];
 #define RT_T0(v) long long v = clock64()
 #define RT_ADD(slot, since) atomicAdd(&g_rt_timing[slot], (unsigned long long)(clock64() - (since)))
 #else
@@ -46,9 +49,10 @@ constexpr int RT_ROWS = 128, RT_HALVES = 2, RT_WORKERS = RT_ROWS * RT_HALVES, RT
 constexpr uint32_t RT_SLOTS = 4, RT_SLOT = PP_RNNTC_SLOT_BYTES;
 constexpr uint32_t SM_RING = 0, SM_HNEW = SM_RING + RT_SLOTS * RT_SLOT, SM_HNEW_LO = SM_HNEW + 32768,
                    SM_X = SM_HNEW + 65536, SM_CTRL = SM_X + 4096, SM_FLAGS = SM_CTRL + 128, SM_TOTAL = SM_FLAGS + 2 * RT_ROWS;
-// control block: full[4] empty[4] ready done[2] dfree[2] step (14 mbarriers), TMEM base, stop flag; then per-row flags
-constexpr uint32_t B_FULL = 0, B_EMPTY = 4, B_READY = 8, B_DONE = 9, B_DFREE = 11, B_STEP = 13, CTRL_TMEM = 14 * 8,
-                   CTRL_STOP = 14 * 8 + 4;
+// control block: full[] empty[] ready done[2] dfree[2] step (mbarriers), TMEM base, stop flag; then per-row flags
+constexpr uint32_t B_FULL = 0, B_EMPTY = RT_SLOTS, B_READY = 2 * RT_SLOTS, B_DONE = B_READY + 1, B_DFREE = B_DONE + 2,
+                   B_STEP = B_DFREE + 2, CTRL_TMEM = (B_STEP + 1) * 8, CTRL_STOP = CTRL_TMEM + 4;
+static_assert(CTRL_STOP + 4 <= 128, "control block");
 // TMEM columns
 constexpr uint32_t T_AHI = 0, T_ALO = 128, T_D0 = 256, T_D1 = 384, T_FHI = 384, T_FLO = 416;
 
@@ -117,6 +121,9 @@ struct Producer {
             tc::mbar_wait(bars + B_EMPTY + slot, (uint32_t)(round ^ 1));       // first round passes at once
             uint32_t off, bytes;
             stage_info(st, off, bytes);
+#ifdef PP_RT_HALFBYTES
+            bytes >>= 1;
+#endif
             if (leader) {
                 tc::mbar_expect_tx(bars + B_FULL + slot, bytes);        // both halves land on this barrier
                 if (pair_rank < 0) {
@@ -244,8 +251,8 @@ struct Worker {
         tc::tc_fence_before();
         tc::mbar_arrive(bars + B_READY);
     }
-    __device__ __forceinline__ void wait_done(int b) {
-        { RT_T0(t_); tc::mbar_wait(bars + B_DONE + b, (done_par >> b) & 1u); if (row == 0 && half == 0) RT_ADD(8, t_); }
+    __device__ __forceinline__ void wait_done(int b, int site = 0) {     // site: which hand-off (phase timers only)
+        { RT_T0(t_); tc::mbar_wait(bars + B_DONE + b, (done_par >> b) & 1u); if (row == 0 && half == 0) { RT_ADD(8, t_); RT_ADD(16 + site, t_); } }
         done_par ^= 1u << b;
         tc::tc_fence_after();
     }
@@ -289,6 +296,9 @@ template <int NCOLS> __device__ __forceinline__ void relu_split_to_tmem(uint32_t
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void lstm_cell(float gi, float gf, float gg, float go, float c_prev, float &c_new, float &h_new) {
+#ifdef PP_RT_NOCELL
+    c_new = gi + gf + c_prev; h_new = gg + go; return;
+#endif
     constexpr float NL2E = -1.4426950408889634f;                       // e^-x = 2^(-x log2 e)
     auto a1 = [](float scaled) { return 1.0f + ex2_approx(fminf(scaled, 60.0f)); };
     const float ai = a1(gi * NL2E), af = a1(gf * NL2E), ao = a1(go * NL2E), ag = a1(gg * (2.0f * NL2E));
@@ -351,11 +361,11 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
     if (row == 0 && half == 0) RT_ADD(9, th_);
     w.publish(true);
     // ---- F1
-    w.wait_done(0);
+    w.wait_done(0, 0);
     relu_split_to_tmem<64>(tm + T_D0, tm + T_FHI, tm + T_FLO, half);
     w.publish(false);
     // ---- f2 -> A columns 0..63
-    w.wait_done(0);
+    w.wait_done(0, 1);
     relu_split_to_tmem<128>(tm + T_D0, tm + T_AHI, tm + T_ALO, half);
     w.publish(false);
     // ---- LSTM cell, quarter by quarter (i, f, g, o at columns 0, 32, 64, 96 of the buffer; 8 units per sub-block, the
@@ -372,7 +382,7 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
             cp[2 * sb] = carry ? cs4[at4(qt * 8 + 2 * b)] : zero4;
             cp[2 * sb + 1] = carry ? cs4[at4(qt * 8 + 2 * b + 1)] : zero4;
         }
-        w.wait_done(qt & 1);
+        w.wait_done(qt & 1, 2 + qt);
         const uint32_t d = tm + ((qt & 1) ? T_D1 : T_D0);
         RT_T0(tc_);
 #pragma unroll
@@ -415,11 +425,11 @@ __device__ __forceinline__ void compute_player_step(Worker &w, const float (&obs
     }
     w.publish(true);
     // ---- shared head -> s into A columns 0..63
-    w.wait_done(0);
+    w.wait_done(0, 6);
     relu_split_to_tmem<128>(tm + T_D0, tm + T_AHI, tm + T_ALO, half);
     w.publish(false);
     // ---- Q
-    w.wait_done(1);
+    w.wait_done(1, 7);
     dueling_q(tm + T_D1, q);
 }
 
@@ -623,10 +633,10 @@ selfplay_rnn_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, in
 }
 
 #ifdef PP_TC_TIMING
-extern "C" int pp_debug_rt_timing(unsigned long long *host16, int reset) {
+extern "C" int pp_debug_rt_timing(unsigned long long *host32, int reset) {
     cudaDeviceSynchronize();
-    cudaError_t e = cudaMemcpyFromSymbol(host16, g_rt_timing, sizeof(g_rt_timing));
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_rt_timing, z, sizeof z); }
+    cudaError_t e = cudaMemcpyFromSymbol(host32, g_rt_timing, sizeof(g_rt_timing));
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_rt_timing, z, sizeof z); }
     return (int)e;
 }
 #endif
