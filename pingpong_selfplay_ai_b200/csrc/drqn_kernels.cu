@@ -381,8 +381,11 @@ lstm_bwd_kernel(const PPQNetRNNParams on, int B, int L, const float *__restrict_
         sm.w[c][k] = on.w_hh[(int64_t)((c / UPC) * HID + r * UPC + (c % UPC)) * HID + k];
     }
     const int row = tid / 16, u = tid % 16, unit = r * UPC + u, b = tile * BT + row;       // cell part
-    const int wc = tid / 4, wk0 = (tid % 4) * 32;                                           // dW_hh part: column wc, 32 k's
-    const int pk0 = (tid % 16) * 8;                                                          // partial-dh part: window row, 8 k's
+    // dW_hh part: column wc, 32 k's as eight float4 groups INTERLEAVED over the four threads of a column (k = 16 i + 4 wq ..
+    // + 3): the four threads of a quad read 64 contiguous bytes of h_{t-1} (a 128-byte stride put them all on one bank)
+    const int wc = tid / 4, wq = tid % 4;
+    // partial-dh part: window row, k = 4 pj .. + 3 and 64 + 4 pj .. + 3: 16 threads read 256 contiguous bytes of a W_hh row
+    const int pj = tid % 16;
     float dwhh[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) dwhh[i] = 0.0f;
@@ -413,22 +416,22 @@ lstm_bwd_kernel(const PPQNetRNNParams on, int B, int L, const float *__restrict_
                 const float a = sm.da[rr][wc];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 h4 = *reinterpret_cast<const float4 *>(&sm.hprev[rr][wk0 + i]);
+                    const float4 h4 = *reinterpret_cast<const float4 *>(&sm.hprev[rr][4 * i + 4 * wq]);
                     dwhh[i] = fmaf(a, h4.x, dwhh[i]); dwhh[i + 1] = fmaf(a, h4.y, dwhh[i + 1]);
                     dwhh[i + 2] = fmaf(a, h4.z, dwhh[i + 2]); dwhh[i + 3] = fmaf(a, h4.w, dwhh[i + 3]);
                 }
             }
-            float p[8] = {};                                                     // partial dh_{t-1}[row][pk0..+8) over this CTA's columns
+            float p[8] = {};                                                     // partial dh_{t-1}[row][this thread's 8 k's] over this CTA's columns
 #pragma unroll 4
             for (int c = 0; c < CPC; ++c) {
                 const float a = sm.da[row][c];
-                const float4 w0 = *reinterpret_cast<const float4 *>(&sm.w[c][pk0]), w1 = *reinterpret_cast<const float4 *>(&sm.w[c][pk0 + 4]);
+                const float4 w0 = *reinterpret_cast<const float4 *>(&sm.w[c][4 * pj]), w1 = *reinterpret_cast<const float4 *>(&sm.w[c][64 + 4 * pj]);
                 p[0] = fmaf(a, w0.x, p[0]); p[1] = fmaf(a, w0.y, p[1]); p[2] = fmaf(a, w0.z, p[2]); p[3] = fmaf(a, w0.w, p[3]);
                 p[4] = fmaf(a, w1.x, p[4]); p[5] = fmaf(a, w1.y, p[5]); p[6] = fmaf(a, w1.z, p[6]); p[7] = fmaf(a, w1.w, p[7]);
             }
-            float *mine = &sm.part[t & 1][row][pk0];
+            float *mine = &sm.part[t & 1][row][4 * pj];
             *reinterpret_cast<float4 *>(mine) = make_float4(p[0], p[1], p[2], p[3]);
-            *reinterpret_cast<float4 *>(mine + 4) = make_float4(p[4], p[5], p[6], p[7]);
+            *reinterpret_cast<float4 *>(mine + 64) = make_float4(p[4], p[5], p[6], p[7]);
             cluster.sync();                                                      // every CTA's partial of this step is in place
             float acc = 0.0f;
 #pragma unroll
@@ -440,9 +443,10 @@ lstm_bwd_kernel(const PPQNetRNNParams on, int B, int L, const float *__restrict_
         }
         __syncthreads();                                                         // da / hprev are rewritten by the next step
     }
-    float *out = ws_dwhh_part + ((int64_t)tile * GATES + (wc / UPC) * HID + r * UPC + (wc % UPC)) * HID + wk0;
+    float *out = ws_dwhh_part + ((int64_t)tile * GATES + (wc / UPC) * HID + r * UPC + (wc % UPC)) * HID;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) out[i] = dwhh[i];
+    for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4 *>(out + 4 * i + 4 * wq) = make_float4(dwhh[i], dwhh[i + 1], dwhh[i + 2], dwhh[i + 3]);
     cluster.sync();                                                              // nobody leaves while peers may still read its partials
 }
 
