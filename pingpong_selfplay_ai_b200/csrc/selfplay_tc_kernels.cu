@@ -48,6 +48,8 @@ constexpr uint32_t W1_BYTES = 2 * 64 * 16, W2_BYTES = 8 * 64 * 16, B2_BYTES = 2 
 constexpr uint32_t W1H_OFF = 0, W1L_OFF = W1H_OFF + W1_BYTES, W2H_OFF = W1L_OFF + W1_BYTES, W2L_OFF = W2H_OFF + W2_BYTES,
                    B2_OFF = W2L_OFF + W2_BYTES, W3H_OFF = B2_OFF + B2_BYTES, W3L_OFF = W3H_OFF + W3_BYTES,
                    B3_OFF = W3L_OFF + W3_BYTES, PLAYER_W_BYTES = B3_OFF + B3_BYTES;              // 27136
+constexpr uint32_t ADV_TABLE_OFF = 66 * 16;     // second fp32 head table (advantages only) behind the 65 float4 of the first
+static_assert(ADV_TABLE_OFF + 33 * 16 <= 2 * W3_BYTES + B3_BYTES, "head tables");
 constexpr uint32_t X_BYTES = 2 * G_ROWS * 16;                                                    // 4096
 constexpr uint32_t GROUP_BYTES = 2 * X_BYTES;                                                    // X rows of both players
 constexpr uint32_t TM_R1 = 64;                  // TMEM columns of a group: region R0 at +0, R1 at +64 (64 columns each)
@@ -111,6 +113,20 @@ __device__ void build_weight_tiles(uint8_t *wt, const float *blob, int tid, int 
         } else {
             const float *b = blob + PP_QNET_BH;
             ht[idx] = make_float4(b[0], b[1], b[2], b[3]);
+        }
+    }
+    // For the fused rollout, which only needs argmax_a Q_a: Q_a = V + (A_a - mean(A)) orders the actions like A_a, and
+    // three numbers are ordered by two differences, so the table holds  D01 = A0 - A1  and  D12 = A1 - A2  only: per four
+    // hidden units k0..k3 two float4 (D01[k0], D01[k1], D12[k0], D12[k1]) (D01[k2], D01[k3], D12[k2], D12[k3]); entry 32 =
+    // (bA0 - bA1, bA1 - bA2, 0, 0)
+    float4 *dt = reinterpret_cast<float4 *>(wt + W3H_OFF + ADV_TABLE_OFF);
+    for (int idx = tid; idx < 33; idx += nthreads) {
+        if (idx < 32) {
+            const float *w = blob + PP_QNET_WHT + (2 * idx) * 4;           // w[k * 4 + 1 + a] = A_a[2 idx + k]
+            dt[idx] = make_float4(__fsub_rn(w[1], w[2]), __fsub_rn(w[5], w[6]), __fsub_rn(w[2], w[3]), __fsub_rn(w[6], w[7]));
+        } else {
+            const float *b = blob + PP_QNET_BH;
+            dt[idx] = make_float4(__fsub_rn(b[1], b[2]), __fsub_rn(b[2], b[3]), 0.0f, 0.0f);
         }
     }
 }
@@ -181,6 +197,47 @@ __device__ __forceinline__ void heads_epilogue(uint32_t src, const uint8_t *tabl
     q[0] = __fadd_rn(V, __fsub_rn(A0, mean));
     q[1] = __fadd_rn(V, __fsub_rn(A1, mean));
     q[2] = __fadd_rn(V, __fsub_rn(A2, mean));
+}
+
+// The fused rollout only ever takes argmax_a Q_a.  Q_a = V + (A_a - mean(A)) orders the actions like A_a, and the order of
+// three numbers follows from two differences, so the rollout evaluates  d01 = A0 - A1  and  d12 = A1 - A2  only (difference
+// weights precomputed per launch): 128 instead of 256 FMAs and, what matters more, 32 instead of 64 broadcast LDS.128
+// per player — the head tables are the largest consumer of the shared-memory data pipe, which ncu shows 52 % busy with
+// LSU wavefronts on top of the tensor core's own 23 %.  Returned as a one-hot triple whose first-argmax is the action.
+// In fp32 this can differ from argmax Q only where two Q values are within rounding of each other.
+__device__ __forceinline__ void advantages_epilogue(uint32_t src, const uint8_t *table, float (&adv)[3]) {
+    const float4 *dt = reinterpret_cast<const float4 *>(table + ADV_TABLE_OFF);
+    const float2 z = make_float2(0.f, 0.f);
+    float2 d01[4] = {z, z, z, z}, d12[4] = {z, z, z, z};                        // eight independent FFMA2 chains
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t r0[16], r1[16];
+        tc::tmem_ld16(src + half * 32, r0);
+        tc::tmem_ld16(src + half * 32 + 16, r1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {                                          // 16 pairs of hidden units
+            const uint32_t *r = j < 8 ? r0 + 2 * j : r1 + 2 * (j - 8);
+            const float2 h = make_float2(fmaxf(__uint_as_float(r[0]), 0.0f), fmaxf(__uint_as_float(r[1]), 0.0f));
+            const float4 w = dt[half * 16 + j];
+            d01[j & 3] = __ffma2_rn(make_float2(w.x, w.y), h, d01[j & 3]);
+            d12[j & 3] = __ffma2_rn(make_float2(w.z, w.w), h, d12[j & 3]);
+        }
+    }
+    const float4 bias = dt[32];
+    const float2 s01 = __fadd2_rn(__fadd2_rn(d01[0], d01[1]), __fadd2_rn(d01[2], d01[3]));
+    const float2 s12 = __fadd2_rn(__fadd2_rn(d12[0], d12[1]), __fadd2_rn(d12[2], d12[3]));
+    const float a01 = __fadd_rn(__fadd_rn(s01.x, s01.y), bias.x), a12 = __fadd_rn(__fadd_rn(s12.x, s12.y), bias.y);
+    // first maximum, decided on the differences themselves (a sum like (A0 - A2, A1 - A2, 0) could absorb a tiny d01)
+    const float a02 = __fadd_rn(a01, a12);
+    const int pick = (a01 >= 0.0f && a02 >= 0.0f) ? 0 : (a12 >= 0.0f ? 1 : 2);
+    adv[0] = pick == 0 ? 1.0f : 0.0f;
+    adv[1] = pick == 1 ? 1.0f : 0.0f;
+    adv[2] = pick == 2 ? 1.0f : 0.0f;
+}
+template <bool FULL_Q> __device__ __forceinline__ void heads(uint32_t src, const uint8_t *table, float (&q)[3]) {
+    if (FULL_Q) heads_epilogue(src, table, q);
+    else advantages_epilogue(src, table, q);
 }
 
 // MMA batches, issued by one thread per group.  d / a_tm are TMEM addresses with lane 0.
@@ -285,6 +342,7 @@ template <int W, typename F> __device__ __forceinline__ void group_issue(GroupCt
 }
 
 // ONE QNet player p: L1 -> R0; H in place; L2 -> R1; (ReLU, fp32 heads on the CUDA cores) -> Q
+template <bool FULL_Q>
 __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles &p, float (&q)[3]) {
     group_issue<0>(g, [&] { issue_l1(g.r0, p); });
     group_wait<0>(g);
@@ -293,7 +351,7 @@ __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles
     tc::bar_sync(g.bar_id, G_ROWS);
     group_issue<1>(g, [&] { issue_l2(g.r0 + TM_R1, g.r0, p); });
     group_wait<1>(g);
-    heads_epilogue(g.r0 + TM_R1 + g.lane_addr, p.w + W3H_OFF, q);
+    heads<FULL_Q>(g.r0 + TM_R1 + g.lane_addr, p.w + W3H_OFF, q);
 }
 
 // BOTH players (the self-play hot path), two 64-column TMEM regions R0, R1 per group:
@@ -304,6 +362,7 @@ __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles
 // regions had four and four).  [A variant that also freed R1 early by sending H_B through a SHARED-MEMORY A tile, so
 // that L2_B could follow L2_A without a drain, was 7 % SLOWER: 12 SS-mode MMAs read 48 KB of A operand per group-step
 // from shared memory and the 32 KB of epilogue stores compete with the head table's LDS traffic.]
+template <bool FULL_Q>
 __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
     group_issue<0>(g, [&] { issue_l1(g.r0, g.pa); });
     PP_TICK(1);
@@ -320,7 +379,7 @@ __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3],
     PP_TICK(6);
     group_issue<0>(g, [&] { issue_l1(g.r0, g.pb); });     // no group barrier since the last commit: the OTHER completion barrier
     PP_TICK(1);
-    heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pa.w + W3H_OFF, q_a);
+    heads<FULL_Q>(g.r0 + TM_R1 + g.lane_addr, g.pa.w + W3H_OFF, q_a);
     PP_TICK(7);
     group_wait<0>(g);
     PP_TICK(2);
@@ -333,19 +392,22 @@ __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3],
     PP_TICK(5);
     group_wait<1>(g);
     PP_TICK(6);
-    heads_epilogue(g.r0 + TM_R1 + g.lane_addr, g.pb.w + W3H_OFF, q_b);
+    heads<FULL_Q>(g.r0 + TM_R1 + g.lane_addr, g.pb.w + W3H_OFF, q_b);
     PP_TICK(7);
 }
 
+// FULL_Q: the dueling Q values themselves (standalone action kernel, which can return them); otherwise only numbers
+// with the same argmax (advantages_epilogue)
+template <bool FULL_Q>
 __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
-    if (g.qa && g.qb) group_forward_both(g, q_a, q_b);
+    if (g.qa && g.qb) group_forward_both<FULL_Q>(g, q_a, q_b);
     else {
-        if (g.qa) group_forward_one(g, g.pa, q_a);
+        if (g.qa) group_forward_one<FULL_Q>(g, g.pa, q_a);
         if (g.qa && g.qb) {                    // R0 / R1 still hold the first player's operands until everyone has read them
             tc::tc_fence_before();
             tc::bar_sync(g.bar_id, G_ROWS);
         }
-        if (g.qb) group_forward_one(g, g.pb, q_b);
+        if (g.qb) group_forward_one<FULL_Q>(g, g.pb, q_b);
     }
 }
 
@@ -394,7 +456,7 @@ qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol,
         tc::tc_fence_before();
         tc::bar_sync(g.bar_id, G_ROWS);
         float q[3], unused[3];
-        group_forward(g, q, unused);
+        group_forward<true>(g, q, unused);
         if (i < n) {
             int a = argmax3(q);
             a = explore(a, pol.eps_threshold, seed, (uint32_t)(env_id_base + i), step_index, stream_id);
@@ -500,7 +562,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
             if (!tc::bar_red_or(g.bar_id, G_ROWS, active)) break;             // whole group frozen by the quota: for good
             PP_TICK(10);
             float q_a[3] = {0.f, 0.f, 0.f}, q_b[3] = {0.f, 0.f, 0.f};
-            if (qa || qb) group_forward(g, q_a, q_b);
+            if (qa || qb) group_forward<false>(g, q_a, q_b);
             int act_a, act_b;
             if (pol_a.kind == PP_POLICY_RANDOM) act_a = random_action(seed, gid, step, STREAM_ACT_A);
             else act_a = explore(qa ? argmax3(q_a) : follower_action(oa, pol_a.follower_tol), pol_a.eps_threshold, seed, gid, step, STREAM_ACT_A);
