@@ -219,7 +219,11 @@ __device__ __forceinline__ void advantages_epilogue(uint32_t src, const uint8_t 
         for (int j = 0; j < 16; ++j) {                                          // 16 pairs of hidden units
             const uint32_t *r = j < 8 ? r0 + 2 * j : r1 + 2 * (j - 8);
             const float2 h = make_float2(fmaxf(__uint_as_float(r[0]), 0.0f), fmaxf(__uint_as_float(r[1]), 0.0f));
+#ifdef PP_TC_NOLDS
+            const float4 w = make_float4(0.25f + j, 0.5f - j, 0.125f * half, 1.0f);   // experiment (wrong results): no table reads
+#else
             const float4 w = dt[half * 16 + j];
+#endif
             d01[j & 3] = __ffma2_rn(make_float2(w.x, w.y), h, d01[j & 3]);
             d12[j & 3] = __ffma2_rn(make_float2(w.z, w.w), h, d12[j & 3]);
         }
