@@ -252,7 +252,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--lockstep", type=int, default=None,
-                    help="lock-step env steps per launch (default: 16384 for the headline workload = 0.1 s per launch, so "
+                    help="lock-step env steps per launch (default: 20480 for the headline workload = 0.11 s per launch, so "
                          "that the timed region of --steps 20 is seconds of sustained load; 64 for the others)")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the config4_rnn / config5_train objects (BASELINE.json configs[3] and configs[4])")
@@ -274,7 +274,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.lockstep is None:
-        args.lockstep = 16384 if args.workload == "qnet" else 64
+        args.lockstep = 20480 if args.workload == "qnet" else 64
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
