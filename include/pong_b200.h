@@ -280,7 +280,13 @@ int pp_qnetrnn_act(int64_t n, const float *obs, const PPPolicy *policy, const ui
 
 /* k fused lock-step iterations of {act A, act B, step, replay row, auto-reset}: the inner loops of
  * scripts/train_iterative.py:171-196,238-245 and tests/arena.py:294-304.  Policies of kind QNET,
- * FOLLOWER and RANDOM; observations never leave registers.  ring may be NULL. */
+ * FOLLOWER and RANDOM; observations never leave registers.  ring may be NULL.
+ * With PP_PREC_F16 QNet players the launch is preceded, on the same stream, by a one-block kernel and a 1 KB
+ * device-to-device copy that place the players' head table in constant memory; every (device, stream) owns a table
+ * slot (16 per process; further streams read the table from shared memory instead), so launches on different
+ * streams never share one.  A launch captured into a CUDA graph keeps the slot of the stream it was captured on:
+ * do not replay it on another stream while the capture stream runs rollouts of other weights.
+ * PP_CONST_HEADS=0 in the environment selects the shared-memory table everywhere. */
 int pp_selfplay_rollout(int mode, int64_t n, int64_t k, const PPParams *params, const PPEnvState *state,
                         const PPPolicy *policy_a, const PPPolicy *policy_b, uint64_t seed, int64_t step_base,
                         const PPServeSource *serve, int32_t quota, int64_t env_id_base,

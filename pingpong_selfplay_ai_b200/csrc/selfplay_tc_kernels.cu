@@ -30,6 +30,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "pp_host.h"
 #include "pp_rollout.cuh"
@@ -80,6 +81,35 @@ struct PlayerTiles {     // shared-memory (generic) pointers of one player's ope
     uint8_t *w, *x;
 };
 
+// ---- the rollout's head table in CONSTANT memory -------------------------------------------------------------------
+// Every thread of a warp needs the same 32 float4 of difference weights per player and step.  From shared memory each
+// warp-wide broadcast load still writes 512 bytes of registers (two wavefronts of the shared-memory data pipe per
+// instruction); from constant memory the values arrive through the UNIFORM datapath (LDCU into uniform registers, which
+// FFMA2 takes as an operand): no register-file write, no load/store unit.  The tables are built per launch by
+// head_diff_kernel into a device staging array and copied into the __constant__ bank with a stream-ordered
+// device-to-device cudaMemcpyToSymbolAsync.  Two launches in flight on DIFFERENT streams must not share a table, so
+// every (device, stream) gets its own slot the first time it launches; when the slots run out a launch uses the
+// shared-memory table instead (HEADS_IN_CONST = false).  A launch captured into a CUDA graph keeps the slot of the
+// stream it was captured on.
+constexpr int HEAD_SLOTS = 16, HEAD_ENTRIES = 33;           // per player: 32 unit pairs + the bias entry
+__constant__ float4 c_head_diff[HEAD_SLOTS][2][HEAD_ENTRIES];
+__device__ float4 g_head_diff_staging[HEAD_SLOTS][2][HEAD_ENTRIES];
+
+// entry kk < 32: (D01[2 kk], D01[2 kk + 1], D12[2 kk], D12[2 kk + 1]) with D01 = A0 - A1, D12 = A1 - A2; entry 32: biases
+__device__ __forceinline__ float4 head_diff_entry(const float *blob, int idx) {
+    if (idx < 32) {
+        const float *w = blob + PP_QNET_WHT + (2 * idx) * 4;             // w[k * 4 + 1 + a] = A_a[2 idx + k]
+        return make_float4(__fsub_rn(w[1], w[2]), __fsub_rn(w[5], w[6]), __fsub_rn(w[2], w[3]), __fsub_rn(w[6], w[7]));
+    }
+    const float *b = blob + PP_QNET_BH;
+    return make_float4(__fsub_rn(b[1], b[2]), __fsub_rn(b[2], b[3]), 0.0f, 0.0f);
+}
+__global__ void head_diff_kernel(const float *blob_a, const float *blob_b, int slot) {
+    const int player = threadIdx.x / 64, idx = threadIdx.x % 64;
+    const float *blob = player ? blob_b : blob_a;
+    if (idx < HEAD_ENTRIES && blob) g_head_diff_staging[slot][player][idx] = head_diff_entry(blob, idx);
+}
+
 // fp32 blob (staging) -> fp16 hi / lo B-operand tiles of one player.  All threads of the CTA.
 __device__ void build_weight_tiles(uint8_t *wt, const float *blob, int tid, int nthreads) {
     auto H = [&](uint32_t off) { return reinterpret_cast<__half *>(wt + off); };
@@ -120,15 +150,7 @@ __device__ void build_weight_tiles(uint8_t *wt, const float *blob, int tid, int 
     // hidden units k0..k3 two float4 (D01[k0], D01[k1], D12[k0], D12[k1]) (D01[k2], D01[k3], D12[k2], D12[k3]); entry 32 =
     // (bA0 - bA1, bA1 - bA2, 0, 0)
     float4 *dt = reinterpret_cast<float4 *>(wt + W3H_OFF + ADV_TABLE_OFF);
-    for (int idx = tid; idx < 33; idx += nthreads) {
-        if (idx < 32) {
-            const float *w = blob + PP_QNET_WHT + (2 * idx) * 4;           // w[k * 4 + 1 + a] = A_a[2 idx + k]
-            dt[idx] = make_float4(__fsub_rn(w[1], w[2]), __fsub_rn(w[5], w[6]), __fsub_rn(w[2], w[3]), __fsub_rn(w[6], w[7]));
-        } else {
-            const float *b = blob + PP_QNET_BH;
-            dt[idx] = make_float4(__fsub_rn(b[1], b[2]), __fsub_rn(b[2], b[3]), 0.0f, 0.0f);
-        }
-    }
+    for (int idx = tid; idx < 33; idx += nthreads) dt[idx] = head_diff_entry(blob, idx);
 }
 
 // 32 accumulator values -> ReLU -> packed fp16 hi pairs and lo pairs.  hi = rz(relu(x)) <= relu(x), so for x >= 0 the
@@ -205,7 +227,8 @@ __device__ __forceinline__ void heads_epilogue(uint32_t src, const uint8_t *tabl
 // per player — the head tables are the largest consumer of the shared-memory data pipe, which ncu shows 52 % busy with
 // LSU wavefronts on top of the tensor core's own 23 %.  Returned as a one-hot triple whose first-argmax is the action.
 // In fp32 this can differ from argmax Q only where two Q values are within rounding of each other.
-__device__ __forceinline__ void advantages_epilogue(uint32_t src, const uint8_t *table, float (&adv)[3]) {
+template <bool HEADS_IN_CONST>
+__device__ __forceinline__ void advantages_epilogue(uint32_t src, const uint8_t *table, int cslot, int player, float (&adv)[3]) {
     const float4 *dt = reinterpret_cast<const float4 *>(table + ADV_TABLE_OFF);
     const float2 z = make_float2(0.f, 0.f);
     float2 d01[4] = {z, z, z, z}, d12[4] = {z, z, z, z};                        // eight independent FFMA2 chains
@@ -222,13 +245,13 @@ __device__ __forceinline__ void advantages_epilogue(uint32_t src, const uint8_t 
 #ifdef PP_TC_NOLDS
             const float4 w = make_float4(0.25f + j, 0.5f - j, 0.125f * half, 1.0f);   // experiment (wrong results): no table reads
 #else
-            const float4 w = dt[half * 16 + j];
+            const float4 w = HEADS_IN_CONST ? c_head_diff[cslot][player][half * 16 + j] : dt[half * 16 + j];
 #endif
             d01[j & 3] = __ffma2_rn(make_float2(w.x, w.y), h, d01[j & 3]);
             d12[j & 3] = __ffma2_rn(make_float2(w.z, w.w), h, d12[j & 3]);
         }
     }
-    const float4 bias = dt[32];
+    const float4 bias = HEADS_IN_CONST ? c_head_diff[cslot][player][32] : dt[32];
     const float2 s01 = __fadd2_rn(__fadd2_rn(d01[0], d01[1]), __fadd2_rn(d01[2], d01[3]));
     const float2 s12 = __fadd2_rn(__fadd2_rn(d12[0], d12[1]), __fadd2_rn(d12[2], d12[3]));
     const float a01 = __fadd_rn(__fadd_rn(s01.x, s01.y), bias.x), a12 = __fadd_rn(__fadd_rn(s12.x, s12.y), bias.y);
@@ -239,9 +262,13 @@ __device__ __forceinline__ void advantages_epilogue(uint32_t src, const uint8_t 
     adv[1] = pick == 1 ? 1.0f : 0.0f;
     adv[2] = pick == 2 ? 1.0f : 0.0f;
 }
-template <bool FULL_Q> __device__ __forceinline__ void heads(uint32_t src, const uint8_t *table, float (&q)[3]) {
-    if (FULL_Q) heads_epilogue(src, table, q);
-    else advantages_epilogue(src, table, q);
+// HEADS: which head evaluation a kernel uses
+constexpr int HEADS_FULL_Q = 0,        // the dueling Q values themselves (standalone action kernel, which can return them)
+              HEADS_DIFF_SMEM = 1,     // action from the two advantage differences, table in shared memory
+              HEADS_DIFF_CONST = 2;    // ... table in constant memory, slot `cslot`
+template <int HEADS> __device__ __forceinline__ void heads(uint32_t src, const uint8_t *table, int cslot, int player, float (&q)[3]) {
+    if (HEADS == HEADS_FULL_Q) heads_epilogue(src, table, q);
+    else advantages_epilogue<HEADS == HEADS_DIFF_CONST>(src, table, cslot, player, q);
 }
 
 // MMA batches, issued by one thread per group.  d / a_tm are TMEM addresses with lane 0.
@@ -323,7 +350,7 @@ struct GroupCtx {
     PlayerTiles pa, pb;
     uint64_t *bar;                               // two completion barriers, used alternately: bar[0] = L1 batches, bar[1] = L2
     uint32_t parity[2], r0, bar_id, lane_addr;   // r0: the group's first TMEM column (lane 0); R1 = r0 + TM_R1
-    int row;
+    int row, cslot;                              // cslot: this launch's table in c_head_diff (HEADS_DIFF_CONST)
     bool qa, qb, issuer_warp;
 };
 
@@ -346,8 +373,8 @@ template <int W, typename F> __device__ __forceinline__ void group_issue(GroupCt
 }
 
 // ONE QNet player p: L1 -> R0; H in place; L2 -> R1; (ReLU, fp32 heads on the CUDA cores) -> Q
-template <bool FULL_Q>
-__device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles &p, float (&q)[3]) {
+template <int HEADS>
+__device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles &p, int player, float (&q)[3]) {
     group_issue<0>(g, [&] { issue_l1(g.r0, p); });
     group_wait<0>(g);
     hidden_epilogue_inplace(g.r0 + g.lane_addr);
@@ -355,7 +382,7 @@ __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles
     tc::bar_sync(g.bar_id, G_ROWS);
     group_issue<1>(g, [&] { issue_l2(g.r0 + TM_R1, g.r0, p); });
     group_wait<1>(g);
-    heads<FULL_Q>(g.r0 + TM_R1 + g.lane_addr, p.w + W3H_OFF, q);
+    heads<HEADS>(g.r0 + TM_R1 + g.lane_addr, p.w + W3H_OFF, g.cslot, player, q);
 }
 
 // BOTH players (the self-play hot path), two 64-column TMEM regions R0, R1 per group:
@@ -366,7 +393,7 @@ __device__ __forceinline__ void group_forward_one(GroupCtx &g, const PlayerTiles
 // regions had four and four).  [A variant that also freed R1 early by sending H_B through a SHARED-MEMORY A tile, so
 // that L2_B could follow L2_A without a drain, was 7 % SLOWER: 12 SS-mode MMAs read 48 KB of A operand per group-step
 // from shared memory and the 32 KB of epilogue stores compete with the head table's LDS traffic.]
-template <bool FULL_Q>
+template <int HEADS>
 __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
     group_issue<0>(g, [&] { issue_l1(g.r0, g.pa); });
     PP_TICK(1);
@@ -383,7 +410,7 @@ __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3],
     PP_TICK(6);
     group_issue<0>(g, [&] { issue_l1(g.r0, g.pb); });     // no group barrier since the last commit: the OTHER completion barrier
     PP_TICK(1);
-    heads<FULL_Q>(g.r0 + TM_R1 + g.lane_addr, g.pa.w + W3H_OFF, q_a);
+    heads<HEADS>(g.r0 + TM_R1 + g.lane_addr, g.pa.w + W3H_OFF, g.cslot, 0, q_a);
     PP_TICK(7);
     group_wait<0>(g);
     PP_TICK(2);
@@ -396,22 +423,20 @@ __device__ __forceinline__ void group_forward_both(GroupCtx &g, float (&q_a)[3],
     PP_TICK(5);
     group_wait<1>(g);
     PP_TICK(6);
-    heads<FULL_Q>(g.r0 + TM_R1 + g.lane_addr, g.pb.w + W3H_OFF, q_b);
+    heads<HEADS>(g.r0 + TM_R1 + g.lane_addr, g.pb.w + W3H_OFF, g.cslot, 1, q_b);
     PP_TICK(7);
 }
 
-// FULL_Q: the dueling Q values themselves (standalone action kernel, which can return them); otherwise only numbers
-// with the same argmax (advantages_epilogue)
-template <bool FULL_Q>
+template <int HEADS>
 __device__ __forceinline__ void group_forward(GroupCtx &g, float (&q_a)[3], float (&q_b)[3]) {
-    if (g.qa && g.qb) group_forward_both<FULL_Q>(g, q_a, q_b);
+    if (g.qa && g.qb) group_forward_both<HEADS>(g, q_a, q_b);
     else {
-        if (g.qa) group_forward_one<FULL_Q>(g, g.pa, q_a);
+        if (g.qa) group_forward_one<HEADS>(g, g.pa, 0, q_a);
         if (g.qa && g.qb) {                    // R0 / R1 still hold the first player's operands until everyone has read them
             tc::tc_fence_before();
             tc::bar_sync(g.bar_id, G_ROWS);
         }
-        if (g.qb) group_forward_one<FULL_Q>(g, g.pb, q_b);
+        if (g.qb) group_forward_one<HEADS>(g, g.pb, 1, q_b);
     }
 }
 
@@ -460,7 +485,7 @@ qnet_act_tc_kernel(int64_t n, const float *__restrict__ obs, const PPPolicy pol,
         tc::tc_fence_before();
         tc::bar_sync(g.bar_id, G_ROWS);
         float q[3], unused[3];
-        group_forward<true>(g, q, unused);
+        group_forward<HEADS_FULL_Q>(g, q, unused);
         if (i < n) {
             int a = argmax3(q);
             a = explore(a, pol.eps_threshold, seed, (uint32_t)(env_id_base + i), step_index, stream_id);
@@ -488,11 +513,11 @@ struct FusedMap {
 static_assert(FusedMap::TOTAL <= 232448, "shared memory of the fused tensor-core kernel exceeds 227 KB");
 static_assert(2 * BLOB_BYTES <= CTA_GROUPS * GROUP_BYTES + TC_FUSED_THREADS * 24, "weight staging aliases the X rows and serve slots");
 
-template <typename R, bool PRECLAIM>
+template <typename R, bool PRECLAIM, bool CHEADS>
 __global__ void __launch_bounds__(TC_FUSED_THREADS, 1)
 selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_t k_steps, const PPPolicy pol_a,
                    const PPPolicy pol_b, uint64_t seed, int64_t step_base, const PPServeSource src, int32_t quota,
-                   int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks) {
+                   int64_t env_id_base, const PPRolloutOut out, const PPReplayRing ring, int64_t n_chunks, int cslot) {
     extern __shared__ __align__(128) uint8_t smem[];
     using M = FusedMap;
     const uint32_t tmem = __shfl_sync(0xffffffffu, tc_prologue<CTA_GROUPS, M>(smem, pol_a, pol_b), 0);
@@ -500,6 +525,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
     const int grp = warp_id >> 2, gw = warp_id & 3, row = threadIdx.x & 127, lane = threadIdx.x & 31;
     const bool qa = pol_a.kind == PP_POLICY_QNET, qb = pol_b.kind == PP_POLICY_QNET;
     GroupCtx g = make_group(smem, M::GROUPS_OFF, M::CTRL, tmem, grp, row, qa, qb);
+    g.cslot = cslot;
     double *serve_slot = reinterpret_cast<double *>(smem + M::SERVE_OFF) + threadIdx.x * 3;
     float *row_stage = reinterpret_cast<float *>(smem + M::STAGE_OFF) + warp_id * 224;
     const EnvConsts<R> c(params);
@@ -566,7 +592,7 @@ selfplay_tc_kernel(const PPParams params, const PPEnvState st, int64_t n, int64_
             if (!tc::bar_red_or(g.bar_id, G_ROWS, active)) break;             // whole group frozen by the quota: for good
             PP_TICK(10);
             float q_a[3] = {0.f, 0.f, 0.f}, q_b[3] = {0.f, 0.f, 0.f};
-            if (qa || qb) group_forward<false>(g, q_a, q_b);
+            if (qa || qb) group_forward<CHEADS ? HEADS_DIFF_CONST : HEADS_DIFF_SMEM>(g, q_a, q_b);
             int act_a, act_b;
             if (pol_a.kind == PP_POLICY_RANDOM) act_a = random_action(seed, gid, step, STREAM_ACT_A);
             else act_a = explore(qa ? argmax3(q_a) : follower_action(oa, pol_a.follower_tol), pol_a.eps_threshold, seed, gid, step, STREAM_ACT_A);
@@ -631,6 +657,36 @@ int qnet_act_tc_launch(int64_t n, const float *obs, const PPPolicy &pol, uint64_
     return (int)cudaGetLastError();
 }
 
+// this device's copy of g_head_diff_staging, resolved once per device (no runtime query inside a stream capture later)
+static float4 *head_staging_of_current_device() {
+    static std::mutex mu;
+    static float4 *by_device[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!by_device[dev] && cudaGetSymbolAddress(reinterpret_cast<void **>(&by_device[dev]), g_head_diff_staging) != cudaSuccess)
+        by_device[dev] = nullptr;
+    return by_device[dev];
+}
+
+// slot of c_head_diff for launches on `stream` of the current device; -1 when all slots are taken by other streams or
+// PP_CONST_HEADS=0 asks for the shared-memory table
+static int head_slot_for(cudaStream_t stream) {
+    static std::mutex mu;
+    static struct { int device; cudaStream_t stream; } owner[HEAD_SLOTS];
+    static int used = 0;
+    static const bool off = [] { const char *e = getenv("PP_CONST_HEADS"); return e && e[0] == '0'; }();
+    if (off) return -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < used; ++i)
+        if (owner[i].device == dev && owner[i].stream == stream) return i;
+    if (used == HEAD_SLOTS) return -1;
+    owner[used] = {dev, stream};
+    return used++;
+}
+
 int selfplay_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const PPEnvState &st, const PPPolicy &pa,
                        const PPPolicy &pb, uint64_t seed, int64_t step_base, const PPServeSource &src, int32_t quota,
                        int64_t env_id_base, const PPRolloutOut &out, const PPReplayRing *ring, cudaStream_t stream) {
@@ -647,15 +703,32 @@ int selfplay_tc_launch(int mode, int64_t n, int64_t k, const PPParams &p, const 
     }
     const unsigned blocks = (unsigned)(n_chunks < slots ? n_chunks : slots);
     const bool preclaim = src.kind == PP_SERVE_QUEUE && src.pool_vx == nullptr;   // a Philox-drawn serve queue (host-buffer evaluation)
+    // the head tables of this launch: built on the device, copied into this (device, stream)'s slot of constant memory
+    const bool qa = pa.kind == PP_POLICY_QNET, qb = pb.kind == PP_POLICY_QNET;
+    int cslot = (qa || qb) ? head_slot_for(stream) : -1;
+    if (cslot >= 0) {
+        cudaError_t err;
+        float4 *mine = head_staging_of_current_device();                         // nullptr: could not be resolved
+        if (!mine) return (int)cudaErrorInvalidSymbol;
+        head_diff_kernel<<<1, 128, 0, stream>>>(qa ? pa.weights : nullptr, qb ? pb.weights : nullptr, cslot);
+        constexpr size_t bytes = 2 * HEAD_ENTRIES * sizeof(float4);
+        err = cudaMemcpyToSymbolAsync(c_head_diff, mine + (size_t)cslot * 2 * HEAD_ENTRIES, bytes, (size_t)cslot * bytes,
+                                      cudaMemcpyDeviceToDevice, stream);
+        if (err != cudaSuccess) return (int)err;
+    }
     auto launch = [&](auto kernel) -> int {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err != cudaSuccess) return (int)err;
         kernel<<<blocks, TC_FUSED_THREADS, smem, stream>>>(p, st, n, k, pa, pb, seed, step_base, src, quota, env_id_base, out, r,
-                                                        n_chunks);
+                                                        n_chunks, cslot);
         return (int)cudaGetLastError();
     };
-    if (mode == PP_MODE_F64) return preclaim ? launch(selfplay_tc_kernel<double, true>) : launch(selfplay_tc_kernel<double, false>);
-    return preclaim ? launch(selfplay_tc_kernel<float, true>) : launch(selfplay_tc_kernel<float, false>);
+    if (mode == PP_MODE_F64) {
+        if (cslot >= 0) return preclaim ? launch(selfplay_tc_kernel<double, true, true>) : launch(selfplay_tc_kernel<double, false, true>);
+        return preclaim ? launch(selfplay_tc_kernel<double, true, false>) : launch(selfplay_tc_kernel<double, false, false>);
+    }
+    if (cslot >= 0) return preclaim ? launch(selfplay_tc_kernel<float, true, true>) : launch(selfplay_tc_kernel<float, false, true>);
+    return preclaim ? launch(selfplay_tc_kernel<float, true, false>) : launch(selfplay_tc_kernel<float, false, false>);
 }
 
 }  // namespace pp

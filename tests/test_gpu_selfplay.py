@@ -381,6 +381,39 @@ def test_selfplay_tensor_core_env_bit_exact_under_its_own_actions(H, nets, mode,
     assert agree >= 0.999                                       # measured 99.94 - 100 %
 
 
+def test_tensor_core_rollout_head_tables_are_per_stream(H, nets):
+    """The fused tensor-core rollout reads its head table from constant memory, one slot per (device, stream); streams
+    beyond the 16 slots use the shared-memory table.  Twenty streams, alternating between two different player pairings,
+    all in flight at once: every stream's actions and counters equal the same rollout run alone on the default stream
+    (a shared table would make one pairing play with the other's heads)."""
+    cfg = H["env_config_yaml"]
+    n, K, depth = 2048, 96, 6
+    pool = gu.make_pool(5, n, depth, cfg, "f64")
+    pairs = [("seed0", "ckpt_model5_1_fault_B"), ("ckpt_model5_1_fault_B", "seed1")]
+
+    def engine(pair):
+        env = pp.VecPongEnv2P(n, mode="f64", serve=pool, env_id_base=7, **cfg)
+        env.reset()
+        return pp.SelfPlayEngine(env, pp.Policy.qnet(nets[pair[0]], precision="f16"), pp.Policy.qnet(nets[pair[1]], precision="f16"), seed=11)
+
+    want = []
+    for pair in pairs:
+        eng = engine(pair)
+        want.append((gu.np_of(eng.run(K, want_actions=True)["actions"]), gu.np_of(eng.env.counters)))
+    assert not np.array_equal(want[0][0], want[1][0])
+    engines = [engine(pairs[i % 2]) for i in range(20)]
+    streams = [torch.cuda.Stream() for _ in engines]
+    torch.cuda.synchronize()
+    outs = []
+    for eng, st in zip(engines, streams):
+        with torch.cuda.stream(st):
+            outs.append(eng.run(K, want_actions=True)["actions"])
+    torch.cuda.synchronize()
+    for i, (eng, out) in enumerate(zip(engines, outs)):
+        assert np.array_equal(gu.np_of(out), want[i % 2][0]), f"stream {i}"
+        assert np.array_equal(gu.np_of(eng.env.counters), want[i % 2][1]), f"stream {i}"
+
+
 def test_selfplay_tensor_core_mixed_players_and_win_rates(H, nets):
     """Follower / random opponents on the tensor-core path, and outcome statistics equal to the fp32 path's within
     sampling noise (same serves, greedy QNets)."""
