@@ -414,6 +414,33 @@ def test_tensor_core_rollout_head_tables_are_per_stream(H, nets):
         assert np.array_equal(gu.np_of(eng.env.counters), want[i % 2][1]), f"stream {i}"
 
 
+def test_tensor_core_rollout_can_be_captured_into_a_cuda_graph(H, nets):
+    """The launch sequence of the fused tensor-core rollout (table kernel, device-to-device copy into constant memory,
+    rollout kernel) is capturable: a replayed graph continues the rollout exactly like an eager launch (greedy players,
+    Philox serves keyed by env and episode, so the baked-in step index does not matter)."""
+    cfg = H["env_config_yaml"]
+    n, K = 4096, 48
+
+    def engine():
+        env = pp.VecPongEnv2P(n, mode="f64", serve="philox", seed=3, **cfg)
+        env.reset()
+        return pp.SelfPlayEngine(env, pp.Policy.qnet(nets["seed0"], precision="f16"), pp.Policy.qnet(nets["seed1"], precision="f16"), seed=5)
+
+    eager = engine()
+    eager.run(K); eager.run(K)
+    graphed = engine()
+    graphed.run(K)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        graphed.run(K)
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(gu.np_of(graphed.env.counters), gu.np_of(eager.env.counters))
+    (r1, i1), (r2, i2) = gu.read_state(graphed.env), gu.read_state(eager.env)
+    assert np.array_equal(gu.bits(r1), gu.bits(r2)) and np.array_equal(i1, i2)
+
+
 def test_selfplay_tensor_core_mixed_players_and_win_rates(H, nets):
     """Follower / random opponents on the tensor-core path, and outcome statistics equal to the fp32 path's within
     sampling noise (same serves, greedy QNets)."""
