@@ -355,7 +355,11 @@ def main():
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": f"{args.mode} env state + {args.precision} QNet", "data": "synthetic",
-        "config": workload_config(args, world), "clocks": clocks, "gpu_launches": args.steps,
+        "config": workload_config(args, world), "clocks": clocks,
+        # per timed step on every rank: the fused rollout kernel, plus for the tensor-core QNet path the one-block kernel
+        # that builds the head tables (its device-to-device copy into constant memory is a memcpy node, not counted)
+        "gpu_launches": args.steps * (2 if (args.workload == "qnet" and args.precision == "f16"
+                                            and os.environ.get("PP_CONST_HEADS", "1")[:1] != "0") else 1),
         "wall_s_timed_region_incl_flush": wall,
         "outcomes": {"episodes": int(total[1].item()), "wins_a": int(total[2].item()), "wins_b": int(total[3].item()),
                      "paddle_hits": int(total[6].item())},
