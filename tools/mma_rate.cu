@@ -77,6 +77,7 @@ int main() {
     run<128, false>("N128 SS"); run<128, true>("N128 TS");
     run<256, false>("N256 SS"); run<256, true>("N256 TS");
     run<128, true, true>("N128 TS + commit/8"); run<64, true, true>("N64 TS + commit/8");
+    run<128, false, false, 1, 288>("N128 SS + 8 warps tcgen05.ld");
     run<128, true, false, 1, 288>("N128 TS + 8 warps tcgen05.ld"); run<128, true, false, 2, 288>("N128 TS + 8 warps MUFU");
     run<64, true, false, 1, 512>("N64 TS + 15 warps tcgen05.ld"); run<64, true, false, 2, 512>("N64 TS + 15 warps MUFU");
     return 0;
