@@ -5,14 +5,15 @@
 #include "tc_ptx.cuh"
 using namespace pp;
 
-template <int N, bool TS, bool COMMIT_EACH, int NOISE = 0>      // NOISE: 1 = the other warps hammer TMEM loads, 2 = MUFU
+// STAGE > 0: like a weight-ring stage of STAGE MMAs: a try_wait on a barrier whose phase completed long ago, the MMAs, a commit
+template <int N, bool TS, bool COMMIT_EACH, int NOISE = 0, int STAGE = 0>      // NOISE: 1 = the other warps hammer TMEM loads, 2 = MUFU
 __global__ void rate_kernel(long long *out, int iters) {
     __shared__ volatile int stop;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar, bar2;
+    __shared__ uint64_t bar, bar2, bar3;
     __shared__ uint32_t slot;
     for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
-    if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::mbar_init(&bar2, 1); tc::fence_mbar_init(); }
+    if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::mbar_init(&bar2, 1); tc::mbar_init(&bar3, 1); tc::fence_mbar_init(); }
     if (threadIdx.x < 32) tc::tmem_alloc<512>(&slot);
     tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
     tc::fence_proxy_async();
@@ -41,6 +42,16 @@ __global__ void rate_kernel(long long *out, int iters) {
         const uint32_t idesc = tc::idesc_f16(128, N);
         long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
+            if (STAGE > 0) {
+#pragma unroll
+                for (int st = 0; st < 8 / STAGE; ++st) {
+                    tc::mbar_wait(&bar3, 1);               // the phase before the first: complete since initialisation
+#pragma unroll
+                    for (int j = 0; j < STAGE; ++j) tc::umma_f16_ts(tm + 256, tm + (st * STAGE + j) * 8, bd, idesc, true);
+                    tc::umma_commit(&bar2);
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if (TS) tc::umma_f16_ts(tm + 256, tm + j * 8, bd, idesc, true);
@@ -59,12 +70,12 @@ __global__ void rate_kernel(long long *out, int iters) {
     if (threadIdx.x < 32) tc::tmem_dealloc<512>(tm);
 }
 
-template <int N, bool TS, bool CE = false, int NOISE = 0, int THREADS = 128> void run(const char *name) {
+template <int N, bool TS, bool CE = false, int NOISE = 0, int THREADS = 128, int STAGE = 0> void run(const char *name) {
     long long *d, h[2];
     cudaMalloc(&d, 16);
-    cudaFuncSetAttribute(rate_kernel<N, TS, CE, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(rate_kernel<N, TS, CE, NOISE, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const int iters = 200;
-    rate_kernel<N, TS, CE, NOISE><<<1, THREADS, 64 * 1024>>>(d, iters);
+    rate_kernel<N, TS, CE, NOISE, STAGE><<<1, THREADS, 64 * 1024>>>(d, iters);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
     printf("%-10s issue %.1f cyc/MMA, complete %.1f cyc/MMA (%s)\n", name, (double)h[0] / (iters * 8), (double)h[1] / (iters * 8), cudaGetErrorString(e));
@@ -77,6 +88,10 @@ int main() {
     run<128, false>("N128 SS"); run<128, true>("N128 TS");
     run<256, false>("N256 SS"); run<256, true>("N256 TS");
     run<128, true, true>("N128 TS + commit/8"); run<64, true, true>("N64 TS + commit/8");
+    run<128, true, false, 0, 128, 8>("N128 TS, stages of 8 (try_wait + 8 MMAs + commit)");
+    run<128, true, false, 0, 128, 4>("N128 TS, stages of 4");
+    run<128, true, false, 1, 288, 4>("N128 TS, stages of 4 + 8 warps tcgen05.ld");
+    run<128, true, false, 2, 288, 4>("N128 TS, stages of 4 + 8 warps MUFU");
     run<128, false, false, 1, 288>("N128 SS + 8 warps tcgen05.ld");
     run<128, true, false, 1, 288>("N128 TS + 8 warps tcgen05.ld"); run<128, true, false, 2, 288>("N128 TS + 8 warps MUFU");
     run<64, true, false, 1, 512>("N64 TS + 15 warps tcgen05.ld"); run<64, true, false, 2, 512>("N64 TS + 15 warps MUFU");
