@@ -46,7 +46,11 @@ namespace {
 // RT_HALVES threads share one env row (same TMEM lane, different columns): more warps per scheduler for the epilogues
 constexpr int RT_ROWS = 128, RT_HALVES = 2, RT_WORKERS = RT_ROWS * RT_HALVES, RT_THREADS = RT_WORKERS + 64,
               RT_ISSUER_WARP = RT_WORKERS / 32, RT_PRODUCER_WARP = RT_ISSUER_WARP + 1;
-constexpr uint32_t RT_SLOTS = 4, RT_SLOT = PP_RNNTC_SLOT_BYTES;
+// The image's 40 tiles are fetched as 21 STAGES of up to two weight tiles (36 KB): every stage hand-off (a try_wait, a commit)
+// idles the tensor pipe for ~85 cycles, so fewer, larger stages (tools/mma_rate.cu: 74 cycles per MMA in stages of 8, 88 in
+// stages of 4, 64 back to back).
+constexpr uint32_t RT_SLOTS = 4, RT_SLOT = 2 * PP_RNNTC_TILE + PP_RNNTC_BIAS;
+constexpr int RT_STAGES = 21;
 constexpr uint32_t SM_RING = 0, SM_HNEW = SM_RING + RT_SLOTS * RT_SLOT, SM_HNEW_LO = SM_HNEW + 32768,
                    SM_X = SM_HNEW + 65536, SM_CTRL = SM_X + 4096, SM_FLAGS = SM_CTRL + 128, SM_TOTAL = SM_FLAGS + 2 * RT_ROWS;
 // control block: full[] empty[] ready done[2] dfree[2] step (mbarriers), TMEM base, stop flag; then per-row flags
@@ -57,19 +61,20 @@ static_assert(CTRL_STOP + 4 <= 128, "control block");
 constexpr uint32_t T_AHI = 0, T_ALO = 128, T_D0 = 256, T_D1 = 384, T_FHI = 384, T_FLO = 416;
 
 __device__ __forceinline__ void stage_info(int i, uint32_t &off, uint32_t &bytes) {
-    if (i == 0) { off = PP_RNNTC_S0; bytes = PP_RNNTC_S0_BYTES; }
-    else if (i == 1) { off = PP_RNNTC_S1; bytes = PP_RNNTC_S1_BYTES; }
-    else if (i == 2) { off = PP_RNNTC_S2; bytes = PP_RNNTC_S2_BYTES; }
-    else if (i < 35) {                            // per quarter: hi c = 0..3 (the first carries the bias tile), lo c = 0..3
-        const int q = (i - 3) >> 3, c = (i - 3) & 7;
-        off = PP_RNNTC_G + q * PP_RNNTC_GQ_BYTES + (c == 0 ? 0 : PP_RNNTC_TILE + PP_RNNTC_BIAS + (c - 1) * PP_RNNTC_TILE);
-        bytes = c == 0 ? PP_RNNTC_TILE + PP_RNNTC_BIAS : PP_RNNTC_TILE;
-    } else if (i < 39) {
-        const int c = i - 35;
-        off = PP_RNNTC_WS + (c == 0 ? 0 : PP_RNNTC_TILE + PP_RNNTC_BIAS + (c - 1) * PP_RNNTC_TILE);
-        bytes = c == 0 ? PP_RNNTC_TILE + PP_RNNTC_BIAS : PP_RNNTC_TILE;
+    constexpr uint32_t PAIR_B = 2 * PP_RNNTC_TILE + PP_RNNTC_BIAS, PAIR_T = 2 * PP_RNNTC_TILE;   // tile + bias + tile / two tiles
+    if (i == 0) { off = PP_RNNTC_S0; bytes = PP_RNNTC_S0_BYTES; }                      // L1
+    else if (i == 1) { off = PP_RNNTC_S1; bytes = PP_RNNTC_S1_BYTES + PP_RNNTC_S2_BYTES; }   // features.2: hi tile + bias, lo tile
+    else if (i < 18) {                            // per quarter: hi (c 0, 1 with the bias tile between), hi (c 2, 3), lo (0, 1), lo (2, 3)
+        const int q = (i - 2) >> 2, j = (i - 2) & 3;
+        off = PP_RNNTC_G + q * PP_RNNTC_GQ_BYTES + (j == 0 ? 0 : PAIR_B + (j - 1) * PAIR_T);
+        bytes = j == 0 ? PAIR_B : PAIR_T;
+    } else if (i < 20) {                          // shared head: hi (c 0 + bias, c 1), lo (c 0, 1)
+        off = PP_RNNTC_WS + (i == 18 ? 0 : PAIR_B);
+        bytes = i == 18 ? PAIR_B : PAIR_T;
     } else { off = PP_RNNTC_HD; bytes = PP_RNNTC_HD_BYTES; }
 }
+static_assert(PP_RNNTC_S1 + PP_RNNTC_S1_BYTES == PP_RNNTC_S2 && PP_RNNTC_S1_BYTES == PP_RNNTC_TILE + PP_RNNTC_BIAS, "image layout");
+static_assert(PP_RNNTC_GQ_BYTES == 8 * PP_RNNTC_TILE + PP_RNNTC_BIAS && PP_RNNTC_WS_BYTES == 4 * PP_RNNTC_TILE + PP_RNNTC_BIAS, "image layout");
 
 // ------------------------------------------------------------------------------------------ issuer side
 struct Issuer {
@@ -117,7 +122,7 @@ struct Producer {
                                    // the cluster (each SM then pulls half the image from L2 per player-step)
     __device__ __forceinline__ void player_step(const uint8_t *img) {
 #pragma unroll 1
-        for (int st = 0; st < PP_RNNTC_STAGES; ++st) {
+        for (int st = 0; st < RT_STAGES; ++st) {
             tc::mbar_wait(bars + B_EMPTY + slot, (uint32_t)(round ^ 1));       // first round passes at once
             uint32_t off, bytes;
             stage_info(st, off, bytes);
@@ -181,9 +186,7 @@ __device__ __forceinline__ void issue_player_step(Issuer &is) {
     mma_ts_run<128, 4>(ld, tm + T_D0, tm + T_FHI, bdesc<128>(a), false);
     mma_ts_run<128, 4>(ld, tm + T_D0, tm + T_FLO, bdesc<128>(a), true);
     mma_ss_run<128, 1>(ld, tm + T_D0, x, bdesc<128>(a + PP_RNNTC_TILE), true);
-    is.release();
-    a = is.acquire();
-    mma_ts_run<128, 4>(ld, tm + T_D0, tm + T_FHI, bdesc<128>(a), true);
+    mma_ts_run<128, 4>(ld, tm + T_D0, tm + T_FHI, bdesc<128>(a + PP_RNNTC_TILE + PP_RNNTC_BIAS), true);
     is.release();
     is.done(0);
     // ---- gates, four quarters of 32 units, K = 256 in four stages of 64 (hi weights), then four more (lo weights)
@@ -193,37 +196,39 @@ __device__ __forceinline__ void issue_player_step(Issuer &is) {
         if (q >= 2) is.wait_dfree(q & 1);
         const uint32_t d = tm + ((q & 1) ? T_D1 : T_D0);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; c += 2) {                // two K chunks of 64 per stage
             a = is.acquire();
-            const uint64_t bd = bdesc<128>(a);
-            mma_ts_run<128, 4>(ld, d, tm + T_AHI + c * 32, bd, c != 0);
-            mma_ts_run<128, 4>(ld, d, tm + T_ALO + c * 32, bd, true);
+            const uint64_t bd0 = bdesc<128>(a), bd1 = bdesc<128>(a + PP_RNNTC_TILE + (c == 0 ? PP_RNNTC_BIAS : 0));
+            mma_ts_run<128, 4>(ld, d, tm + T_AHI + c * 32, bd0, c != 0);
+            mma_ts_run<128, 4>(ld, d, tm + T_ALO + c * 32, bd0, true);
             if (c == 0) mma_ss_run<128, 1>(ld, d, x, bdesc<128>(a + PP_RNNTC_TILE), true);
+            mma_ts_run<128, 4>(ld, d, tm + T_AHI + (c + 1) * 32, bd1, true);
+            mma_ts_run<128, 4>(ld, d, tm + T_ALO + (c + 1) * 32, bd1, true);
             is.release();
         }
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {                   // A_hi * W_lo
+        for (int c = 0; c < 4; c += 2) {                // A_hi * W_lo
             a = is.acquire();
             mma_ts_run<128, 4>(ld, d, tm + T_AHI + c * 32, bdesc<128>(a), true);
+            mma_ts_run<128, 4>(ld, d, tm + T_AHI + (c + 1) * 32, bdesc<128>(a + PP_RNNTC_TILE), true);
             is.release();
         }
         is.done(q & 1);
     }
     // ---- shared head: D0[0..127] = Hh*Wsh + Hl*Wsh + X*B + Hh*Wsl   (A = h_new tile in shared memory, K = 128)
     is.wait_ready();
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
         a = is.acquire();
-        const uint64_t bd = bdesc<128>(a);
-        mma_ss_run<128, 4>(ld, tm + T_D0, hh + c * 4 * A_KSTEP, bd, c != 0);
-        mma_ss_run<128, 4>(ld, tm + T_D0, hl + c * 4 * A_KSTEP, bd, true);
-        if (c == 0) mma_ss_run<128, 1>(ld, tm + T_D0, x, bdesc<128>(a + PP_RNNTC_TILE), true);
+        const uint64_t bd0 = bdesc<128>(a), bd1 = bdesc<128>(a + PP_RNNTC_TILE + PP_RNNTC_BIAS);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hh, bd0, false);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hl, bd0, true);
+        mma_ss_run<128, 1>(ld, tm + T_D0, x, bdesc<128>(a + PP_RNNTC_TILE), true);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hh + 4 * A_KSTEP, bd1, true);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hl + 4 * A_KSTEP, bd1, true);
         is.release();
-    }
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
         a = is.acquire();
-        mma_ss_run<128, 4>(ld, tm + T_D0, hh + c * 4 * A_KSTEP, bdesc<128>(a), true);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hh, bdesc<128>(a), true);
+        mma_ss_run<128, 4>(ld, tm + T_D0, hh + 4 * A_KSTEP, bdesc<128>(a + PP_RNNTC_TILE), true);
         is.release();
     }
     is.done(0);
